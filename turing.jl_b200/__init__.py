@@ -1,0 +1,20 @@
+"""turing.jl_b200 -- host side of the B200-native many-chain HMC/NUTS engine.
+
+Holds only what the hot path needs: `csrc/` (CUDA kernels + the C ABI of include/tnuts.h)
+and a Python mirror of the reference's sampler interface for that path
+(`sample(model, NUTS(delta), MCMCThreads(), N, n_chains)`).  The directory name contains a
+dot, so import it through the repo-root shim:  `import turing_jl_b200`.
+"""
+from . import _lib, build, models  # noqa: F401
+from .chains import Chains, chainscat  # noqa: F401
+from .engine import Engine  # noqa: F401
+from .inference import LogDensityFunction, loadstate, post_sample_hook, sample  # noqa: F401
+from .models import (EightSchools, GDemo, HierLinearRegression, LinearRegression,  # noqa: F401
+                     LogisticRegression, StdNormal, gdemo_default)
+from .samplers import (HMC, HMCDA, NUTS, InitFromParams, InitFromUniform, MCMCDistributed,  # noqa: F401
+                       MCMCSerial, MCMCThreads)
+
+__all__ = ["sample", "NUTS", "HMC", "HMCDA", "MCMCThreads", "MCMCSerial", "MCMCDistributed",
+           "Chains", "chainscat", "loadstate", "LogDensityFunction", "Engine", "InitFromParams",
+           "InitFromUniform", "GDemo", "gdemo_default", "LinearRegression", "EightSchools",
+           "LogisticRegression", "HierLinearRegression", "StdNormal", "models"]

@@ -1,0 +1,93 @@
+// chain_kernels.cu -- launchers of the one-thread-per-chain strategy (chain_kernels.cuh).
+#include "chain_kernels.cuh"
+#include "engine.cuh"
+
+namespace tnuts {
+
+// family / dimension dispatch: every instantiation is a separate fully-unrolled kernel
+#define TN_DISPATCH_SMALL(e, CALL)                                                     \
+  do {                                                                                 \
+    const int _f = (e)->model.family, _D = (e)->D;                                     \
+    if (_f == TNUTS_GDEMO && _D == 2) { CALL(GDemo); }                                 \
+    else if (_f == TNUTS_LINREG && _D == 3) { CALL(LinReg); }                          \
+    else if (_f == TNUTS_EIGHT_SCHOOLS && _D == 10) { CALL(EightSchools<8>); }         \
+    else if (_f == TNUTS_STD_NORMAL && _D == 1) { CALL(StdNormal<1>); }                \
+    else if (_f == TNUTS_STD_NORMAL && _D == 2) { CALL(StdNormal<2>); }                \
+    else if (_f == TNUTS_STD_NORMAL && _D == 4) { CALL(StdNormal<4>); }                \
+    else if (_f == TNUTS_STD_NORMAL && _D == 10) { CALL(StdNormal<10>); }              \
+    else return set_error((e), TNUTS_E_UNSUPPORTED, "no thread-per-chain kernel for this family/D"); \
+  } while (0)
+
+bool thread_strategy_supported(const Engine *e) {
+  const int f = e->model.family, D = e->D;
+  const long long N = e->model.N;
+  if (e->cfg.max_depth > kMaxCk + 1) return false;
+  if (f == TNUTS_GDEMO) return D == 2 && N <= 16;
+  if (f == TNUTS_LINREG) return D == 3 && N <= 16;
+  if (f == TNUTS_EIGHT_SCHOOLS) return D == 10 && N == 8;
+  if (f == TNUTS_STD_NORMAL) return D == 1 || D == 2 || D == 4 || D == 10;
+  return false;
+}
+
+static inline int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
+
+int thread_init(Engine *e, const double *theta0_dev) {
+#define CALL(M)                                                                          \
+  k_chain_init<M><<<grid_for(e->st.C, kChainBlock), kChainBlock, 0, e->stream>>>(        \
+      e->small, e->st, e->rp, theta0_dev, e->cfg.init_eps)
+  TN_DISPATCH_SMALL(e, CALL);
+#undef CALL
+  e->launches += 1;
+  TN_CUDA(e, cudaGetLastError());
+  return TNUTS_OK;
+}
+
+int thread_run(Engine *e) {
+#define CALL(M)                                                                         \
+  k_chain_run<M><<<grid_for(e->st.C, kChainBlock), kChainBlock, 0, e->stream>>>(        \
+      e->small, e->st, e->out, e->rp)
+  TN_DISPATCH_SMALL(e, CALL);
+#undef CALL
+  e->launches += 1;
+  TN_CUDA(e, cudaGetLastError());
+  return TNUTS_OK;
+}
+
+int thread_point_lpgrad(Engine *e, const double *theta_dev, long long n, double *lp_dev,
+                        double *grad_dev) {
+#define CALL(M) \
+  k_point_lpgrad<M><<<grid_for(n, 128), 128, 0, e->stream>>>(e->small, theta_dev, n, lp_dev, grad_dev)
+  TN_DISPATCH_SMALL(e, CALL);
+#undef CALL
+  e->launches += 1;
+  TN_CUDA(e, cudaGetLastError());
+  return TNUTS_OK;
+}
+
+int thread_point_constrain(Engine *e, const double *theta_dev, long long n, double *params_dev,
+                           double *logp_dev) {
+#define CALL(M)                                                                              \
+  k_point_constrain<M><<<grid_for(n, 128), 128, 0, e->stream>>>(e->small, theta_dev, n,      \
+                                                                params_dev, logp_dev)
+  TN_DISPATCH_SMALL(e, CALL);
+#undef CALL
+  e->launches += 1;
+  TN_CUDA(e, cudaGetLastError());
+  return TNUTS_OK;
+}
+
+int thread_point_leapfrog(Engine *e, const double *theta_dev, const double *r_dev,
+                          const double *minv_dev, double eps, int L, long long n, double *tt_dev,
+                          double *tr_dev, double *tH_dev) {
+#define CALL(M)                                                                               \
+  k_point_leapfrog<M><<<grid_for(n, 128), 128, 0, e->stream>>>(e->small, theta_dev, r_dev,    \
+                                                               minv_dev, eps, L, n, tt_dev,   \
+                                                               tr_dev, tH_dev)
+  TN_DISPATCH_SMALL(e, CALL);
+#undef CALL
+  e->launches += 1;
+  TN_CUDA(e, cudaGetLastError());
+  return TNUTS_OK;
+}
+
+}  // namespace tnuts

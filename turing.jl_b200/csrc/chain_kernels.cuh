@@ -1,0 +1,621 @@
+// chain_kernels.cuh -- "one thread per chain" execution strategy (tiny-D families).
+//
+// A whole NUTS transition -- momentum refresh, tree doubling, leapfrogs, gradient,
+// multinomial sampling, generalised U-turn, divergence check, dual averaging, Welford
+// mass-matrix update, constrained output -- runs inside ONE thread with the position,
+// momentum and gradient in registers; a single launch advances every chain by many
+// transitions.  Chains are laid out chain-fastest ([D][C]) so every state load/store and
+// every output row is a coalesced 256-byte warp transaction.
+//
+// Replaces, per chain (paths into Turing.jl v0.46.1; [dep] = AdvancedHMC 0.8.3 restated in
+// SURVEY.md App. A):
+//   AbstractMCMC.step(rng, model, spl, state)       src/mcmc/hmc.jl:210-252
+//   AHMC.transition(rng, h, kernel, z)        [dep] call site src/mcmc/hmc.jl:225
+//   AHMC.adapt!(h, kernel, adaptor, i, n, th, a) [dep] call site src/mcmc/hmc.jl:229-241
+//   DynamicPPL.ParamsWithStats(theta, ldf, stat)    src/mcmc/hmc.jl:247
+//   AbstractMCMC.step(rng, model, spl; ...)  (init) src/mcmc/hmc.jl:156-208
+//   find_initial_params_ldf                         src/mcmc/abstractmcmc.jl:42-70
+//   AHMC.find_good_stepsize                   [dep] call site src/mcmc/hmc.jl:190
+//
+// The tree is built iteratively (no recursion, no per-level candidate copies):
+//   * sub-tree U-turn checks use per-level checkpoints of (r, cumulative rho): leaf n stores
+//     at level popc(n>>1) when even and checks its ctz(~n) enclosing aligned sub-trees when
+//     odd -- exactly the set of combine() checks of the recursive build_tree;
+//   * the candidate inside a doubling is chosen by streaming (reservoir) multinomial
+//     sampling -- leaf n replaces the candidate w.p. w_n / sum_{k<=n} w_k -- which has the
+//     same law as AdvancedHMC's per-merge uniform progressive sampling;
+//   * the top-level step is AdvancedHMC's biased progressive sampling, min(1, exp(lw'-lw)).
+#pragma once
+#include "common.cuh"
+#include "models.cuh"
+#include "philox.cuh"
+
+namespace tnuts {
+
+constexpr int kChainBlock = 128;
+constexpr int kMaxCk = 12;  // checkpoint levels: max_depth <= kMaxCk + 1 for this strategy
+
+__device__ __forceinline__ double logaddexp_d(double a, double b) {
+  if (a == -CUDART_INF) return b;
+  if (b == -CUDART_INF) return a;
+  const double mx = fmax(a, b);
+  return mx + log1p(exp(-fabs(a - b)));
+}
+
+template <int D>
+__device__ __forceinline__ double energy_d(double lp, const double (&g)[D], const double (&r)[D],
+                                           const double (&minv)[D]) {
+  double k = 0;
+  bool ok = isfinite(lp);
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    k += minv[d] * r[d] * r[d];
+    ok = ok && isfinite(g[d]);
+  }
+  k *= 0.5;
+  return (ok && isfinite(k)) ? (-lp + k) : CUDART_INF;
+}
+
+// one leapfrog step of signed size eps: half kick, drift, gradient, half kick
+template <class M>
+__device__ __forceinline__ void leapfrog_d(const SmallData &md, double (&th)[M::D],
+                                           double (&r)[M::D], double (&g)[M::D],
+                                           const double (&minv)[M::D], double eps, double &lp,
+                                           double &H) {
+  constexpr int D = M::D;
+  const double half = 0.5 * eps;
+#pragma unroll
+  for (int d = 0; d < D; ++d) r[d] = r[d] + half * g[d];
+#pragma unroll
+  for (int d = 0; d < D; ++d) th[d] = th[d] + eps * (minv[d] * r[d]);
+  lp = M::lpgrad(md, th, g);
+#pragma unroll
+  for (int d = 0; d < D; ++d) r[d] = r[d] + half * g[d];
+  H = energy_d<D>(lp, g, r, minv);
+}
+
+template <int D>
+__device__ __forceinline__ void draw_momentum_d(unsigned long long seed, uint32_t chain,
+                                                uint32_t iter, uint32_t slot,
+                                                const double (&minv)[D], double (&r)[D]) {
+#pragma unroll
+  for (int p = 0; 2 * p < D; ++p) {
+    double z0, z1;
+    normal2(seed, chain, iter, slot, (uint32_t)p, z0, z1);
+    r[2 * p] = z0 / sqrt(minv[2 * p]);
+    if (2 * p + 1 < D) r[2 * p + 1] = z1 / sqrt(minv[2 * p + 1]);
+  }
+}
+
+template <int D>
+__device__ __forceinline__ bool uturn_d(const double (&rho)[D], const double *rl, const double *rr,
+                                        const double (&minv)[D]) {
+  double a = 0, b = 0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    a += rho[d] * (minv[d] * rl[d]);
+    b += rho[d] * (minv[d] * rr[d]);
+  }
+  return (a <= 0) || (b <= 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// NUTS transition.  On entry th/g/lp = current point; on exit = the selected candidate.
+// ------------------------------------------------------------------------------------------
+template <class M>
+__device__ __forceinline__ void nuts_transition_d(const SmallData &md, const RunParams &rp,
+                                                  uint32_t gchain, uint32_t it,
+                                                  double (&th)[M::D], double (&g)[M::D],
+                                                  double &lp, const double (&minv)[M::D],
+                                                  double eps, long long &ngrad,
+                                                  double (&stats)[TNUTS_NSTAT]) {
+  constexpr int D = M::D;
+  double r[D];
+  draw_momentum_d<D>(rp.seed, gchain, it, SLOT_MOMENTUM, minv, r);
+  const double H0 = energy_d<D>(lp, g, r, minv);
+
+  // tree edges: [0] = left (v = -1), [1] = right (v = +1); each holds theta | r | grad
+  double edge[2][3 * D];
+  double elp[2];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    edge[0][d] = edge[1][d] = th[d];
+    edge[0][D + d] = edge[1][D + d] = r[d];
+    edge[0][2 * D + d] = edge[1][2 * D + d] = g[d];
+  }
+  elp[0] = elp[1] = lp;
+
+  double rho[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) rho[d] = r[d];
+  double sum_a = 0.0, dHmax = 0.0, lw = 0.0;
+  long long n_a = 0;
+  // candidate of the whole tree (starts at z0)
+  double thC[D], gC[D], lpC = lp, HC = H0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    thC[d] = th[d];
+    gC[d] = g[d];
+  }
+  // per-level checkpoints for the sub-tree U-turn checks
+  double ck_r[kMaxCk][D], ck_rho[kMaxCk][D];
+
+  int j = 0;
+  bool term = false, numerr = false;
+  while (!term && j < rp.max_depth) {
+    const int v = (uniform1(rp.seed, gchain, it, SLOT_DIRECTION, (uint32_t)j) < 0.5) ? 0 : 1;
+    const double se = v ? eps : -eps;
+    double zt[D], zr[D], zg[D], zlp = elp[v], zH;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      zt[d] = edge[v][d];
+      zr[d] = edge[v][D + d];
+      zg[d] = edge[v][2 * D + d];
+    }
+    double rho_s[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) rho_s[d] = 0.0;
+    double lw_s = -CUDART_INF;
+    double thS[D], gS[D], lpS = 0.0, HS = 0.0;
+    bool term_s = false;
+    const int nleaf = 1 << j;
+    for (int n = 0; n < nleaf; ++n) {
+      leapfrog_d<M>(md, zt, zr, zg, minv, se, zlp, zH);
+      ++ngrad;
+      const double dH = zH - H0;
+      const double a = exp(fmin(0.0, -dH));
+      sum_a += a;
+      ++n_a;
+      if (fabs(dH) > fabs(dHmax)) dHmax = dH;
+      // streaming multinomial candidate
+      const double lw_leaf = -dH;
+      const double lw_new = logaddexp_d(lw_s, lw_leaf);
+      const double p = (lw_leaf == -CUDART_INF) ? 0.0 : exp(lw_leaf - lw_new);
+      const double u = uniform1(rp.seed, gchain, it, SLOT_LEAF, (1u << j) + (uint32_t)n);
+      if (u < p) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          thS[d] = zt[d];
+          gS[d] = zg[d];
+        }
+        lpS = zlp;
+        HS = zH;
+      }
+      lw_s = lw_new;
+#pragma unroll
+      for (int d = 0; d < D; ++d) rho_s[d] += zr[d];
+      if (!(dH < rp.delta_max)) {  // divergence (NaN-safe)
+        numerr = true;
+        term_s = true;
+        break;
+      }
+      const int idx_max = __popc((unsigned)n >> 1);
+      if ((n & 1) == 0) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          ck_r[idx_max][d] = zr[d];
+          ck_rho[idx_max][d] = rho_s[d];
+        }
+      } else {
+        const int ntrail = __ffs(~(unsigned)n) - 1;  // trailing ones of n
+        const int idx_min = idx_max - ntrail + 1;
+        for (int i = idx_max; i >= idx_min; --i) {
+          double sr[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) sr[d] = rho_s[d] - ck_rho[i][d] + ck_r[i][d];
+          if (uturn_d<D>(sr, ck_r[i], zr, minv)) {
+            term_s = true;
+            break;
+          }
+        }
+        if (term_s) break;
+      }
+    }
+    // the new sub-tree becomes the tree's edge on side v (combine)
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      edge[v][d] = zt[d];
+      edge[v][D + d] = zr[d];
+      edge[v][2 * D + d] = zg[d];
+    }
+    elp[v] = zlp;
+    if (!term_s) {
+      const double u = uniform1(rp.seed, gchain, it, SLOT_MH, (uint32_t)j);
+      ++j;
+      const double dl = lw_s - lw;
+      if (u < (dl < 0.0 ? exp(dl) : 1.0)) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          thC[d] = thS[d];
+          gC[d] = gS[d];
+        }
+        lpC = lpS;
+        HC = HS;
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) rho[d] += rho_s[d];
+    lw = logaddexp_d(lw, lw_s);
+    term = term_s || uturn_d<D>(rho, &edge[0][D], &edge[1][D], minv);
+  }
+  stats[ST_NSTEPS] = (double)n_a;
+  stats[ST_ACC] = sum_a / (double)n_a;
+  stats[ST_LP] = lpC;
+  stats[ST_H] = HC;
+  stats[ST_HERR] = HC - H0;
+  stats[ST_MAXHERR] = dHmax;
+  stats[ST_DEPTH] = (double)j;
+  stats[ST_NUMERR] = numerr ? 1.0 : 0.0;
+  stats[ST_EPS] = eps;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    th[d] = thC[d];
+    g[d] = gC[d];
+  }
+  lp = lpC;
+}
+
+// HMC / HMCDA: static trajectory + Metropolis accept (src/mcmc/hmc.jl:425-434)
+template <class M>
+__device__ __forceinline__ void hmc_transition_d(const SmallData &md, const RunParams &rp,
+                                                 uint32_t gchain, uint32_t it, double (&th)[M::D],
+                                                 double (&g)[M::D], double &lp,
+                                                 const double (&minv)[M::D], double eps,
+                                                 long long &ngrad, double (&stats)[TNUTS_NSTAT]) {
+  constexpr int D = M::D;
+  int L = rp.n_leapfrog;
+  if (rp.algorithm == TNUTS_ALG_HMCDA) {
+    L = (int)floor(rp.lambda / eps);
+    if (L < 1) L = 1;
+  }
+  double r[D];
+  draw_momentum_d<D>(rp.seed, gchain, it, SLOT_MOMENTUM, minv, r);
+  const double H0 = energy_d<D>(lp, g, r, minv);
+  double zt[D], zg[D], zlp = lp, zH = H0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    zt[d] = th[d];
+    zg[d] = g[d];
+  }
+  int nsteps = 0;
+  for (int l = 0; l < L; ++l) {
+    leapfrog_d<M>(md, zt, r, zg, minv, eps, zlp, zH);
+    ++ngrad;
+    ++nsteps;
+    if (!isfinite(zH)) break;
+  }
+  const double dH = zH - H0;
+  const double alpha = exp(fmin(0.0, -dH));
+  const double u = uniform1(rp.seed, gchain, it, SLOT_MH, 0u);
+  const bool accept = u < alpha;
+  if (accept) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      th[d] = zt[d];
+      g[d] = zg[d];
+    }
+    lp = zlp;
+  }
+  stats[ST_NSTEPS] = (double)nsteps;
+  stats[ST_ACC] = alpha;
+  stats[ST_LP] = lp;
+  stats[ST_H] = accept ? zH : H0;
+  stats[ST_HERR] = accept ? dH : 0.0;
+  stats[ST_MAXHERR] = dH;
+  stats[ST_DEPTH] = accept ? 1.0 : 0.0;
+  stats[ST_NUMERR] = isfinite(zH) ? 0.0 : 1.0;
+  stats[ST_EPS] = eps;
+}
+
+// ------------------------------------------------------------------------------------------
+// run kernel: n_transitions for every chain
+// ------------------------------------------------------------------------------------------
+template <class M>
+__global__ void __launch_bounds__(kChainBlock) k_chain_run(SmallData md, ChainState st,
+                                                          DrawBuffers out, RunParams rp) {
+  constexpr int D = M::D;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int C = st.C;
+  if (c >= C) return;
+  if (st.status[c] != 0) return;
+  const uint32_t gchain = (uint32_t)(rp.chain_offset + c);
+
+  double th[D], g[D], minv[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    th[d] = st.theta[(size_t)d * C + c];
+    g[d] = st.grad[(size_t)d * C + c];
+    minv[d] = st.minv[(size_t)d * C + c];
+  }
+  double lp = st.lp[c], eps = st.eps[c];
+  long long iter = st.iter[c], ngrad = st.n_grad[c];
+  double da_mu = st.da_mu[c], da_xbar = st.da_xbar[c], da_hbar = st.da_hbar[c],
+         da_eps = st.da_eps[c];
+  long long da_m = st.da_m[c], wf_n = st.wf_n[c];
+
+  for (long long t = 1; t <= rp.n_transitions; ++t) {
+    const uint32_t it = (uint32_t)(iter + 1);
+    double stats[TNUTS_NSTAT];
+    if (rp.algorithm == TNUTS_ALG_NUTS)
+      nuts_transition_d<M>(md, rp, gchain, it, th, g, lp, minv, eps, ngrad, stats);
+    else
+      hmc_transition_d<M>(md, rp, gchain, it, th, g, lp, minv, eps, ngrad, stats);
+    iter += 1;
+
+    // ---- AHMC.adapt!: StanHMCAdaptor(MassMatrixAdaptor, StepSizeAdaptor) ----
+    if (rp.algorithm != TNUTS_ALG_HMC && iter <= rp.n_adapts) {
+      {  // Nesterov dual averaging: gamma = 0.05, t0 = 10, kappa = 0.75
+        const double alpha = fmin(stats[ST_ACC], 1.0);
+        const long long mm = da_m + 1;
+        const double eta_h = 1.0 / ((double)mm + 10.0);
+        const double hbar = (1.0 - eta_h) * da_hbar + eta_h * (rp.delta - alpha);
+        const double x = da_mu - hbar * sqrt((double)mm) / 0.05;
+        const double eta_x = pow((double)mm, -0.75);
+        const double xbar = (1.0 - eta_x) * da_xbar + eta_x * x;
+        const double e = exp(x);
+        da_m = mm;
+        if (isfinite(e)) {
+          da_hbar = hbar;
+          da_xbar = xbar;
+          da_eps = e;
+        }
+      }
+      bool wend = false;
+      for (int k = 0; k < rp.n_splits; ++k) wend = wend || (rp.splits[k] == iter);
+      if (iter >= rp.window_start && iter <= rp.window_end) {
+        wf_n += 1;
+        const double n = (double)wf_n;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const size_t o = (size_t)d * C + c;
+          double mean = st.wf_mean[o], m2 = st.wf_m2[o];
+          const double delta = th[d] - mean;
+          mean += delta / n;
+          m2 += delta * (th[d] - mean);
+          if (wend) {
+            if (wf_n >= 10) minv[d] = n / ((n + 5.0) * (n - 1.0)) * m2 + 1e-3 * (5.0 / (n + 5.0));
+            mean = 0.0;
+            m2 = 0.0;
+          }
+          st.wf_mean[o] = mean;
+          st.wf_m2[o] = m2;
+        }
+      }
+      if (wend) {
+        da_mu = log(10.0 * da_eps);
+        da_m = 0;
+        da_xbar = 0.0;
+        da_hbar = 0.0;
+        wf_n = 0;
+      }
+      if (iter == rp.n_adapts) da_eps = exp(da_xbar);
+      eps = da_eps;
+    }
+
+    // ---- record (ParamsWithStats): constrained params, user-space log-probs, stats ----
+    if (rp.first_keep >= 1 && t >= rp.first_keep && (t - rp.first_keep) % rp.thin == 0) {
+      const long long k = (t - rp.first_keep) / rp.thin;
+      double p[D], prior, lik;
+      M::constrain(md, th, p, prior, lik);
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        out.params[((size_t)k * D + d) * C + c] = p[d];
+        out.theta[((size_t)k * D + d) * C + c] = th[d];
+      }
+      out.logp[((size_t)k * 3 + 0) * C + c] = prior;
+      out.logp[((size_t)k * 3 + 1) * C + c] = lik;
+      out.logp[((size_t)k * 3 + 2) * C + c] = prior + lik;
+#pragma unroll
+      for (int s = 0; s < TNUTS_NSTAT; ++s) out.stats[((size_t)k * TNUTS_NSTAT + s) * C + c] = stats[s];
+    }
+  }
+
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    st.theta[(size_t)d * C + c] = th[d];
+    st.grad[(size_t)d * C + c] = g[d];
+    st.minv[(size_t)d * C + c] = minv[d];
+  }
+  st.lp[c] = lp;
+  st.eps[c] = eps;
+  st.iter[c] = iter;
+  st.n_grad[c] = ngrad;
+  st.da_mu[c] = da_mu;
+  st.da_xbar[c] = da_xbar;
+  st.da_hbar[c] = da_hbar;
+  st.da_eps[c] = da_eps;
+  st.da_m[c] = da_m;
+  st.wf_n[c] = wf_n;
+}
+
+// ------------------------------------------------------------------------------------------
+// init kernel: initial parameters, phase point, find_good_stepsize, adaptor state
+// ------------------------------------------------------------------------------------------
+template <class M>
+__device__ __forceinline__ double find_good_stepsize_d(const SmallData &md, const RunParams &rp,
+                                                       uint32_t gchain, const double (&th)[M::D],
+                                                       const double (&g)[M::D], double lp,
+                                                       const double (&minv)[M::D],
+                                                       long long &ngrad) {
+  constexpr int D = M::D;
+  const double a_min = 0.25, a_cross = 0.5, a_max = 0.75, dd = 2.0;
+  double eps = 0.1, eps_p = 0.1;
+  double r0[D];
+  draw_momentum_d<D>(rp.seed, gchain, 0u, SLOT_EPS_MOMENTUM, minv, r0);
+  const double H = energy_d<D>(lp, g, r0, minv);
+  double zt[D], zr[D], zg[D], zlp, zH;
+  auto trial = [&](double e) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      zt[d] = th[d];
+      zr[d] = r0[d];
+      zg[d] = g[d];
+    }
+    leapfrog_d<M>(md, zt, zr, zg, minv, e, zlp, zH);
+    ++ngrad;
+    return H - zH;
+  };
+  double dH = trial(eps);
+  const double lc = log(a_cross);
+  const int direction = dH > lc ? 1 : -1;
+  for (int i = 0; i < 100; ++i) {
+    eps_p = direction == 1 ? dd * eps : 1.0 / dd * eps;
+    dH = trial(eps);
+    if (direction == 1 && !(dH > lc)) break;
+    else if (direction == -1 && !(dH < lc)) break;
+    else eps = eps_p;
+  }
+  if (eps > eps_p) {
+    const double t = eps;
+    eps = eps_p;
+    eps_p = t;
+  }
+  for (int i = 0; i < 100; ++i) {
+    const double mid = 0.5 * (eps + eps_p);
+    dH = trial(mid);
+    const double ea = exp(dH);
+    if (ea > a_max) eps = mid;
+    else if (ea < a_min) eps_p = mid;
+    else {
+      eps = mid;
+      break;
+    }
+  }
+  return eps;
+}
+
+template <class M>
+__global__ void __launch_bounds__(kChainBlock) k_chain_init(SmallData md, ChainState st,
+                                                           RunParams rp, const double *theta0,
+                                                           double init_eps) {
+  constexpr int D = M::D;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int C = st.C;
+  if (c >= C) return;
+  const uint32_t gchain = (uint32_t)(rp.chain_offset + c);
+  double th[D], g[D], minv[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) minv[d] = 1.0;  // DiagEuclideanMetric(D)
+  double lp = 0.0;
+  long long ngrad = 0;
+  bool ok = false;
+  int tries = 0;
+  constexpr int npair = (D + 1) / 2;
+  if (theta0 != nullptr) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) th[d] = theta0[(size_t)c * D + d];
+    lp = M::lpgrad(md, th, g);
+    ++ngrad;
+    ok = isfinite(lp);
+#pragma unroll
+    for (int d = 0; d < D; ++d) ok = ok && isfinite(g[d]);
+    tries = 1;
+  } else {
+    for (int t = 0; t < 1000 && !ok; ++t) {  // max_attempts = 1000
+#pragma unroll
+      for (int p = 0; p < npair; ++p) {
+        double u0, u1;
+        uniform2(rp.seed, gchain, 0u, SLOT_INIT, (uint32_t)(t * npair + p), u0, u1);
+        th[2 * p] = 4.0 * u0 - 2.0;  // InitFromUniform: U(-2, 2) in linked space
+        if (2 * p + 1 < D) th[2 * p + 1] = 4.0 * u1 - 2.0;
+      }
+      lp = M::lpgrad(md, th, g);
+      ++ngrad;
+      ok = isfinite(lp);
+#pragma unroll
+      for (int d = 0; d < D; ++d) ok = ok && isfinite(g[d]);
+      tries = t + 1;
+    }
+  }
+  st.init_tries[c] = tries;
+  st.status[c] = ok ? 0 : 1;
+  double eps = init_eps;
+  if (ok && init_eps == 0.0) {
+    if (rp.algorithm == TNUTS_ALG_HMC) eps = 0.1;
+    else eps = find_good_stepsize_d<M>(md, rp, gchain, th, g, lp, minv, ngrad);
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const size_t o = (size_t)d * C + c;
+    st.theta[o] = th[d];
+    st.grad[o] = g[d];
+    st.minv[o] = minv[d];
+    st.wf_mean[o] = 0.0;
+    st.wf_m2[o] = 0.0;
+  }
+  st.lp[c] = lp;
+  st.eps[c] = eps;
+  st.da_eps[c] = eps;
+  st.da_mu[c] = log(10.0 * eps);  // StepSizeAdaptor(delta, eps)
+  st.da_xbar[c] = 0.0;
+  st.da_hbar[c] = 0.0;
+  st.da_m[c] = 0;
+  st.wf_n[c] = 0;
+  st.iter[c] = 0;
+  st.n_grad[c] = ngrad;
+}
+
+// ------------------------------------------------------------------------------------------
+// point-wise helpers (LogDensityProblems interface, constrain, leapfrog trajectories)
+// ------------------------------------------------------------------------------------------
+template <class M>
+__global__ void k_point_lpgrad(SmallData md, const double *theta, long long n, double *lp,
+                               double *grad) {
+  constexpr int D = M::D;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double th[D], g[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) th[d] = theta[i * D + d];
+  lp[i] = M::lpgrad(md, th, g);
+  if (grad != nullptr) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) grad[i * D + d] = g[d];
+  }
+}
+
+template <class M>
+__global__ void k_point_constrain(SmallData md, const double *theta, long long n, double *params,
+                                  double *logp) {
+  constexpr int D = M::D;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double th[D], p[D], prior, lik;
+#pragma unroll
+  for (int d = 0; d < D; ++d) th[d] = theta[i * D + d];
+  M::constrain(md, th, p, prior, lik);
+#pragma unroll
+  for (int d = 0; d < D; ++d) params[i * D + d] = p[d];
+  logp[i * 3 + 0] = prior;
+  logp[i * 3 + 1] = lik;
+  logp[i * 3 + 2] = prior + lik;
+}
+
+template <class M>
+__global__ void k_point_leapfrog(SmallData md, const double *theta, const double *r0,
+                                 const double *minv_in, double eps, int L, long long n,
+                                 double *traj_theta, double *traj_r, double *traj_H) {
+  constexpr int D = M::D;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double th[D], r[D], g[D], minv[D], lp, H;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    th[d] = theta[i * D + d];
+    r[d] = r0[i * D + d];
+    minv[d] = minv_in[d];
+  }
+  lp = M::lpgrad(md, th, g);
+  H = energy_d<D>(lp, g, r, minv);
+  for (int l = 0; l <= L; ++l) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      traj_theta[(i * (L + 1) + l) * D + d] = th[d];
+      traj_r[(i * (L + 1) + l) * D + d] = r[d];
+    }
+    traj_H[i * (L + 1) + l] = H;
+    if (l < L) leapfrog_d<M>(md, th, r, g, minv, eps, lp, H);
+  }
+}
+
+}  // namespace tnuts

@@ -1,0 +1,655 @@
+// engine.cu -- C ABI of the tnuts engine (include/tnuts.h).  Host-side plumbing only:
+// device memory, model upload, strategy selection, launches, D2H of kept draws.
+#include "engine.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace tnuts {
+
+static std::string g_create_error;
+static std::mutex g_create_mu;
+
+int set_error(Engine *e, int code, const std::string &msg) {
+  if (e) e->err = msg;
+  else {
+    std::lock_guard<std::mutex> lk(g_create_mu);
+    g_create_error = msg;
+  }
+  return code;
+}
+
+template <class T>
+static int dev_alloc(Engine *e, std::vector<void *> &pool, T **p, size_t n) {
+  void *q = nullptr;
+  TN_CUDA(e, cudaMalloc(&q, (n ? n : 1) * sizeof(T)));
+  TN_CUDA(e, cudaMemsetAsync(q, 0, (n ? n : 1) * sizeof(T), e->stream));
+  pool.push_back(q);
+  *p = (T *)q;
+  return TNUTS_OK;
+}
+static void free_pool(std::vector<void *> &pool) {
+  for (void *p : pool) cudaFree(p);
+  pool.clear();
+}
+
+// Stan's windowed-adaptation schedule as used by AdvancedHMC's StanHMCAdaptor
+// (init_buffer 75, term_buffer 50, window_size 25), 1-based.
+static void window_schedule(long long n, RunParams &rp) {
+  long long init_buffer = 75, term_buffer = 50, base = 25;
+  rp.n_splits = 0;
+  if (n < 20) {
+    rp.window_start = n + 1;
+    rp.window_end = n;
+    return;
+  }
+  if (init_buffer + base + term_buffer > n) {
+    init_buffer = (long long)(0.15 * (double)n);
+    term_buffer = (long long)(0.1 * (double)n);
+    base = n - init_buffer - term_buffer;
+  }
+  rp.window_start = init_buffer + 1;
+  rp.window_end = n - term_buffer;
+  long long next = init_buffer + base;
+  while (rp.n_splits < 24) {
+    if (next >= rp.window_end) {
+      rp.splits[rp.n_splits++] = rp.window_end;
+      break;
+    }
+    rp.splits[rp.n_splits++] = next;
+    base *= 2;
+    long long nn = next + base;
+    if (nn != rp.window_end && nn + 2 * base > rp.window_end) nn = rp.window_end;
+    next = nn;
+  }
+}
+
+static int ensure_draw_capacity(Engine *e, long long keep) {
+  if (keep <= e->out.capacity) return TNUTS_OK;
+  for (double **p : {&e->out.params, &e->out.logp, &e->out.stats, &e->out.theta}) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  const size_t C = (size_t)e->st.C;
+  e->out.capacity = 0;
+  TN_CUDA(e, cudaMalloc((void **)&e->out.params, sizeof(double) * (size_t)keep * e->P * C));
+  TN_CUDA(e, cudaMalloc((void **)&e->out.theta, sizeof(double) * (size_t)keep * e->D * C));
+  TN_CUDA(e, cudaMalloc((void **)&e->out.logp, sizeof(double) * (size_t)keep * 3 * C));
+  TN_CUDA(e, cudaMalloc((void **)&e->out.stats, sizeof(double) * (size_t)keep * TNUTS_NSTAT * C));
+  e->out.capacity = keep;
+  e->out.P = e->P;
+  return TNUTS_OK;
+}
+
+static int build_small(Engine *e, const tnuts_model *m) {
+  SmallData &s = e->small;
+  std::memset(&s, 0, sizeof(s));
+  s.n = (int)m->N;
+  const int n = s.n;
+  switch (m->family) {
+    case TNUTS_GDEMO: {
+      if (n > 16) return TNUTS_OK;
+      for (int i = 0; i < n; ++i) s.a[i] = m->y[i];
+      const double al = m->hyper[0], be = m->hyper[1];
+      s.h[0] = al;
+      s.h[1] = be;
+      s.cst = al * std::log(be) - std::lgamma(al) - 0.5 * (n + 1) * kLog2Pi;
+    } break;
+    case TNUTS_LINREG: {
+      if (n > 16) return TNUTS_OK;
+      for (int i = 0; i < n; ++i) {
+        s.a[i] = m->y[i];
+        s.b[i] = m->X[i];
+      }
+      const double sd = m->hyper[0], c = m->hyper[1];
+      s.h[0] = sd;
+      s.h[1] = c;
+      s.h[2] = 1.0 / (sd * sd);
+      s.h[3] = 1.0 / c;
+      s.cst_lik = -0.5 * n * kLog2Pi;
+      s.cst = -kLog2Pi - 2.0 * std::log(sd) + kLog2 - kLogPi - std::log(c) + s.cst_lik;
+    } break;
+    case TNUTS_EIGHT_SCHOOLS: {
+      if (n > 16) return TNUTS_OK;
+      const double sd = m->hyper[0], c = m->hyper[1];
+      s.h[0] = sd;
+      s.h[1] = c;
+      s.h[2] = 1.0 / (sd * sd);
+      s.h[3] = 1.0 / c;
+      s.cst_lik = 0.0;
+      for (int j = 0; j < n; ++j) {
+        s.a[j] = m->y[j];
+        s.b[j] = 1.0 / (m->sigma[j] * m->sigma[j]);
+        s.cst_lik += -0.5 * kLog2Pi - std::log(m->sigma[j]);
+      }
+      s.cst = -0.5 * kLog2Pi - std::log(sd) + kLog2 - kLogPi - std::log(c) - 0.5 * n * kLog2Pi +
+              s.cst_lik;
+    } break;
+    case TNUTS_STD_NORMAL:
+      s.cst = -0.5 * m->D * kLog2Pi;
+      break;
+    default:
+      break;
+  }
+  return TNUTS_OK;
+}
+
+}  // namespace tnuts
+
+using namespace tnuts;
+
+extern "C" {
+
+int tnuts_abi_version(void) { return TNUTS_ABI_VERSION; }
+
+const char *tnuts_last_error(const tnuts_engine *h) {
+  if (h) return ((const Engine *)h)->err.c_str();
+  return g_create_error.c_str();
+}
+
+int tnuts_create(const tnuts_config *cfg, tnuts_engine **out) {
+  if (!cfg || !out) return set_error(nullptr, TNUTS_E_ARG, "tnuts_create: null argument");
+  *out = nullptr;
+  if (cfg->n_chains <= 0) return set_error(nullptr, TNUTS_E_ARG, "tnuts_create: n_chains must be > 0");
+  if (cfg->max_depth < 1 || cfg->max_depth > 24)
+    return set_error(nullptr, TNUTS_E_ARG, "tnuts_create: max_depth must be in 1..24");
+  int ndev = 0;
+  cudaError_t s = cudaGetDeviceCount(&ndev);
+  if (s != cudaSuccess || ndev == 0)
+    return set_error(nullptr, TNUTS_E_CUDA,
+                     std::string("tnuts_create: no CUDA device (this engine has no CPU fallback): ") +
+                         cudaGetErrorString(s));
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return set_error(nullptr, TNUTS_E_ARG, "tnuts_create: bad device ordinal");
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cfg->device);
+  if (prop.major != 10)
+    return set_error(nullptr, TNUTS_E_CUDA,
+                     std::string("tnuts_create: libtnuts is built for sm_100a only; device is ") +
+                         prop.name);
+  Engine *e = new Engine();
+  e->cfg = *cfg;
+  e->device = cfg->device;
+  if (cudaSetDevice(e->device) != cudaSuccess || cudaStreamCreate(&e->stream) != cudaSuccess ||
+      cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) {
+    delete e;
+    return set_error(nullptr, TNUTS_E_CUDA, "tnuts_create: stream/event creation failed");
+  }
+  RunParams &rp = e->rp;
+  rp.algorithm = cfg->algorithm;
+  rp.delta = cfg->delta;
+  rp.max_depth = cfg->max_depth;
+  rp.delta_max = cfg->delta_max;
+  rp.n_adapts = cfg->n_adapts;
+  rp.n_leapfrog = cfg->n_leapfrog;
+  rp.lambda = cfg->lambda;
+  rp.seed = cfg->seed;
+  rp.chain_offset = cfg->chain_offset;
+  window_schedule(cfg->n_adapts, rp);
+  *out = (tnuts_engine *)e;
+  return TNUTS_OK;
+}
+
+int tnuts_destroy(tnuts_engine *h) {
+  if (!h) return TNUTS_OK;
+  Engine *e = (Engine *)h;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  lockstep_destroy(e);
+  diagnostics_destroy(e);
+  free_pool(e->model_allocs);
+  free_pool(e->state_allocs);
+  for (double *p : {e->out.params, e->out.logp, e->out.stats, e->out.theta})
+    if (p) cudaFree(p);
+  cudaEventDestroy(e->ev0);
+  cudaEventDestroy(e->ev1);
+  cudaStreamDestroy(e->stream);
+  delete e;
+  return TNUTS_OK;
+}
+
+int tnuts_set_model(tnuts_engine *h, const tnuts_model *m) {
+  Engine *e = (Engine *)h;
+  if (!e || !m) return set_error(e, TNUTS_E_ARG, "tnuts_set_model: null argument");
+  if (e->has_model) return set_error(e, TNUTS_E_ARG, "tnuts_set_model: model already set");
+  if (m->D <= 0) return set_error(e, TNUTS_E_ARG, "tnuts_set_model: D must be > 0");
+  TN_CUDA(e, cudaSetDevice(e->device));
+  e->D = m->D;
+  e->P = m->D;
+  ModelDev &md = e->model;
+  md.family = m->family;
+  md.D = m->D;
+  md.G = m->G;
+  md.N = m->N;
+  std::memcpy(md.hyper, m->hyper, sizeof(md.hyper));
+  auto upload = [&](const void *src, size_t bytes, const void **dst) -> int {
+    if (!src || bytes == 0) return TNUTS_OK;
+    void *q = nullptr;
+    TN_CUDA(e, cudaMalloc(&q, bytes));
+    e->model_allocs.push_back(q);
+    TN_CUDA(e, cudaMemcpyAsync(q, src, bytes, cudaMemcpyHostToDevice, e->stream));
+    *dst = q;
+    return TNUTS_OK;
+  };
+  int rc = TNUTS_OK;
+  const size_t N = (size_t)m->N;
+  switch (m->family) {
+    case TNUTS_GDEMO:
+      if (!m->y) return set_error(e, TNUTS_E_ARG, "gdemo needs y");
+      rc = upload(m->y, N * 8, (const void **)&md.y);
+      break;
+    case TNUTS_LINREG:
+      if (!m->y || !m->X || m->D != 3) return set_error(e, TNUTS_E_ARG, "linreg needs x, y, D=3");
+      rc = upload(m->y, N * 8, (const void **)&md.y);
+      if (!rc) rc = upload(m->X, N * 8, (const void **)&md.X);
+      break;
+    case TNUTS_EIGHT_SCHOOLS:
+      if (!m->y || !m->sigma || m->D != m->N + 2)
+        return set_error(e, TNUTS_E_ARG, "eight schools needs y, sigma, D=N+2");
+      rc = upload(m->y, N * 8, (const void **)&md.y);
+      if (!rc) rc = upload(m->sigma, N * 8, (const void **)&md.sigma);
+      break;
+    case TNUTS_LOGISTIC:
+      if (!m->y || !m->X) return set_error(e, TNUTS_E_ARG, "logistic needs X, y");
+      rc = upload(m->y, N * 8, (const void **)&md.y);
+      if (!rc) rc = upload(m->X, N * (size_t)m->D * 8, (const void **)&md.X);
+      break;
+    case TNUTS_HIER_LINREG:
+      if (!m->y || !m->X || !m->group || m->D != 5 + 2 * m->G)
+        return set_error(e, TNUTS_E_ARG, "hier needs x, y, group, D=5+2G");
+      rc = upload(m->y, N * 8, (const void **)&md.y);
+      if (!rc) rc = upload(m->X, N * 8, (const void **)&md.X);
+      if (!rc) rc = upload(m->group, N * 4, (const void **)&md.group);
+      break;
+    case TNUTS_STD_NORMAL:
+      break;
+    default:
+      return set_error(e, TNUTS_E_ARG, "tnuts_set_model: unknown family");
+  }
+  if (rc) return rc;
+  build_small(e, m);
+  // strategy
+  const bool thread_ok = thread_strategy_supported(e);
+  if (e->cfg.strategy == STRAT_THREAD && !thread_ok)
+    return set_error(e, TNUTS_E_UNSUPPORTED, "thread-per-chain strategy not available for this model");
+  e->strategy = (e->cfg.strategy == STRAT_LOCKSTEP || !thread_ok) ? STRAT_LOCKSTEP : STRAT_THREAD;
+
+  // chain state
+  const size_t C = (size_t)e->cfg.n_chains, D = (size_t)m->D;
+  ChainState &st = e->st;
+  st.C = (int)C;
+  st.D = (int)D;
+  auto &pool = e->state_allocs;
+  if ((rc = dev_alloc(e, pool, &st.theta, D * C))) return rc;
+  if ((rc = dev_alloc(e, pool, &st.grad, D * C))) return rc;
+  if ((rc = dev_alloc(e, pool, &st.minv, D * C))) return rc;
+  if ((rc = dev_alloc(e, pool, &st.wf_mean, D * C))) return rc;
+  if ((rc = dev_alloc(e, pool, &st.wf_m2, D * C))) return rc;
+  if ((rc = dev_alloc(e, pool, &st.lp, C))) return rc;
+  if ((rc = dev_alloc(e, pool, &st.eps, C))) return rc;
+  if ((rc = dev_alloc(e, pool, &st.da_mu, C))) return rc;
+  if ((rc = dev_alloc(e, pool, &st.da_xbar, C))) return rc;
+  if ((rc = dev_alloc(e, pool, &st.da_hbar, C))) return rc;
+  if ((rc = dev_alloc(e, pool, &st.da_eps, C))) return rc;
+  if ((rc = dev_alloc(e, pool, &st.da_m, C))) return rc;
+  if ((rc = dev_alloc(e, pool, &st.wf_n, C))) return rc;
+  if ((rc = dev_alloc(e, pool, &st.iter, C))) return rc;
+  if ((rc = dev_alloc(e, pool, &st.n_grad, C))) return rc;
+  if ((rc = dev_alloc(e, pool, &st.init_tries, C))) return rc;
+  if ((rc = dev_alloc(e, pool, &st.status, C))) return rc;
+  if (e->strategy == STRAT_LOCKSTEP) {
+    if ((rc = lockstep_create(e))) return rc;
+  }
+  TN_CUDA(e, cudaStreamSynchronize(e->stream));
+  e->has_model = true;
+  return TNUTS_OK;
+}
+
+int tnuts_dimension(const tnuts_engine *h) { return h ? ((const Engine *)h)->D : TNUTS_E_ARG; }
+int tnuts_num_params(const tnuts_engine *h) { return h ? ((const Engine *)h)->P : TNUTS_E_ARG; }
+
+static const char *kInitFailMsg =
+    "failed to find valid initial parameters in 1000 tries. See "
+    "https://turinglang.org/docs/uri/initial-parameters for common causes and solutions. If the "
+    "issue persists, please open an issue at https://github.com/TuringLang/Turing.jl/issues";
+
+int tnuts_init(tnuts_engine *h, const double *theta0) {
+  Engine *e = (Engine *)h;
+  if (!e || !e->has_model) return set_error(e, TNUTS_E_ARG, "tnuts_init: set a model first");
+  TN_CUDA(e, cudaSetDevice(e->device));
+  double *t0 = nullptr;
+  const size_t bytes = sizeof(double) * (size_t)e->st.C * e->D;
+  if (theta0) {
+    TN_CUDA(e, cudaMalloc((void **)&t0, bytes));
+    TN_CUDA(e, cudaMemcpyAsync(t0, theta0, bytes, cudaMemcpyHostToDevice, e->stream));
+  }
+  int rc = (e->strategy == STRAT_THREAD) ? thread_init(e, t0) : lockstep_init(e, t0);
+  cudaError_t s = cudaStreamSynchronize(e->stream);
+  if (t0) cudaFree(t0);
+  if (rc) return rc;
+  if (s != cudaSuccess) return set_error(e, TNUTS_E_CUDA, std::string("tnuts_init: ") + cudaGetErrorString(s));
+  std::vector<int> status((size_t)e->st.C);
+  TN_CUDA(e, cudaMemcpy(status.data(), e->st.status, sizeof(int) * status.size(), cudaMemcpyDeviceToHost));
+  for (int v : status)
+    if (v != 0) return set_error(e, TNUTS_E_INIT, kInitFailMsg);
+  e->inited = true;
+  e->n_kept = 0;
+  return TNUTS_OK;
+}
+
+int tnuts_run(tnuts_engine *h, int64_t n_transitions, int64_t first_keep, int64_t thin,
+              int64_t *n_kept) {
+  Engine *e = (Engine *)h;
+  if (!e || !e->inited) return set_error(e, TNUTS_E_ARG, "tnuts_run: call tnuts_init first");
+  if (n_transitions < 0 || thin < 1) return set_error(e, TNUTS_E_ARG, "tnuts_run: bad n_transitions/thin");
+  TN_CUDA(e, cudaSetDevice(e->device));
+  long long keep = 0;
+  if (first_keep >= 1 && n_transitions >= first_keep) keep = (n_transitions - first_keep) / thin + 1;
+  int rc = ensure_draw_capacity(e, keep > 0 ? keep : 1);
+  if (rc) return rc;
+  e->rp.n_transitions = n_transitions;
+  e->rp.first_keep = first_keep;
+  e->rp.thin = thin;
+  TN_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+  rc = (e->strategy == STRAT_THREAD) ? thread_run(e) : lockstep_run(e);
+  if (rc) return rc;
+  TN_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+  TN_CUDA(e, cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  TN_CUDA(e, cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  e->last_run_seconds = ms * 1e-3;
+  e->n_kept = keep;
+  if (n_kept) *n_kept = keep;
+  return TNUTS_OK;
+}
+
+int tnuts_fetch(tnuts_engine *h, double *params, double *logp, double *stats, double *theta) {
+  Engine *e = (Engine *)h;
+  if (!e || !e->inited) return set_error(e, TNUTS_E_ARG, "tnuts_fetch: nothing to fetch");
+  TN_CUDA(e, cudaSetDevice(e->device));
+  const size_t K = (size_t)e->n_kept, C = (size_t)e->st.C;
+  if (K == 0) return TNUTS_OK;
+  if (params)
+    TN_CUDA(e, cudaMemcpyAsync(params, e->out.params, 8 * K * e->P * C, cudaMemcpyDeviceToHost, e->stream));
+  if (logp)
+    TN_CUDA(e, cudaMemcpyAsync(logp, e->out.logp, 8 * K * 3 * C, cudaMemcpyDeviceToHost, e->stream));
+  if (stats)
+    TN_CUDA(e, cudaMemcpyAsync(stats, e->out.stats, 8 * K * TNUTS_NSTAT * C, cudaMemcpyDeviceToHost, e->stream));
+  if (theta)
+    TN_CUDA(e, cudaMemcpyAsync(theta, e->out.theta, 8 * K * e->D * C, cudaMemcpyDeviceToHost, e->stream));
+  TN_CUDA(e, cudaStreamSynchronize(e->stream));
+  return TNUTS_OK;
+}
+
+// [D][C] device -> [C][D] host
+static int fetch_dc(Engine *e, const double *dev, double *host) {
+  const size_t C = (size_t)e->st.C, D = (size_t)e->D;
+  std::vector<double> tmp(C * D);
+  TN_CUDA(e, cudaMemcpy(tmp.data(), dev, 8 * C * D, cudaMemcpyDeviceToHost));
+  for (size_t d = 0; d < D; ++d)
+    for (size_t c = 0; c < C; ++c) host[c * D + d] = tmp[d * C + c];
+  return TNUTS_OK;
+}
+
+int tnuts_get_theta(tnuts_engine *h, double *theta) {
+  Engine *e = (Engine *)h;
+  if (!e || !e->inited || !theta) return set_error(e, TNUTS_E_ARG, "tnuts_get_theta: bad call");
+  TN_CUDA(e, cudaSetDevice(e->device));
+  return fetch_dc(e, e->st.theta, theta);
+}
+
+int tnuts_get_inv_metric(tnuts_engine *h, double *minv) {
+  Engine *e = (Engine *)h;
+  if (!e || !e->inited || !minv) return set_error(e, TNUTS_E_ARG, "tnuts_get_inv_metric: bad call");
+  TN_CUDA(e, cudaSetDevice(e->device));
+  return fetch_dc(e, e->st.minv, minv);
+}
+
+int tnuts_get_stepsize(tnuts_engine *h, double *eps) {
+  Engine *e = (Engine *)h;
+  if (!e || !e->inited || !eps) return set_error(e, TNUTS_E_ARG, "tnuts_get_stepsize: bad call");
+  TN_CUDA(e, cudaSetDevice(e->device));
+  TN_CUDA(e, cudaMemcpy(eps, e->st.eps, 8 * (size_t)e->st.C, cudaMemcpyDeviceToHost));
+  return TNUTS_OK;
+}
+
+// scratch helper: host -> device copies for the point-wise entry points
+struct Scratch {
+  std::vector<void *> p;
+  ~Scratch() {
+    for (void *q : p) cudaFree(q);
+  }
+  double *put(Engine *e, const double *src, size_t n, int *rc) {
+    double *q = nullptr;
+    if (cudaMalloc((void **)&q, 8 * (n ? n : 1)) != cudaSuccess) {
+      *rc = set_error(e, TNUTS_E_CUDA, "scratch cudaMalloc failed");
+      return nullptr;
+    }
+    p.push_back(q);
+    if (src && cudaMemcpyAsync(q, src, 8 * n, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) {
+      *rc = set_error(e, TNUTS_E_CUDA, "scratch H2D failed");
+      return nullptr;
+    }
+    return q;
+  }
+};
+
+int tnuts_logdensity_and_gradient(tnuts_engine *h, const double *theta, int64_t n, double *lp,
+                                  double *grad) {
+  Engine *e = (Engine *)h;
+  if (!e || !e->has_model || !theta || !lp || n < 0)
+    return set_error(e, TNUTS_E_ARG, "tnuts_logdensity_and_gradient: bad call");
+  if (n == 0) return TNUTS_OK;
+  TN_CUDA(e, cudaSetDevice(e->device));
+  Scratch s;
+  int rc = TNUTS_OK;
+  const size_t D = (size_t)e->D;
+  double *th = s.put(e, theta, (size_t)n * D, &rc);
+  double *dlp = s.put(e, nullptr, (size_t)n, &rc);
+  double *dg = grad ? s.put(e, nullptr, (size_t)n * D, &rc) : nullptr;
+  if (rc) return rc;
+  rc = (e->strategy == STRAT_THREAD) ? thread_point_lpgrad(e, th, n, dlp, dg)
+                                     : lockstep_point_lpgrad(e, th, n, dlp, dg);
+  if (rc) return rc;
+  TN_CUDA(e, cudaMemcpyAsync(lp, dlp, 8 * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+  if (grad) TN_CUDA(e, cudaMemcpyAsync(grad, dg, 8 * (size_t)n * D, cudaMemcpyDeviceToHost, e->stream));
+  TN_CUDA(e, cudaStreamSynchronize(e->stream));
+  return TNUTS_OK;
+}
+
+int tnuts_logdensity(tnuts_engine *h, const double *theta, int64_t n, double *lp) {
+  return tnuts_logdensity_and_gradient(h, theta, n, lp, nullptr);
+}
+
+int tnuts_constrain(tnuts_engine *h, const double *theta, int64_t n, double *params, double *logp) {
+  Engine *e = (Engine *)h;
+  if (!e || !e->has_model || !theta || !params || !logp || n < 0)
+    return set_error(e, TNUTS_E_ARG, "tnuts_constrain: bad call");
+  if (n == 0) return TNUTS_OK;
+  TN_CUDA(e, cudaSetDevice(e->device));
+  Scratch s;
+  int rc = TNUTS_OK;
+  const size_t D = (size_t)e->D;
+  double *th = s.put(e, theta, (size_t)n * D, &rc);
+  double *dp = s.put(e, nullptr, (size_t)n * e->P, &rc);
+  double *dl = s.put(e, nullptr, (size_t)n * 3, &rc);
+  if (rc) return rc;
+  rc = (e->strategy == STRAT_THREAD) ? thread_point_constrain(e, th, n, dp, dl)
+                                     : lockstep_point_constrain(e, th, n, dp, dl);
+  if (rc) return rc;
+  TN_CUDA(e, cudaMemcpyAsync(params, dp, 8 * (size_t)n * e->P, cudaMemcpyDeviceToHost, e->stream));
+  TN_CUDA(e, cudaMemcpyAsync(logp, dl, 8 * (size_t)n * 3, cudaMemcpyDeviceToHost, e->stream));
+  TN_CUDA(e, cudaStreamSynchronize(e->stream));
+  return TNUTS_OK;
+}
+
+int tnuts_leapfrog(tnuts_engine *h, const double *theta, const double *r, const double *minv,
+                   double eps, int32_t L, int64_t n, double *traj_theta, double *traj_r,
+                   double *traj_H) {
+  Engine *e = (Engine *)h;
+  if (!e || !e->has_model || !theta || !r || !minv || L < 0 || n < 0 || !traj_theta || !traj_r || !traj_H)
+    return set_error(e, TNUTS_E_ARG, "tnuts_leapfrog: bad call");
+  if (n == 0) return TNUTS_OK;
+  TN_CUDA(e, cudaSetDevice(e->device));
+  Scratch s;
+  int rc = TNUTS_OK;
+  const size_t D = (size_t)e->D, T = (size_t)n * (L + 1);
+  double *th = s.put(e, theta, (size_t)n * D, &rc);
+  double *dr = s.put(e, r, (size_t)n * D, &rc);
+  double *dm = s.put(e, minv, D, &rc);
+  double *tt = s.put(e, nullptr, T * D, &rc);
+  double *tr = s.put(e, nullptr, T * D, &rc);
+  double *tH = s.put(e, nullptr, T, &rc);
+  if (rc) return rc;
+  rc = (e->strategy == STRAT_THREAD) ? thread_point_leapfrog(e, th, dr, dm, eps, L, n, tt, tr, tH)
+                                     : lockstep_point_leapfrog(e, th, dr, dm, eps, L, n, tt, tr, tH);
+  if (rc) return rc;
+  TN_CUDA(e, cudaMemcpyAsync(traj_theta, tt, 8 * T * D, cudaMemcpyDeviceToHost, e->stream));
+  TN_CUDA(e, cudaMemcpyAsync(traj_r, tr, 8 * T * D, cudaMemcpyDeviceToHost, e->stream));
+  TN_CUDA(e, cudaMemcpyAsync(traj_H, tH, 8 * T, cudaMemcpyDeviceToHost, e->stream));
+  TN_CUDA(e, cudaStreamSynchronize(e->stream));
+  return TNUTS_OK;
+}
+
+// ---- state blob: header + every ChainState array, in a fixed order ----
+struct BlobHeader {
+  uint32_t magic, version;
+  int32_t C, D, family, algorithm;
+  int64_t n_adapts;
+  uint64_t seed;
+};
+static constexpr uint32_t kBlobMagic = 0x544e5554u;  // "TUNT"
+
+static size_t blob_bytes(const Engine *e) {
+  const size_t C = (size_t)e->st.C, D = (size_t)e->D;
+  return sizeof(BlobHeader) + 8 * (5 * D * C + 6 * C) + 8 * 5 * C;
+}
+
+int tnuts_get_state(tnuts_engine *h, void *blob, size_t *nbytes) {
+  Engine *e = (Engine *)h;
+  if (!e || !e->inited || !nbytes) return set_error(e, TNUTS_E_ARG, "tnuts_get_state: bad call");
+  const size_t need = blob_bytes(e);
+  if (!blob) {
+    *nbytes = need;
+    return TNUTS_OK;
+  }
+  if (*nbytes < need) return set_error(e, TNUTS_E_ARG, "tnuts_get_state: buffer too small");
+  TN_CUDA(e, cudaSetDevice(e->device));
+  const size_t C = (size_t)e->st.C, D = (size_t)e->D;
+  BlobHeader hd{kBlobMagic, 1u, (int32_t)C, (int32_t)D, e->model.family, e->cfg.algorithm,
+                e->cfg.n_adapts, e->cfg.seed};
+  char *p = (char *)blob;
+  std::memcpy(p, &hd, sizeof(hd));
+  p += sizeof(hd);
+  const ChainState &st = e->st;
+  const void *arrs[] = {st.theta, st.grad, st.minv, st.wf_mean, st.wf_m2};
+  for (const void *a : arrs) {
+    TN_CUDA(e, cudaMemcpy(p, a, 8 * D * C, cudaMemcpyDeviceToHost));
+    p += 8 * D * C;
+  }
+  const void *sc[] = {st.lp, st.eps, st.da_mu, st.da_xbar, st.da_hbar, st.da_eps,
+                      st.da_m, st.wf_n, st.iter, st.n_grad};
+  for (const void *a : sc) {
+    TN_CUDA(e, cudaMemcpy(p, a, 8 * C, cudaMemcpyDeviceToHost));
+    p += 8 * C;
+  }
+  // 11th scalar slot: status/init_tries are not part of the resumable state
+  std::memset(p, 0, 8 * C);
+  *nbytes = need;
+  return TNUTS_OK;
+}
+
+int tnuts_set_state(tnuts_engine *h, const void *blob, size_t nbytes) {
+  Engine *e = (Engine *)h;
+  if (!e || !e->has_model || !blob) return set_error(e, TNUTS_E_ARG, "tnuts_set_state: bad call");
+  if (nbytes < blob_bytes(e)) return set_error(e, TNUTS_E_ARG, "tnuts_set_state: blob too small");
+  BlobHeader hd;
+  std::memcpy(&hd, blob, sizeof(hd));
+  if (hd.magic != kBlobMagic || hd.C != e->st.C || hd.D != e->D || hd.family != e->model.family)
+    return set_error(e, TNUTS_E_ARG, "tnuts_set_state: blob does not match this engine");
+  TN_CUDA(e, cudaSetDevice(e->device));
+  const size_t C = (size_t)e->st.C, D = (size_t)e->D;
+  const char *p = (const char *)blob + sizeof(hd);
+  ChainState &st = e->st;
+  void *arrs[] = {st.theta, st.grad, st.minv, st.wf_mean, st.wf_m2};
+  for (void *a : arrs) {
+    TN_CUDA(e, cudaMemcpy(a, p, 8 * D * C, cudaMemcpyHostToDevice));
+    p += 8 * D * C;
+  }
+  void *sc[] = {st.lp, st.eps, st.da_mu, st.da_xbar, st.da_hbar, st.da_eps,
+                st.da_m, st.wf_n, st.iter, st.n_grad};
+  for (void *a : sc) {
+    TN_CUDA(e, cudaMemcpy(a, p, 8 * C, cudaMemcpyHostToDevice));
+    p += 8 * C;
+  }
+  TN_CUDA(e, cudaMemset(st.status, 0, sizeof(int) * C));
+  e->inited = true;
+  e->n_kept = 0;
+  return TNUTS_OK;
+}
+
+int tnuts_diagnostics(tnuts_engine *h, double *rhat, double *ess_bulk) {
+  Engine *e = (Engine *)h;
+  if (!e || !e->inited || e->n_kept < 4)
+    return set_error(e, TNUTS_E_ARG, "tnuts_diagnostics: need >= 4 kept draws");
+  TN_CUDA(e, cudaSetDevice(e->device));
+  return diagnostics_run(e, rhat, ess_bulk);
+}
+
+static int64_t sum_ll(const Engine *e, const long long *dev) {
+  std::vector<long long> v((size_t)e->st.C);
+  if (cudaMemcpy(v.data(), dev, 8 * v.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  long long s = 0;
+  for (long long x : v) s += x;
+  return s;
+}
+
+int64_t tnuts_num_grad_evals(const tnuts_engine *h) {
+  const Engine *e = (const Engine *)h;
+  if (!e || !e->has_model) return -1;
+  cudaSetDevice(e->device);
+  return sum_ll(e, e->st.n_grad);
+}
+
+int64_t tnuts_num_divergences(const tnuts_engine *h) {
+  const Engine *e = (const Engine *)h;
+  if (!e || !e->inited || e->n_kept == 0) return 0;
+  cudaSetDevice(e->device);
+  const size_t K = (size_t)e->n_kept, C = (size_t)e->st.C;
+  std::vector<double> col(C);
+  long long s = 0;
+  for (size_t k = 0; k < K; ++k) {
+    if (cudaMemcpy(col.data(), e->out.stats + (k * TNUTS_NSTAT + ST_NUMERR) * C, 8 * C,
+                   cudaMemcpyDeviceToHost) != cudaSuccess)
+      return -1;
+    for (double v : col) s += (v != 0.0);
+  }
+  return s;
+}
+
+int64_t tnuts_num_kernel_launches(const tnuts_engine *h) {
+  return h ? ((const Engine *)h)->launches : -1;
+}
+double tnuts_device_seconds(const tnuts_engine *h) {
+  return h ? ((const Engine *)h)->last_run_seconds : -1.0;
+}
+int tnuts_init_tries_max(const tnuts_engine *h) {
+  const Engine *e = (const Engine *)h;
+  if (!e || !e->has_model) return -1;
+  cudaSetDevice(e->device);
+  std::vector<int> v((size_t)e->st.C);
+  if (cudaMemcpy(v.data(), e->st.init_tries, 4 * v.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  int m = 0;
+  for (int x : v) m = x > m ? x : m;
+  return m;
+}
+
+int tnuts_host_alloc(void **p, size_t nbytes) {
+  if (!p) return TNUTS_E_ARG;
+  return cudaMallocHost(p, nbytes) == cudaSuccess ? TNUTS_OK : TNUTS_E_CUDA;
+}
+int tnuts_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? TNUTS_OK : TNUTS_E_CUDA; }
+
+}  // extern "C"

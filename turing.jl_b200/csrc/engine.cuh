@@ -1,0 +1,95 @@
+// engine.cuh -- host-side engine object behind the C ABI (include/tnuts.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "models.cuh"
+
+struct ncclComm;
+
+namespace tnuts {
+
+struct LockstepState;  // lockstep.cu
+struct DiagWork;       // diagnostics.cu
+
+enum Strategy { STRAT_AUTO = 0, STRAT_THREAD = 1, STRAT_LOCKSTEP = 2 };
+
+struct Engine {
+  tnuts_config cfg{};
+  std::string err;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool has_model = false, inited = false;
+  int strategy = STRAT_THREAD;
+
+  // model
+  ModelDev model{};        // device pointers
+  SmallData small{};       // constant-bank copy for tiny families
+  std::vector<void *> model_allocs;
+  int D = 0, P = 0;
+
+  // chain state
+  ChainState st{};
+  std::vector<void *> state_allocs;
+  RunParams rp{};
+
+  // kept draws
+  DrawBuffers out{};
+  long long n_kept = 0;
+
+  // counters
+  long long launches = 0;
+  double last_run_seconds = 0.0;
+
+  LockstepState *ls = nullptr;
+  DiagWork *diag = nullptr;
+
+  // multi-GPU
+  ncclComm *comm = nullptr;
+  int world = 1, rank = 0;
+};
+
+// error helpers ---------------------------------------------------------------------------
+int set_error(Engine *e, int code, const std::string &msg);
+#define TN_CUDA(e, call)                                                                      \
+  do {                                                                                        \
+    cudaError_t _s = (call);                                                                  \
+    if (_s != cudaSuccess)                                                                    \
+      return ::tnuts::set_error((e), TNUTS_E_CUDA,                                            \
+                                std::string(#call) + ": " + cudaGetErrorString(_s));          \
+  } while (0)
+
+// small-family (thread-per-chain) entry points, chain_kernels.cu
+bool thread_strategy_supported(const Engine *e);
+int thread_init(Engine *e, const double *theta0_dev);
+int thread_run(Engine *e);
+int thread_point_lpgrad(Engine *e, const double *theta_dev, long long n, double *lp_dev,
+                        double *grad_dev);
+int thread_point_constrain(Engine *e, const double *theta_dev, long long n, double *params_dev,
+                           double *logp_dev);
+int thread_point_leapfrog(Engine *e, const double *theta_dev, const double *r_dev,
+                          const double *minv_dev, double eps, int L, long long n, double *tt_dev,
+                          double *tr_dev, double *tH_dev);
+
+// lock-step strategy, lockstep.cu
+int lockstep_create(Engine *e);
+void lockstep_destroy(Engine *e);
+int lockstep_init(Engine *e, const double *theta0_dev);
+int lockstep_run(Engine *e);
+int lockstep_point_lpgrad(Engine *e, const double *theta_dev, long long n, double *lp_dev,
+                          double *grad_dev);
+int lockstep_point_constrain(Engine *e, const double *theta_dev, long long n, double *params_dev,
+                             double *logp_dev);
+int lockstep_point_leapfrog(Engine *e, const double *theta_dev, const double *r_dev,
+                            const double *minv_dev, double eps, int L, long long n,
+                            double *tt_dev, double *tr_dev, double *tH_dev);
+
+// diagnostics.cu
+int diagnostics_run(Engine *e, double *rhat_host, double *ess_host);
+void diagnostics_destroy(Engine *e);
+
+}  // namespace tnuts

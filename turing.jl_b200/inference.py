@@ -1,0 +1,258 @@
+"""`sample(model, NUTS(delta), MCMCThreads(), N, n_chains)` -- host mirror of the reference's
+entry points, driving the CUDA engine through the C ABI.
+
+Mirrors, with the same names, argument meaning and error behaviour:
+  sample(rng, model, ::AdaptiveHamiltonian, N; ...)            src/mcmc/hmc.jl:85-154
+  sample(rng, model, spl, ensemble, N, n_chains; ...)          src/mcmc/abstractmcmc.jl:133-166
+  AbstractMCMC.mcmcsample loop (discard_initial, thinning)     SURVEY.md App. C
+  post_sample_hook (divergence warning)                        src/mcmc/hmc.jl:476-486
+  loadstate / initial_state resume                             src/mcmc/hmc.jl:135-152
+The difference: all chains advance inside one engine call instead of one task per chain.
+"""
+import threading
+import time
+import warnings
+
+import numpy as np
+
+from . import _lib
+from .chains import INTERNALS, Chains
+from .engine import Engine
+from .samplers import (Hamiltonian, InitFromParams, InitFromUniform, MCMCThreads)
+
+_DEFAULT_RNG = np.random.default_rng()
+
+
+def _check_model(model, spl):
+    """Turing._check_model (src/common.jl:31-46): HMC-family samplers reject discrete variables."""
+    if isinstance(spl, Hamiltonian) and model.has_discrete_variables():
+        raise ValueError("Discrete variables are not supported by HMC/NUTS samplers")
+
+
+def _seed_from(rng, seed):
+    if seed is not None:
+        return int(seed)
+    if rng is None:
+        rng = _DEFAULT_RNG
+    if isinstance(rng, (int, np.integer)):
+        return int(rng)
+    return int(rng.integers(0, 2 ** 63 - 1))
+
+
+def _resolve_initial_params(model, initial_params, n_chains):
+    """-> [n_chains, D] linked-space array, or None for InitFromUniform."""
+    if initial_params is None or isinstance(initial_params, InitFromUniform):
+        return None
+    if not isinstance(initial_params, (list, tuple)) or len(initial_params) != n_chains:
+        raise ValueError("`initial_params` must be an AbstractVector of length `n_chains`; "
+                         "one element per chain")
+    if all(ip is None or isinstance(ip, InitFromUniform) for ip in initial_params):
+        return None
+    rows = []
+    for ip in initial_params:
+        if isinstance(ip, InitFromParams):
+            ip = ip.params
+        if isinstance(ip, dict):
+            vec = []
+            for n in model.param_names:
+                base = n.split("[")[0]
+                if n in ip:
+                    vec.append(ip[n])
+                elif base in ip:
+                    vec.append(np.ravel(ip[base])[int(n.split("[")[1][:-1]) - 1])
+                else:
+                    raise ValueError("initial_params is missing a value for %s" % n)
+            ip = vec
+        if ip is None or isinstance(ip, InitFromUniform):
+            raise ValueError("mixing InitFromUniform with explicit initial_params is not supported")
+        rows.append(model.link(np.asarray(ip, dtype=np.float64)))
+    return np.stack(rows)
+
+
+def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_params=None,
+           initial_state=None, nadapts=None, discard_adapt=True, discard_initial=-1, thinning=1,
+           save_state=False, progress=False, verbose=True, check_model=True, devices=None,
+           diagnostics=False, strategy=0, keep_engine=False):
+    """sample(model, spl, N) | sample(model, spl, ensemble, N, n_chains)."""
+    if len(args) == 1:
+        N, n_chains, single = int(args[0]), 1, True
+        if initial_params is not None and not isinstance(initial_params, (list, tuple)):
+            initial_params = [initial_params]
+        elif initial_params is not None and not isinstance(initial_params[0], (InitFromParams, dict, list, tuple, np.ndarray)):
+            initial_params = [initial_params]
+    elif len(args) == 3:
+        if not isinstance(args[0], MCMCThreads):
+            raise TypeError("sample(model, spl, ensemble, N, n_chains): bad ensemble")
+        N, n_chains, single = int(args[1]), int(args[2]), False
+    else:
+        raise TypeError("sample(model, spl, N) or sample(model, spl, ensemble, N, n_chains)")
+    if check_model:
+        _check_model(model, spl)
+    if N < 1:
+        raise ValueError("N must be >= 1")
+
+    # --- src/mcmc/hmc.jl:104-152 ---
+    if initial_state is None:
+        na = spl.n_adapts if nadapts is None else nadapts
+        if spl.adaptive:
+            _nadapts = min(1000, N // 2) if na == -1 else int(na)
+        else:
+            _nadapts = 0
+        if spl.adaptive and discard_initial == -1:
+            _discard = _nadapts if discard_adapt else 0
+        else:
+            _discard = max(0, discard_initial)
+    else:
+        _nadapts, _discard = 0, 0
+    theta0 = _resolve_initial_params(model, initial_params, n_chains) if initial_state is None else None
+    seed64 = _seed_from(rng, seed)
+    if initial_state is not None:
+        seed64 = initial_state["seed"]
+
+    devices = list(devices) if devices else [0]
+    ndev = len(devices)
+    if n_chains < ndev:
+        devices, ndev = devices[:n_chains], n_chains
+    bounds = [n_chains * i // ndev for i in range(ndev + 1)]
+
+    t_start = time.perf_counter()
+    engines = []
+    for i, dev in enumerate(devices):
+        engines.append(Engine(model, spl, bounds[i + 1] - bounds[i], _nadapts, seed64, device=dev,
+                              chain_offset=bounds[i], strategy=strategy))
+    results = [None] * ndev
+    errors = [None] * ndev
+
+    def work(i):
+        try:
+            e = engines[i]
+            lo, hi = bounds[i], bounds[i + 1]
+            first = None
+            if initial_state is not None:
+                e.set_state(initial_state["blobs"][i])
+                n_tr, first_keep = N * thinning, thinning
+            else:
+                e.init(None if theta0 is None else theta0[lo:hi])
+                if _discard == 0:
+                    # first sample = initial parameters, no sampler stats (test/mcmc/hmc.jl:173-197)
+                    th = e.theta()
+                    p, lp = e.constrain(th)
+                    first = (p, lp)
+                    n_tr, first_keep = (N - 1) * thinning, thinning
+                else:
+                    n_tr, first_keep = _discard + (N - 1) * thinning, _discard
+            if n_tr > 0:
+                e.run(n_tr, first_keep, thinning)
+                out = e.fetch()
+            else:
+                e.n_kept = 0
+                out = dict(params=np.empty((0, e.P, e.C)), logp=np.empty((0, 3, e.C)),
+                           stats=np.empty((0, _lib.NSTAT, e.C)))
+            diag = e.diagnostics() if (diagnostics and ndev == 1 and e.n_kept >= 4) else None
+            results[i] = (first, out, diag, e.grad_evals, e.device_seconds, e.stepsize(),
+                          e.get_state() if save_state else None)
+        except Exception as ex:  # re-raised on the caller's thread
+            errors[i] = ex
+
+    if ndev == 1:
+        work(0)
+    else:
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(ndev)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+    for ex in errors:
+        if ex is not None:
+            for e in engines:
+                e.close()
+            if isinstance(ex, _lib.TnutsError) and ex.code == _lib.E_INIT:
+                raise RuntimeError(ex.message) from None
+            raise ex
+    wall = time.perf_counter() - t_start
+
+    # --- bundle_samples: (iterations x names x chains) ---
+    P = model.D
+    nint = len(INTERNALS)
+    value = np.full((N, P + nint, n_chains), np.nan)
+    for i in range(ndev):
+        first, out, *_ = results[i]
+        lo, hi = bounds[i], bounds[i + 1]
+        row = 0
+        if first is not None:
+            value[0, :P, lo:hi] = first[0].T
+            value[0, P:P + 3, lo:hi] = first[1].T
+            row = 1
+        K = out["params"].shape[0]
+        value[row:row + K, :P, lo:hi] = out["params"]
+        value[row:row + K, P:P + 3, lo:hi] = out["logp"]
+        value[row:row + K, P + 3:P + 3 + _lib.NSTAT, lo:hi] = out["stats"]
+        value[row:row + K, P + 3 + _lib.NSTAT, lo:hi] = 1.0 if spl.algorithm == 0 else out["stats"][:, 6, :]
+        value[row:row + K, P + 4 + _lib.NSTAT, lo:hi] = out["stats"][:, 8, :]
+    info = {
+        "sampling_time": np.full(n_chains, wall),
+        "wall_seconds": wall,
+        "device_seconds": max(r[4] for r in results),
+        "grad_evals": int(sum(r[3] for r in results)),
+        "step_size": np.concatenate([r[5] for r in results]),
+        "nadapts": _nadapts, "discard_initial": _discard, "thinning": thinning, "seed": seed64,
+    }
+    if results[0][2] is not None:
+        info["rhat"], info["ess_bulk"] = results[0][2]
+    if save_state:
+        info["samplerstate"] = {"blobs": [r[6] for r in results], "seed": seed64,
+                                "bounds": bounds, "devices": devices}
+    chain = chain_type(value, model.param_names, INTERNALS, info)
+    if keep_engine:
+        chain.info["engines"] = engines
+    else:
+        for e in engines:
+            e.close()
+    post_sample_hook(chain, spl, verbose=verbose)
+    return chain
+
+
+def post_sample_hook(chain, spl, verbose=True):
+    """src/mcmc/hmc.jl:476-486"""
+    n_div = int(np.nansum(chain["numerical_error"]))
+    if verbose and n_div > 0:
+        warnings.warn("There were %d divergent transitions. Consider reparameterising your model or "
+                      "using a smaller step size. For adaptive samplers such as NUTS and HMCDA, "
+                      "consider increasing `target_accept`." % n_div)
+
+
+def loadstate(chain):
+    """Turing.Inference.loadstate (src/mcmc/Inference.jl:75-77)"""
+    st = chain.info.get("samplerstate")
+    if st is None:
+        raise ValueError("the chain object does not contain the final state of the sampler; "
+                         "sample with `save_state=true`")
+    return st
+
+
+class LogDensityFunction:
+    """Engine-backed object with the LogDensityProblems interface (dimension, logdensity,
+    logdensity_and_gradient) so the host can cross-check it against
+    `DynamicPPL.LogDensityFunction(model, getlogjoint_internal, LinkAll())`
+    (src/mcmc/hmc.jl:170-182)."""
+
+    def __init__(self, model, device=0, strategy=0):
+        from .samplers import NUTS
+        self.model = model
+        self._e = Engine(model, NUTS(), 1, 0, 0, device=device, strategy=strategy)
+
+    def dimension(self):
+        return self._e.D
+
+    def logdensity(self, theta):
+        lp = self._e.logdensity(theta)
+        return lp[0] if np.ndim(theta) == 1 else lp
+
+    def logdensity_and_gradient(self, theta):
+        lp, g = self._e.logdensity_and_gradient(theta)
+        if np.ndim(theta) == 1:
+            return lp[0], g[0]
+        return lp, g
+
+    def capabilities(self):
+        return 1  # LogDensityOrder{1}: gradient available

@@ -1,0 +1,212 @@
+"""Registered model families: the host-side descriptor the engine needs instead of Turing's
+opaque `DynamicPPL.Model` closure (SURVEY.md section 7.3 "black-box model vs registered family").
+
+Each class mirrors a Turing `@model` (quoted in its docstring), carries the observed data,
+names its parameters in model statement order (vector parameters flattened as `x[1], x[2]`,
+test/mcmc/chains.jl:233-251) and knows the link transform (`Bijectors`: positive support
+links by log) so that user-space `initial_params` can be mapped to linked space.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+GDEMO, LINREG, EIGHT_SCHOOLS, LOGISTIC, HIER_LINREG, STD_NORMAL = range(6)
+
+
+class Model:
+    family = -1
+    #: names of parameters whose support is (0, inf) -> linked by log
+    positive = ()
+
+    def __init__(self):
+        self.X = self.y = self.sigma = self.group = None
+        self.N = 0
+        self.G = 0
+        self.hyper = ()
+
+    # --- interface used by sample() ---
+    @property
+    def D(self):
+        return len(self.param_names)
+
+    def has_discrete_variables(self):
+        """Turing._check_model (src/common.jl:31-46) rejects discrete variables for HMC."""
+        return False
+
+    def link(self, params):
+        """user-space (constrained) vector -> linked space."""
+        p = np.array(params, dtype=np.float64, copy=True)
+        for i, n in enumerate(self.param_names):
+            if n in self.positive:
+                if not p[..., i].min() > 0:
+                    raise ValueError("initial value of %s must be positive" % n)
+                p[..., i] = np.log(p[..., i])
+        return p
+
+    def invlink(self, theta):
+        t = np.array(theta, dtype=np.float64, copy=True)
+        for i, n in enumerate(self.param_names):
+            if n in self.positive:
+                t[..., i] = np.exp(t[..., i])
+        return t
+
+    def c_struct(self):
+        """tnuts_model with host pointers into this object's arrays (kept alive by self)."""
+        m = _lib.TnutsModel()
+        m.family, m.D, m.N, m.G = self.family, self.D, int(self.N), int(self.G)
+        dp = C.POINTER(C.c_double)
+        m.X = self.X.ctypes.data_as(dp) if self.X is not None else None
+        m.y = self.y.ctypes.data_as(dp) if self.y is not None else None
+        m.sigma = self.sigma.ctypes.data_as(dp) if self.sigma is not None else None
+        m.group = (self.group.ctypes.data_as(C.POINTER(C.c_int32))
+                   if self.group is not None else None)
+        for i, h in enumerate(self.hyper):
+            m.hyper[i] = float(h)
+        return m
+
+    def data_nbytes(self):
+        return sum(a.nbytes for a in (self.X, self.y, self.sigma, self.group) if a is not None)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class GDemo(Model):
+    """@model function gdemo(x, y)
+           s ~ InverseGamma(2, 3); m ~ Normal(0, sqrt(s))
+           x ~ Normal(m, sqrt(s)); y ~ Normal(m, sqrt(s))
+       end                                   (test/test_utils/models.jl:15-21)"""
+    family = GDEMO
+    positive = ("s",)
+    param_names = ("s", "m")
+
+    def __init__(self, x=1.5, y=2.0, alpha=2.0, beta=3.0):
+        super().__init__()
+        self.y = _f64([x, y] if np.isscalar(x) else np.concatenate([np.ravel(x), np.ravel(y)]))
+        self.N = self.y.size
+        self.hyper = (alpha, beta)
+
+
+def gdemo_default():
+    return GDemo(1.5, 2.0)
+
+
+class LinearRegression(Model):
+    """@model function linear_regression(x)
+           alpha ~ Normal(0, 1); beta ~ Normal(0, 1)
+           sigma2 ~ truncated(Cauchy(0, 3); lower=0)
+           y ~ MvNormal(alpha .+ beta .* x, sigma2 * I)
+       end                                   (README.md:38-47)"""
+    family = LINREG
+    positive = ("σ²",)
+    param_names = ("α", "β", "σ²")
+
+    def __init__(self, x, y, prior_sd=1.0, cauchy_scale=3.0):
+        super().__init__()
+        self.X, self.y = _f64(x), _f64(y)
+        self.N = self.y.size
+        self.hyper = (prior_sd, cauchy_scale)
+
+
+class EightSchools(Model):
+    """@model function eight_schools_nc(y, sigma)
+           mu ~ Normal(0, 5); tau ~ truncated(Cauchy(0, 5); lower=0)
+           theta_t ~ MvNormal(zeros(J), I)
+           y ~ MvNormal(mu .+ tau .* theta_t, Diagonal(sigma .^ 2))
+       end                                   (BASELINE.json configs[1])"""
+    family = EIGHT_SCHOOLS
+    positive = ("τ",)
+    Y = (28.0, 8.0, -3.0, 7.0, -1.0, 1.0, 18.0, 12.0)
+    SIGMA = (15.0, 10.0, 16.0, 11.0, 9.0, 11.0, 10.0, 18.0)
+
+    def __init__(self, y=Y, sigma=SIGMA, mu_sd=5.0, cauchy_scale=5.0):
+        super().__init__()
+        self.y, self.sigma = _f64(y), _f64(sigma)
+        self.N = self.y.size
+        self.hyper = (mu_sd, cauchy_scale)
+        self.param_names = ("μ", "τ") + tuple("θ̃[%d]" % (j + 1) for j in range(self.N))
+
+
+class LogisticRegression(Model):
+    """@model function logreg(X, y)
+           beta ~ MvNormal(zeros(D), sd^2 * I)
+           y .~ BernoulliLogit.(X * beta)
+       end                                   (BASELINE.json configs[2], configs[4])"""
+    family = LOGISTIC
+
+    def __init__(self, X, y, prior_sd=1.0):
+        super().__init__()
+        self.X, self.y = _f64(X), _f64(y)
+        self.N, d = self.X.shape
+        self.hyper = (prior_sd,)
+        self.param_names = tuple("β[%d]" % (j + 1) for j in range(d))
+
+
+class HierLinearRegression(Model):
+    """@model function hier_linreg(x, y, g, G)
+           mu_a ~ Normal(0, 10); mu_b ~ Normal(0, 10)
+           sigma_a ~ truncated(Normal(0, 5); lower=0); sigma_b ~ ...; sigma_y ~ ...
+           a ~ filldist(Normal(mu_a, sigma_a), G); b ~ filldist(Normal(mu_b, sigma_b), G)
+           y ~ MvNormal(a[g] .+ b[g] .* x, sigma_y^2 * I)
+       end                                   (BASELINE.json configs[3])"""
+    family = HIER_LINREG
+    positive = ("σ_a", "σ_b", "σ_y")
+
+    def __init__(self, x, y, group, n_groups, mu_sd=10.0, sigma_sd=5.0):
+        super().__init__()
+        self.X, self.y = _f64(x), _f64(y)
+        self.group = np.ascontiguousarray(group, dtype=np.int32)
+        self.N, self.G = self.y.size, int(n_groups)
+        self.hyper = (mu_sd, sigma_sd)
+        self.param_names = (("μ_a", "μ_b", "σ_a", "σ_b", "σ_y")
+                            + tuple("a[%d]" % (g + 1) for g in range(self.G))
+                            + tuple("b[%d]" % (g + 1) for g in range(self.G)))
+
+
+class StdNormal(Model):
+    """@model f() = x ~ MvNormal(zeros(D), I)     (test/main.jl:39-48 for D = 1)"""
+    family = STD_NORMAL
+
+    def __init__(self, D=1):
+        super().__init__()
+        self.param_names = ("x",) if D == 1 else tuple("x[%d]" % (i + 1) for i in range(D))
+
+
+# ---- synthetic data of the BASELINE.json configs ----
+def config1_linear_regression(seed=0):
+    rng = np.random.default_rng(seed)
+    x, y = rng.random(10), rng.random(10)
+    return LinearRegression(x, y)
+
+
+def config2_eight_schools():
+    return EightSchools()
+
+
+def synthetic_logistic(N, D, seed=1):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((N, D))
+    beta = rng.standard_normal(D) * (2.0 / np.sqrt(D))
+    y = (rng.random(N) < 1.0 / (1.0 + np.exp(-(X @ beta)))).astype(np.float64)
+    return LogisticRegression(X, y)
+
+
+def config3_logistic(N=100_000, D=100, seed=1):
+    return synthetic_logistic(N, D, seed)
+
+
+def synthetic_hier(G, n_per, seed=2):
+    rng = np.random.default_rng(seed)
+    a = 1.0 + 0.7 * rng.standard_normal(G)
+    b = -0.5 + 0.4 * rng.standard_normal(G)
+    group = np.repeat(np.arange(G, dtype=np.int32), n_per)
+    x = rng.standard_normal(G * n_per)
+    y = a[group] + b[group] * x + 0.8 * rng.standard_normal(G * n_per)
+    return HierLinearRegression(x, y, group, G)
+
+
+def config4_hier(G=1000, n_per=100, seed=2):
+    return synthetic_hier(G, n_per, seed)

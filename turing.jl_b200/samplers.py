@@ -1,0 +1,84 @@
+"""Sampler structs and ensemble markers with the reference's names, defaults and argument
+meaning (src/mcmc/hmc.jl:59-80 HMC, :285-327 HMCDA, :352-402 NUTS; src/Turing.jl:105-107)."""
+
+
+class Hamiltonian:
+    """`allow_discrete_variables = false` (src/mcmc/hmc.jl:4); InitFromUniform (:82)."""
+    algorithm = -1
+    adaptive = False
+
+
+class NUTS(Hamiltonian):
+    """NUTS()                     -> n_adapts=-1, delta=0.65          (hmc.jl:400-402)
+    NUTS(delta)                   -> n_adapts=-1                       (hmc.jl:389-398)
+    NUTS(n_adapts, delta; max_depth=10, Delta_max=1000.0, init_eps=0.0) (hmc.jl:377-387)"""
+    algorithm = 0
+    adaptive = True
+
+    def __init__(self, *args, max_depth=10, Delta_max=1000.0, init_eps=0.0, metricT="diag"):
+        if len(args) == 0:
+            n_adapts, delta = -1, 0.65
+        elif len(args) == 1:
+            if not isinstance(args[0], float):
+                raise TypeError("NUTS(delta): delta must be a Float64 (use NUTS(n_adapts, delta))")
+            n_adapts, delta = -1, args[0]
+        elif len(args) == 2:
+            n_adapts, delta = int(args[0]), float(args[1])
+        else:
+            raise TypeError("NUTS takes at most (n_adapts, delta)")
+        if metricT != "diag":
+            raise NotImplementedError("only DiagEuclideanMetric (the NUTS default, hmc.jl:383) "
+                                      "is implemented by the engine")
+        self.n_adapts, self.delta = n_adapts, float(delta)
+        self.max_depth, self.Delta_max, self.eps = int(max_depth), float(Delta_max), float(init_eps)
+
+
+class HMC(Hamiltonian):
+    """HMC(eps, n_leapfrog): static trajectory, no adaptation (hmc.jl:59-80)."""
+    algorithm = 1
+    adaptive = False
+
+    def __init__(self, eps, n_leapfrog):
+        self.eps, self.n_leapfrog = float(eps), int(n_leapfrog)
+        self.n_adapts, self.delta = 0, 0.0
+        self.max_depth, self.Delta_max = 10, 1000.0
+
+
+class HMCDA(Hamiltonian):
+    """HMCDA(n_adapts, delta, lambda; init_eps=0.0) / HMCDA(delta, lambda) (hmc.jl:285-327)."""
+    algorithm = 2
+    adaptive = True
+
+    def __init__(self, *args, init_eps=0.0):
+        if len(args) == 2:
+            n_adapts, delta, lam = -1, args[0], args[1]
+        elif len(args) == 3:
+            n_adapts, delta, lam = args
+        else:
+            raise TypeError("HMCDA(n_adapts, delta, lambda) or HMCDA(delta, lambda)")
+        self.n_adapts, self.delta, self.lam = int(n_adapts), float(delta), float(lam)
+        self.eps = float(init_eps)
+        self.max_depth, self.Delta_max = 10, 1000.0
+
+
+class MCMCThreads:
+    """all chains advance together on the GPU(s)"""
+
+
+class MCMCSerial(MCMCThreads):
+    pass
+
+
+class MCMCDistributed(MCMCThreads):
+    pass
+
+
+class InitFromUniform:
+    """theta ~ U(-2, 2) in linked space (HISTORY.md:689; src/mcmc/hmc.jl:82)"""
+
+
+class InitFromParams:
+    """user-space (constrained) initial values: mapping name -> value, or a vector in model order"""
+
+    def __init__(self, params):
+        self.params = params
