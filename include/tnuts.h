@@ -140,6 +140,15 @@ int tnuts_run(tnuts_engine *e, int64_t n_transitions, int64_t first_keep, int64_
  *   theta  [n_kept][D][n_chains]   linked-space draws */
 int tnuts_fetch(tnuts_engine *e, double *params, double *logp, double *stats, double *theta);
 
+/* the whole kept-draw array in one contiguous copy: [n_kept][ncol][n_chains] with
+ * ncol = tnuts_num_columns() = P + 3 + TNUTS_NSTAT (params | logp | stats): this IS the
+ * (iterations x names x chains) array of MCMCChains.Chains in C order. */
+int tnuts_num_columns(const tnuts_engine *e);
+int tnuts_fetch_draws(tnuts_engine *e, double *draws);
+
+/* engine options: "keep_theta" (0/1, default 0) keeps linked-space draws for tnuts_fetch */
+int tnuts_set_option(tnuts_engine *e, const char *name, double value);
+
 /* current linked-space position of every chain, [n_chains][D] row-major */
 int tnuts_get_theta(tnuts_engine *e, double *theta);
 /* constrained parameters + user-space log-probs of arbitrary points: theta [n][D],
@@ -173,6 +182,7 @@ int64_t tnuts_num_grad_evals(const tnuts_engine *e);    /* summed over local cha
 int64_t tnuts_num_divergences(const tnuts_engine *e);   /* kept draws with numerical_error */
 int64_t tnuts_num_kernel_launches(const tnuts_engine *e);
 double tnuts_device_seconds(const tnuts_engine *e);     /* CUDA-event time of last tnuts_run */
+double tnuts_init_device_seconds(const tnuts_engine *e);/* CUDA-event time of last tnuts_init */
 int tnuts_init_tries_max(const tnuts_engine *e);        /* worst chain's init attempts  */
 
 /* multi-GPU: NCCL communicator for row sharding and cross-GPU diagnostics.

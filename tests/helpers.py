@@ -1,0 +1,52 @@
+"""shared test helpers: the same data as a host model descriptor and as an oracle model"""
+import json
+import os
+
+import numpy as np
+
+import oracle as O
+import turing_jl_b200 as T
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "lpgrad_golden.json")
+
+
+def oracle_of(model):
+    return O.OracleModel(model.family, D=model.D, N=model.N, G=model.G, X=model.X, y=model.y,
+                         sigma=model.sigma, group=model.group, hyper=model.hyper)
+
+
+def model_from_golden(case):
+    d, name = case["data"], case["name"]
+    if name == "gdemo":
+        return T.GDemo(d["y"][0], d["y"][1], *d["hyper"])
+    if name == "linreg":
+        return T.LinearRegression(d["X"], d["y"], *d["hyper"])
+    if name == "eight_schools":
+        return T.EightSchools(d["y"], d["sigma"], *d["hyper"])
+    if name == "logistic":
+        return T.LogisticRegression(np.array(d["X"]), d["y"], *d["hyper"])
+    if name == "hier":
+        return T.HierLinearRegression(d["X"], d["y"], d["group"], d["G"], *d["hyper"])
+    if name == "std_normal":
+        return T.StdNormal(len(case["points"][0]["theta"]))
+    raise KeyError(name)
+
+
+def golden_cases():
+    with open(GOLDEN) as f:
+        return json.load(f)
+
+
+def small_models():
+    return {
+        "gdemo": T.gdemo_default(),
+        "linreg": T.models.config1_linear_regression(),
+        "eight_schools": T.EightSchools(),
+    }
+
+
+def oracle_config(spl, n_adapts, seed, mode=1):
+    return O.make_config(delta=spl.delta, max_depth=spl.max_depth, delta_max=spl.Delta_max,
+                         init_eps=spl.eps, n_adapts=n_adapts, seed=seed, sampler_mode=mode,
+                         algorithm=spl.algorithm, n_leapfrog=getattr(spl, "n_leapfrog", 0),
+                         lambda_=getattr(spl, "lam", 0.0))

@@ -1,0 +1,156 @@
+"""GPU: the CUDA engine, called through the C ABI, against the oracle on the same seeded inputs.
+
+Tolerances (fp64 everywhere; the reference's HMC is Float64-only, test/floattypes/main.jl:54-57):
+  lp / gradient ............ 1e-12 relative (north star)
+  leapfrog trajectories .... 1e-10 absolute over 64 steps (libm + FMA contraction differences)
+  NUTS chains .............. integer tree statistics identical and |dtheta| < 1e-8 over the first
+                             transitions (the dynamics is chaotic: an ulp grows ~5x per transition)
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+import turing_jl_b200 as T
+
+from helpers import golden_cases, model_from_golden, oracle_config, oracle_of, small_models
+
+pytestmark = pytest.mark.gpu
+
+
+def _strategies(model):
+    """every execution strategy that supports the model must agree with the oracle"""
+    out = [0]
+    return out
+
+
+@pytest.fixture(scope="module")
+def golden(built):
+    return golden_cases()
+
+
+def test_lpgrad_golden_and_oracle(golden):
+    rng = np.random.default_rng(1)
+    for case in golden["cases"]:
+        model = model_from_golden(case)
+        try:
+            ldf = T.LogDensityFunction(model)
+        except T._lib.TnutsError as ex:
+            if ex.code == T._lib.E_UNSUPPORTED:
+                pytest.fail("no CUDA path for family %s: %s" % (case["name"], ex))
+            raise
+        assert ldf.dimension() == model.D
+        th = np.array([p["theta"] for p in case["points"]])
+        lp, g = ldf.logdensity_and_gradient(th)
+        np.testing.assert_allclose(lp, [p["lp"] for p in case["points"]], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(g, [p["grad"] for p in case["points"]], rtol=1e-11, atol=1e-11)
+        th = rng.standard_normal((257, model.D)) * 0.8
+        lp, g = ldf.logdensity_and_gradient(th)
+        olp, og = oracle_of(model).lpgrad(th)
+        np.testing.assert_allclose(lp, olp, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(g, og, rtol=1e-11, atol=1e-10)
+        np.testing.assert_allclose(ldf.logdensity(th), lp, rtol=0, atol=0)
+        # single point form
+        l1, g1 = ldf.logdensity_and_gradient(th[0])
+        assert l1 == lp[0] and np.array_equal(g1, g[0])
+
+
+def test_constrain_and_user_space_logp(golden):
+    rng = np.random.default_rng(2)
+    for case in golden["cases"]:
+        model = model_from_golden(case)
+        eng = T.Engine(model, T.NUTS(), 1, 0, 0)
+        th = rng.standard_normal((33, model.D)) * 0.7
+        p, lp3 = eng.constrain(th)
+        om = oracle_of(model)
+        for i in range(33):
+            op, olp3 = om.constrain(th[i])
+            np.testing.assert_allclose(p[i], op, rtol=1e-14)
+            np.testing.assert_allclose(lp3[i], olp3, rtol=1e-12, atol=1e-12)
+        eng.close()
+
+
+def test_leapfrog_trajectories(golden):
+    rng = np.random.default_rng(3)
+    for case in golden["cases"]:
+        model = model_from_golden(case)
+        om = oracle_of(model)
+        eng = T.Engine(model, T.NUTS(), 1, 0, 0)
+        n, L = 16, 64
+        th = rng.standard_normal((n, model.D)) * 0.5
+        r = rng.standard_normal((n, model.D))
+        minv = np.exp(rng.standard_normal(model.D) * 0.3)
+        tt, tr, tH = eng.leapfrog(th, r, minv, 0.01, L)
+        for i in range(n):
+            ot, orr, oH = O.leapfrog_trajectory(om, th[i], r[i], minv, 0.01, L)
+            np.testing.assert_allclose(tt[i], ot, atol=1e-10, rtol=1e-10)
+            np.testing.assert_allclose(tr[i], orr, atol=1e-9, rtol=1e-10)
+            np.testing.assert_allclose(tH[i], oH, atol=1e-8, rtol=1e-12)
+        eng.close()
+
+
+@pytest.mark.parametrize("name", ["gdemo", "linreg", "eight_schools"])
+@pytest.mark.parametrize("n_adapts", [0, 30])
+def test_nuts_chains_match_oracle(built, name, n_adapts):
+    model = small_models()[name]
+    spl = T.NUTS(n_adapts, 0.8)
+    C, n_tr = 96, n_adapts + 12
+    eng = T.Engine(model, spl, C, n_adapts, seed=5)
+    eng.set_option("keep_theta", 1)
+    eng.init()
+    eng.run(n_tr, 1, 1)
+    out = eng.fetch(theta=True)
+    ref = O.sample_chains(oracle_of(model), oracle_config(spl, n_adapts, 5), C, n_tr)
+    st = out["stats"].transpose(2, 0, 1)
+    th = out["theta"].transpose(2, 0, 1)
+    # first 8 transitions: exact tree statistics, tight positions
+    for col in (0, 6, 7):   # n_steps, tree_depth, numerical_error
+        np.testing.assert_array_equal(st[:, :8, col], ref["stats"][:, :8, col])
+    np.testing.assert_allclose(th[:, :8], ref["theta"][:, :8], atol=1e-8, rtol=1e-8)
+    np.testing.assert_allclose(st[:, :8, 1], ref["stats"][:, :8, 1], atol=1e-8)   # acceptance_rate
+    np.testing.assert_allclose(st[:, :8, 8], ref["stats"][:, :8, 8], rtol=1e-9)   # step_size
+    # whole run: the overwhelming majority of transitions still has identical trees
+    same = (st[..., 0] == ref["stats"][..., 0]) & (st[..., 6] == ref["stats"][..., 6])
+    assert same.mean() > 0.9
+    # constrained params / log-probs of kept draws are consistent with theta
+    p, lp3 = eng.constrain(th[:, -1])
+    np.testing.assert_allclose(out["params"].transpose(2, 0, 1)[:, -1], p, rtol=1e-13)
+    np.testing.assert_allclose(out["logp"].transpose(2, 0, 1)[:, -1], lp3, rtol=1e-12, atol=1e-12)
+    eng.close()
+
+
+def test_init_matches_oracle(built):
+    model = T.EightSchools()
+    spl = T.NUTS(0.8)
+    eng = T.Engine(model, spl, 512, 0, seed=77)
+    eng.init()
+    ref = O.sample_chains(oracle_of(model), oracle_config(spl, 0, 77), 512, 0)
+    np.testing.assert_allclose(eng.stepsize(), ref["eps"], rtol=1e-12)   # find_good_stepsize
+    th = eng.theta()
+    assert np.all(np.abs(th) <= 2.0)                                     # InitFromUniform
+    assert eng.init_tries_max == 1
+    eng.close()
+
+
+def test_hmc_and_hmcda_match_oracle(built):
+    model = T.gdemo_default()
+    for spl, nad in ((T.HMC(0.1, 7), 0), (T.HMCDA(40, 0.65, 0.5), 40)):
+        C, n_tr = 64, nad + 10
+        eng = T.Engine(model, spl, C, nad, seed=9)
+        eng.set_option("keep_theta", 1)
+        eng.init()
+        eng.run(n_tr, 1, 1)
+        out = eng.fetch(theta=True)
+        ref = O.sample_chains(oracle_of(model), oracle_config(spl, nad, 9), C, n_tr)
+        th = out["theta"].transpose(2, 0, 1)
+        np.testing.assert_allclose(th[:, :8], ref["theta"][:, :8], atol=1e-8)
+        np.testing.assert_array_equal(out["stats"].transpose(2, 0, 1)[:, :8, 0], ref["stats"][:, :8, 0])
+        eng.close()
+
+
+def test_init_failure_message(built):
+    """test/mcmc/hmc.jl:284-296: the error names the initial-parameters URL"""
+    model = T.GDemo(float("nan"), 2.0)   # lp is NaN everywhere -> no finite initial point
+    with pytest.raises(RuntimeError) as ei:
+        T.sample(model, T.NUTS(0.8), T.MCMCThreads(), 10, 4, verbose=False)
+    assert "failed to find valid initial parameters in 1000 tries" in str(ei.value)
+    assert "https://turinglang.org/docs/uri/initial-parameters" in str(ei.value)

@@ -1,0 +1,122 @@
+"""GPU: the public `sample` API -- posterior agreement (4 MCSE, R-hat < 1.01), plumbing the
+reference's tests pin (sizes, determinism, initial_params, discard_adapt, resume), diagnostics."""
+import warnings
+
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import diagnostics as dg
+import turing_jl_b200 as T
+
+from helpers import oracle_config, oracle_of
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gdemo_posterior_known_answer(built):
+    """E[s] = 49/24, E[m] = 7/6 (test/mcmc/hmc.jl:138-142, atol 0.2); we also require 4 MCSE"""
+    ch = T.sample(T.gdemo_default(), T.NUTS(1000, 0.8), T.MCMCThreads(), 2000, 256, seed=1,
+                  diagnostics=True, verbose=False)
+    assert ch.size() == (2000, 14, 256)
+    x = ch.get_params().transpose(2, 0, 1)[:64]
+    s = dg.summarize(x)
+    z = (np.array([ch.mean("s"), ch.mean("m")]) - [49 / 24, 7 / 6])
+    assert np.abs(z).max() < 0.2
+    assert np.abs(z / (s["mcse"] / 2)).max() < 4.0     # 256 chains: MCSE halves vs 64
+    assert ch.rhat().max() < 1.01
+
+
+def test_eight_schools_agrees_with_oracle_posterior(built):
+    model = T.EightSchools()
+    ch = T.sample(model, T.NUTS(0.8), T.MCMCThreads(), 1000, 1024, seed=3, verbose=False,
+                  diagnostics=True)
+    spl = T.NUTS(0.8)
+    ref = O.sample_chains(oracle_of(model), oracle_config(spl, 500, 1003), 64, 1499, first_keep=500)
+    sr = dg.summarize(ref["params"])
+    gp = ch.get_params()                                # [iters, P, chains]
+    mean = gp.mean(axis=(0, 2))
+    var = gp.transpose(1, 0, 2).reshape(10, -1).var(axis=1, ddof=1)
+    # oracle's MCSE dominates (64 chains vs 1024)
+    assert np.abs((mean - sr["mean"]) / sr["mcse"]).max() < 4.0
+    assert np.abs(var / sr["var"] - 1).max() < 0.15
+    assert ch.rhat().max() < 1.01 and sr["rhat"].max() < 1.01
+    assert ch.ess_bulk().min() > 0.2 * 1024 * 1000
+
+
+def test_device_diagnostics_match_numpy(built):
+    ch = T.sample(T.EightSchools(), T.NUTS(0.8), T.MCMCThreads(), 400, 48, seed=4, verbose=False,
+                  diagnostics=True)
+    gp = ch.get_params()
+    for p in range(10):
+        x = gp[:, p, :]
+        assert ch.ess_bulk()[p] == pytest.approx(dg.ess_bulk(x), rel=1e-6)
+        assert ch.rhat()[p] == pytest.approx(dg.rhat(x), rel=1e-8)
+
+
+def test_same_seed_same_chains_any_sharding(built):
+    """test/mcmc/hmc.jl:164-171, test/mcmc/chains.jl:92-105: same rng => identical chains,
+    different rng => different; and chain k does not depend on how many chains run beside it"""
+    m = T.models.config1_linear_regression()
+    a = T.sample(m, T.NUTS(), T.MCMCThreads(), 200, 8, seed=42, verbose=False)
+    b = T.sample(m, T.NUTS(), T.MCMCThreads(), 200, 8, seed=42, verbose=False)
+    c = T.sample(m, T.NUTS(), T.MCMCThreads(), 200, 8, seed=43, verbose=False)
+    assert np.array_equal(a.value, b.value)
+    assert not np.array_equal(a.value, c.value)
+    d = T.sample(m, T.NUTS(), T.MCMCThreads(), 200, 200, seed=42, verbose=False)
+    assert np.array_equal(a.value, d.value[:, :, :8])
+    rng1, rng2 = np.random.default_rng(7), np.random.default_rng(7)
+    e = T.sample(m, T.NUTS(), T.MCMCThreads(), 50, 2, rng=rng1, verbose=False)
+    f = T.sample(m, T.NUTS(), T.MCMCThreads(), 50, 2, rng=rng2, verbose=False)
+    assert np.array_equal(e.value, f.value)
+
+
+def test_sizes_discard_adapt_and_initial_params(built):
+    m = T.gdemo_default()
+    # test/mcmc/hmc.jl:144-152
+    ch = T.sample(m, T.NUTS(100, 0.8), 300, seed=1, verbose=False)
+    assert ch.size() == (300, 14, 1)
+    ch = T.sample(m, T.NUTS(100, 0.8), 300, seed=1, discard_adapt=False, verbose=False)
+    assert ch.size() == (300, 14, 1)
+    # first un-discarded sample = the initial parameters, with missing stats (hmc.jl:173-197)
+    ip = [T.InitFromParams({"s": 4.0, "m": -1.0}), T.InitFromParams({"s": 0.5, "m": 2.0})]
+    ch = T.sample(m, T.NUTS(0.8), T.MCMCThreads(), 20, 2, seed=1, discard_adapt=False,
+                  initial_params=ip, verbose=False)
+    np.testing.assert_allclose(ch["s"][0], [4.0, 0.5], rtol=1e-14)
+    np.testing.assert_allclose(ch["m"][0], [-1.0, 2.0], rtol=1e-14)
+    assert np.all(np.isnan(ch["tree_depth"][0])) and not np.any(np.isnan(ch["tree_depth"][1:]))
+    assert np.all(np.isfinite(ch["logjoint"][0]))
+    # thinning
+    ch = T.sample(m, T.NUTS(50, 0.8), T.MCMCThreads(), 40, 3, seed=2, thinning=3, verbose=False)
+    assert ch.size() == (40, 14, 3)
+    # stats keys / user-space log-prob identity (test/test_utils/sampler.jl:14-29)
+    np.testing.assert_allclose(ch["logjoint"], ch["logprior"] + ch["loglikelihood"], rtol=1e-12)
+    assert ch.info["step_size"].dtype == np.float64                      # getstepsize: Float64
+    assert np.all(ch["n_steps"] >= 1) and np.all(ch["tree_depth"] <= 10)
+
+
+def test_save_state_resume(built):
+    """test/mcmc/hmc.jl:199-218: resume with initial_state; here resuming is exactly the
+    uninterrupted run because every random draw is addressed by (chain, iteration)"""
+    m = T.EightSchools()
+    full = T.sample(m, T.NUTS(60, 0.8), T.MCMCThreads(), 100, 16, seed=8, discard_adapt=True,
+                    verbose=False)
+    first = T.sample(m, T.NUTS(60, 0.8), T.MCMCThreads(), 50, 16, seed=8, save_state=True,
+                     verbose=False)
+    rest = T.sample(m, T.NUTS(60, 0.8), T.MCMCThreads(), 50, 16, initial_state=T.loadstate(first),
+                    verbose=False)
+    assert np.array_equal(first.value, full.value[:50])
+    assert np.array_equal(rest.value, full.value[50:])
+    with pytest.raises(ValueError):
+        T.loadstate(full)
+
+
+def test_divergence_warning(built):
+    """post_sample_hook (src/mcmc/hmc.jl:476-486; regex of test/mcmc/abstractmcmc.jl:238)"""
+    m = T.EightSchools()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        ch = T.sample(m, T.NUTS(0, 0.8, init_eps=3.0), T.MCMCThreads(), 200, 64, seed=1)
+    n = int(np.nansum(ch["numerical_error"]))
+    assert n > 0
+    assert any("There were %d divergent transitions" % n in str(x.message) for x in w)

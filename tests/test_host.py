@@ -1,0 +1,119 @@
+"""CPU: host-side mirror of the reference interface and the C-ABI surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import turing_jl_b200 as T
+from turing_jl_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "tnuts.h")).read()
+    declared = set(re.findall(r"\b(tnuts_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libtnuts.so does not export " + name
+    # the binding declares a prototype for each of them too
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert _lib.load().tnuts_abi_version() == 1
+
+
+def test_struct_layout_matches_header(built):
+    # tnuts_config / tnuts_model are passed by pointer: sizes must agree with the C compiler
+    import subprocess
+    import tempfile
+    src = '#include <stdio.h>\n#include "tnuts.h"\nint main(){printf("%zu %zu\\n", sizeof(tnuts_model), sizeof(tnuts_config));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", os.path.join(d, "s")])
+        a, b = map(int, subprocess.check_output([os.path.join(d, "s")]).split())
+    assert a == ctypes.sizeof(_lib.TnutsModel)
+    assert b == ctypes.sizeof(_lib.TnutsConfig)
+
+
+def test_no_gpu_fails_loudly(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.TnutsError) as ei:
+        T.sample(T.gdemo_default(), T.NUTS(0.8), T.MCMCThreads(), 10, 2)
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_nuts_constructors():
+    # src/mcmc/hmc.jl:377-402
+    s = T.NUTS()
+    assert (s.n_adapts, s.delta, s.max_depth, s.Delta_max, s.eps) == (-1, 0.65, 10, 1000.0, 0.0)
+    s = T.NUTS(0.8)
+    assert (s.n_adapts, s.delta) == (-1, 0.8)
+    s = T.NUTS(1000, 0.8, max_depth=7, init_eps=0.1)
+    assert (s.n_adapts, s.delta, s.max_depth, s.eps) == (1000, 0.8, 7, 0.1)
+    with pytest.raises(TypeError):
+        T.NUTS(1)          # NUTS(::Int) does not exist in the reference either
+    h = T.HMC(0.05, 10)
+    assert (h.eps, h.n_leapfrog, h.adaptive) == (0.05, 10, False)
+    d = T.HMCDA(200, 0.65, 0.3)
+    assert (d.n_adapts, d.delta, d.lam, d.adaptive) == (200, 0.65, 0.3, True)
+
+
+def test_model_descriptors_and_link():
+    m = T.EightSchools()
+    assert m.D == 10 and m.param_names[:3] == ("μ", "τ", "θ̃[1]")
+    th = np.arange(10.0) / 10
+    np.testing.assert_allclose(m.link(m.invlink(th)), th)
+    assert m.invlink(th)[1] == pytest.approx(np.exp(0.1))
+    with pytest.raises(ValueError):
+        m.link(-np.ones(10))
+    lr = T.models.synthetic_logistic(50, 4)
+    assert lr.D == 4 and lr.X.shape == (50, 4) and set(np.unique(lr.y)) <= {0.0, 1.0}
+    h = T.models.synthetic_hier(3, 5)
+    assert h.D == 11 and h.param_names[5] == "a[1]" and h.param_names[8] == "b[1]"
+    cs = m.c_struct()
+    assert (cs.family, cs.D, cs.N) == (2, 10, 8) and cs.hyper[0] == 5.0
+
+
+def test_sample_argument_validation(built):
+    m = T.gdemo_default()
+    with pytest.raises(TypeError):
+        T.sample(m, T.NUTS(0.8))
+    with pytest.raises(ValueError) as ei:   # src/mcmc/abstractmcmc.jl:147-150
+        T.sample(m, T.NUTS(0.8), T.MCMCThreads(), 10, 4, initial_params=[None, None])
+    assert "one element per chain" in str(ei.value)
+
+    class Disc(T.GDemo):
+        def has_discrete_variables(self):
+            return True
+    with pytest.raises(ValueError):          # src/common.jl:31-46
+        T.sample(Disc(), T.NUTS(0.8), T.MCMCThreads(), 10, 2)
+
+
+def test_initial_params_resolution():
+    from turing_jl_b200.inference import _resolve_initial_params
+    m = T.gdemo_default()
+    th = _resolve_initial_params(m, [T.InitFromParams({"s": 2.0, "m": 0.5}), [1.0, -1.0]], 2)
+    np.testing.assert_allclose(th, [[np.log(2.0), 0.5], [0.0, -1.0]])
+    assert _resolve_initial_params(m, None, 3) is None
+    es = T.EightSchools()
+    th = _resolve_initial_params(es, [{"μ": 1.0, "τ": 2.0, "θ̃": np.zeros(8)}], 1)
+    assert th.shape == (1, 10) and th[0, 1] == pytest.approx(np.log(2.0))
+
+
+def test_chains_container():
+    from turing_jl_b200.chains import INTERNALS
+    v = np.random.default_rng(0).standard_normal((5, 2 + len(INTERNALS), 3))
+    c = T.Chains(v, ("s", "m"))
+    assert c.size() == (5, 14, 3) and c["m"].shape == (5, 3)
+    assert c.names[:5] == ("s", "m", "logprior", "loglikelihood", "logjoint")
+    for k in ("tree_depth", "n_steps", "acceptance_rate", "hamiltonian_energy", "numerical_error"):
+        assert k in c.names       # test/mcmc/callbacks.jl:61-64, src/mcmc/hmc.jl:480
+    np.testing.assert_array_equal(c["nom_step_size"], c["step_size"])
+    assert np.all(c["is_accept"] == 1.0)
+    cc = T.chainscat([c, c])
+    assert cc.size() == (5, 14, 6)

@@ -54,6 +54,9 @@ SYMBOLS = {
     "tnuts_init": (C.c_int, [_H, _dp]),
     "tnuts_run": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
     "tnuts_fetch": (C.c_int, [_H, _dp, _dp, _dp, _dp]),
+    "tnuts_num_columns": (C.c_int, [_H]),
+    "tnuts_fetch_draws": (C.c_int, [_H, _dp]),
+    "tnuts_set_option": (C.c_int, [_H, C.c_char_p, C.c_double]),
     "tnuts_get_theta": (C.c_int, [_H, _dp]),
     "tnuts_constrain": (C.c_int, [_H, _dp, C.c_int64, _dp, _dp]),
     "tnuts_get_stepsize": (C.c_int, [_H, _dp]),
@@ -68,6 +71,7 @@ SYMBOLS = {
     "tnuts_num_divergences": (C.c_int64, [_H]),
     "tnuts_num_kernel_launches": (C.c_int64, [_H]),
     "tnuts_device_seconds": (C.c_double, [_H]),
+    "tnuts_init_device_seconds": (C.c_double, [_H]),
     "tnuts_init_tries_max": (C.c_int, [_H]),
     "tnuts_comm_unique_id": (C.c_int, [C.c_void_p]),
     "tnuts_comm_init": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),

@@ -82,10 +82,13 @@ def build(force=False, verbose=False):
     if verbose:
         for _, log in res:
             sys.stderr.write(log)
-    link = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart"]
+    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
+    link = ["g++", "-shared", "-o", LIB, *objs, "-L", cuda_lib, "-lcudart_static", "-ldl", "-lrt", "-lpthread",
+            ]
     if ncclib:
         # link the exact file (torch's wheel only ships libnccl.so.2) and leave an rpath
-        link += [ncclib, "-Xlinker", "-rpath", "-Xlinker", os.path.dirname(ncclib)]
+        link += ["-L", os.path.dirname(ncclib), "-l:" + os.path.basename(ncclib),
+                 "-Wl,-rpath," + os.path.dirname(ncclib)]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr)

@@ -5,7 +5,9 @@ import numpy as np
 
 from ._lib import STAT_NAMES
 
-INTERNALS = ("logprior", "loglikelihood", "logjoint") + STAT_NAMES + ("is_accept", "nom_step_size")
+INTERNALS = ("logprior", "loglikelihood", "logjoint") + STAT_NAMES
+#: columns AdvancedHMC also reports; derived on access instead of stored
+DERIVED = ("is_accept", "nom_step_size")
 
 
 class Chains:
@@ -30,6 +32,13 @@ class Chains:
     def __getitem__(self, name):
         """chain[name] -> [iters, chains]"""
         if isinstance(name, str):
+            if name == "nom_step_size":
+                return self["step_size"]
+            if name == "is_accept":
+                # NUTS always accepts; HMC/HMCDA carry their accept flag in the tree_depth column
+                if self.info.get("algorithm", 0) == 0:
+                    return np.where(np.isnan(self["n_steps"]), np.nan, 1.0)
+                return self["tree_depth"]
             return self.value[:, self.names.index(name), :]
         raise KeyError(name)
 

@@ -397,16 +397,18 @@ __global__ void __launch_bounds__(kChainBlock) k_chain_run(SmallData md, ChainSt
       const long long k = (t - rp.first_keep) / rp.thin;
       double p[D], prior, lik;
       M::constrain(md, th, p, prior, lik);
+      double *row = out.draws + (size_t)k * out.ncol * C + c;
 #pragma unroll
-      for (int d = 0; d < D; ++d) {
-        out.params[((size_t)k * D + d) * C + c] = p[d];
-        out.theta[((size_t)k * D + d) * C + c] = th[d];
+      for (int d = 0; d < D; ++d) row[(size_t)d * C] = p[d];
+      row[(size_t)(D + 0) * C] = prior;
+      row[(size_t)(D + 1) * C] = lik;
+      row[(size_t)(D + 2) * C] = prior + lik;
+#pragma unroll
+      for (int s = 0; s < TNUTS_NSTAT; ++s) row[(size_t)(D + 3 + s) * C] = stats[s];
+      if (out.theta != nullptr) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) out.theta[((size_t)k * D + d) * C + c] = th[d];
       }
-      out.logp[((size_t)k * 3 + 0) * C + c] = prior;
-      out.logp[((size_t)k * 3 + 1) * C + c] = lik;
-      out.logp[((size_t)k * 3 + 2) * C + c] = prior + lik;
-#pragma unroll
-      for (int s = 0; s < TNUTS_NSTAT; ++s) out.stats[((size_t)k * TNUTS_NSTAT + s) * C + c] = stats[s];
     }
   }
 

@@ -61,14 +61,16 @@ struct ChainState {
   int *status;               // [C] 0 ok, 1 init failed
 };
 
-// Kept-draw output buffers on the device.
+// Kept-draw output buffer on the device: ONE array [keep][ncol][C] whose columns are
+// P constrained parameters | logprior, loglikelihood, logjoint | NSTAT sampler stats --
+// exactly the (iterations x names x chains) array MCMCChains wants, so the host fetch is a
+// single contiguous copy.  theta (linked-space draws) is optional.
 struct DrawBuffers {
   long long capacity;  // draws
   int P;
-  double *params;  // [keep][P][C]
-  double *logp;    // [keep][3][C]
-  double *stats;   // [keep][NSTAT][C]
-  double *theta;   // [keep][D][C]
+  int ncol;        // P + 3 + TNUTS_NSTAT
+  double *draws;   // [keep][ncol][C]
+  double *theta;   // [keep][D][C] or nullptr
 };
 
 struct RunParams {

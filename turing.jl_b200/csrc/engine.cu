@@ -67,19 +67,20 @@ static void window_schedule(long long n, RunParams &rp) {
 }
 
 static int ensure_draw_capacity(Engine *e, long long keep) {
-  if (keep <= e->out.capacity) return TNUTS_OK;
-  for (double **p : {&e->out.params, &e->out.logp, &e->out.stats, &e->out.theta}) {
+  const bool want_theta = e->keep_theta;
+  if (keep <= e->out.capacity && (!want_theta || e->out.theta)) return TNUTS_OK;
+  for (double **p : {&e->out.draws, &e->out.theta}) {
     if (*p) cudaFree(*p);
     *p = nullptr;
   }
   const size_t C = (size_t)e->st.C;
   e->out.capacity = 0;
-  TN_CUDA(e, cudaMalloc((void **)&e->out.params, sizeof(double) * (size_t)keep * e->P * C));
-  TN_CUDA(e, cudaMalloc((void **)&e->out.theta, sizeof(double) * (size_t)keep * e->D * C));
-  TN_CUDA(e, cudaMalloc((void **)&e->out.logp, sizeof(double) * (size_t)keep * 3 * C));
-  TN_CUDA(e, cudaMalloc((void **)&e->out.stats, sizeof(double) * (size_t)keep * TNUTS_NSTAT * C));
-  e->out.capacity = keep;
   e->out.P = e->P;
+  e->out.ncol = e->P + 3 + TNUTS_NSTAT;
+  TN_CUDA(e, cudaMalloc((void **)&e->out.draws, sizeof(double) * (size_t)keep * e->out.ncol * C));
+  if (want_theta)
+    TN_CUDA(e, cudaMalloc((void **)&e->out.theta, sizeof(double) * (size_t)keep * e->D * C));
+  e->out.capacity = keep;
   return TNUTS_OK;
 }
 
@@ -201,7 +202,7 @@ int tnuts_destroy(tnuts_engine *h) {
   diagnostics_destroy(e);
   free_pool(e->model_allocs);
   free_pool(e->state_allocs);
-  for (double *p : {e->out.params, e->out.logp, e->out.stats, e->out.theta})
+  for (double *p : {e->out.draws, e->out.theta})
     if (p) cudaFree(p);
   cudaEventDestroy(e->ev0);
   cudaEventDestroy(e->ev1);
@@ -325,8 +326,15 @@ int tnuts_init(tnuts_engine *h, const double *theta0) {
     TN_CUDA(e, cudaMalloc((void **)&t0, bytes));
     TN_CUDA(e, cudaMemcpyAsync(t0, theta0, bytes, cudaMemcpyHostToDevice, e->stream));
   }
+  cudaEventRecord(e->ev0, e->stream);
   int rc = (e->strategy == STRAT_THREAD) ? thread_init(e, t0) : lockstep_init(e, t0);
+  cudaEventRecord(e->ev1, e->stream);
   cudaError_t s = cudaStreamSynchronize(e->stream);
+  {
+    float ms = 0;
+    if (s == cudaSuccess && cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess)
+      e->last_init_seconds = ms * 1e-3;
+  }
   if (t0) cudaFree(t0);
   if (rc) return rc;
   if (s != cudaSuccess) return set_error(e, TNUTS_E_CUDA, std::string("tnuts_init: ") + cudaGetErrorString(s));
@@ -365,20 +373,52 @@ int tnuts_run(tnuts_engine *h, int64_t n_transitions, int64_t first_keep, int64_
   return TNUTS_OK;
 }
 
+int tnuts_num_columns(const tnuts_engine *h) {
+  const Engine *e = (const Engine *)h;
+  return e ? e->P + 3 + TNUTS_NSTAT : TNUTS_E_ARG;
+}
+
+int tnuts_set_option(tnuts_engine *h, const char *name, double value) {
+  Engine *e = (Engine *)h;
+  if (!e || !name) return set_error(e, TNUTS_E_ARG, "tnuts_set_option: null argument");
+  const std::string n(name);
+  if (n == "keep_theta") e->keep_theta = value != 0.0;
+  else return set_error(e, TNUTS_E_ARG, "tnuts_set_option: unknown option " + n);
+  return TNUTS_OK;
+}
+
+int tnuts_fetch_draws(tnuts_engine *h, double *draws) {
+  Engine *e = (Engine *)h;
+  if (!e || !e->inited || !draws) return set_error(e, TNUTS_E_ARG, "tnuts_fetch_draws: bad call");
+  TN_CUDA(e, cudaSetDevice(e->device));
+  const size_t K = (size_t)e->n_kept, C = (size_t)e->st.C;
+  if (K == 0) return TNUTS_OK;
+  TN_CUDA(e, cudaMemcpyAsync(draws, e->out.draws, 8 * K * e->out.ncol * C, cudaMemcpyDeviceToHost, e->stream));
+  TN_CUDA(e, cudaStreamSynchronize(e->stream));
+  return TNUTS_OK;
+}
+
 int tnuts_fetch(tnuts_engine *h, double *params, double *logp, double *stats, double *theta) {
   Engine *e = (Engine *)h;
   if (!e || !e->inited) return set_error(e, TNUTS_E_ARG, "tnuts_fetch: nothing to fetch");
   TN_CUDA(e, cudaSetDevice(e->device));
-  const size_t K = (size_t)e->n_kept, C = (size_t)e->st.C;
+  const size_t K = (size_t)e->n_kept, C = (size_t)e->st.C, P = (size_t)e->P;
   if (K == 0) return TNUTS_OK;
-  if (params)
-    TN_CUDA(e, cudaMemcpyAsync(params, e->out.params, 8 * K * e->P * C, cudaMemcpyDeviceToHost, e->stream));
-  if (logp)
-    TN_CUDA(e, cudaMemcpyAsync(logp, e->out.logp, 8 * K * 3 * C, cudaMemcpyDeviceToHost, e->stream));
-  if (stats)
-    TN_CUDA(e, cudaMemcpyAsync(stats, e->out.stats, 8 * K * TNUTS_NSTAT * C, cudaMemcpyDeviceToHost, e->stream));
-  if (theta)
+  const size_t pitch = 8 * (size_t)e->out.ncol * C;  // one draw
+  auto cols = [&](double *dst, size_t col0, size_t ncols) -> int {
+    if (!dst) return TNUTS_OK;
+    TN_CUDA(e, cudaMemcpy2DAsync(dst, 8 * ncols * C, e->out.draws + col0 * C, pitch, 8 * ncols * C, K,
+                                 cudaMemcpyDeviceToHost, e->stream));
+    return TNUTS_OK;
+  };
+  int rc;
+  if ((rc = cols(params, 0, P))) return rc;
+  if ((rc = cols(logp, P, 3))) return rc;
+  if ((rc = cols(stats, P + 3, TNUTS_NSTAT))) return rc;
+  if (theta) {
+    if (!e->out.theta) return set_error(e, TNUTS_E_ARG, "tnuts_fetch: theta was not kept (set option keep_theta)");
     TN_CUDA(e, cudaMemcpyAsync(theta, e->out.theta, 8 * K * e->D * C, cudaMemcpyDeviceToHost, e->stream));
+  }
   TN_CUDA(e, cudaStreamSynchronize(e->stream));
   return TNUTS_OK;
 }
@@ -621,7 +661,7 @@ int64_t tnuts_num_divergences(const tnuts_engine *h) {
   std::vector<double> col(C);
   long long s = 0;
   for (size_t k = 0; k < K; ++k) {
-    if (cudaMemcpy(col.data(), e->out.stats + (k * TNUTS_NSTAT + ST_NUMERR) * C, 8 * C,
+    if (cudaMemcpy(col.data(), e->out.draws + (k * e->out.ncol + e->P + 3 + ST_NUMERR) * C, 8 * C,
                    cudaMemcpyDeviceToHost) != cudaSuccess)
       return -1;
     for (double v : col) s += (v != 0.0);
@@ -634,6 +674,9 @@ int64_t tnuts_num_kernel_launches(const tnuts_engine *h) {
 }
 double tnuts_device_seconds(const tnuts_engine *h) {
   return h ? ((const Engine *)h)->last_run_seconds : -1.0;
+}
+double tnuts_init_device_seconds(const tnuts_engine *h) {
+  return h ? ((const Engine *)h)->last_init_seconds : -1.0;
 }
 int tnuts_init_tries_max(const tnuts_engine *h) {
   const Engine *e = (const Engine *)h;

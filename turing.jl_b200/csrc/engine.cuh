@@ -43,7 +43,8 @@ struct Engine {
 
   // counters
   long long launches = 0;
-  double last_run_seconds = 0.0;
+  double last_run_seconds = 0.0, last_init_seconds = 0.0;
+  bool keep_theta = false;
 
   LockstepState *ls = nullptr;
   DiagWork *diag = nullptr;

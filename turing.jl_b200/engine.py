@@ -69,6 +69,22 @@ class Engine:
         self.n_kept = k.value
         return self.n_kept
 
+    def set_option(self, name, value):
+        check(self.h, self.L.tnuts_set_option(self.h, name.encode(), float(value)))
+
+    @property
+    def ncol(self):
+        return self.L.tnuts_num_columns(self.h)
+
+    def fetch_draws(self, out=None):
+        """the whole kept array [n_kept, ncol, n_chains] in one contiguous copy"""
+        if out is None:
+            out = np.empty((self.n_kept, self.ncol, self.C))
+        assert out.shape == (self.n_kept, self.ncol, self.C) and out.flags.c_contiguous
+        if self.n_kept:
+            check(self.h, self.L.tnuts_fetch_draws(self.h, _dp(out)))
+        return out
+
     def fetch(self, params=True, logp=True, stats=True, theta=False):
         K, Cn = self.n_kept, self.C
         out = {}
@@ -169,7 +185,8 @@ class Engine:
 
     @property
     def device_seconds(self):
-        return self.L.tnuts_device_seconds(self.h)
+        """CUDA-event seconds of the last init + the last run"""
+        return self.L.tnuts_device_seconds(self.h) + self.L.tnuts_init_device_seconds(self.h)
 
     @property
     def init_tries_max(self):

@@ -15,7 +15,7 @@ import warnings
 
 import numpy as np
 
-from . import _lib
+from . import _lib, pinned
 from .chains import INTERNALS, Chains
 from .engine import Engine
 from .samplers import (Hamiltonian, InitFromParams, InitFromUniform, MCMCThreads)
@@ -122,6 +122,13 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
                               chain_offset=bounds[i], strategy=strategy))
     results = [None] * ndev
     errors = [None] * ndev
+    # bundle_samples target: (iterations x names x chains); the engine's device layout is
+    # identical, so a single-GPU run copies straight into it (pinned host memory)
+    P = model.D
+    nint = len(INTERNALS)
+    value = pinned.empty((N, P + nint, n_chains))
+    if _discard == 0 and initial_state is None:
+        value[0, P + 3:, :] = np.nan
 
     def work(i):
         try:
@@ -141,16 +148,21 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
                     n_tr, first_keep = (N - 1) * thinning, thinning
                 else:
                     n_tr, first_keep = _discard + (N - 1) * thinning, _discard
+            row = 0 if first is None else 1
+            if first is not None:
+                value[0, :P, lo:hi] = first[0].T
+                value[0, P:P + 3, lo:hi] = first[1].T
             if n_tr > 0:
                 e.run(n_tr, first_keep, thinning)
-                out = e.fetch()
+                if ndev == 1 and row == 0:
+                    e.fetch_draws(value)  # straight into the chain array: one contiguous D2H
+                else:
+                    value[row:row + e.n_kept, :, lo:hi] = e.fetch_draws()
             else:
                 e.n_kept = 0
-                out = dict(params=np.empty((0, e.P, e.C)), logp=np.empty((0, 3, e.C)),
-                           stats=np.empty((0, _lib.NSTAT, e.C)))
             diag = e.diagnostics() if (diagnostics and ndev == 1 and e.n_kept >= 4) else None
-            results[i] = (first, out, diag, e.grad_evals, e.device_seconds, e.stepsize(),
-                          e.get_state() if save_state else None)
+            results[i] = (diag, e.grad_evals, e.device_seconds, e.stepsize(),
+                          e.get_state() if save_state else None, e.launches)
         except Exception as ex:  # re-raised on the caller's thread
             errors[i] = ex
 
@@ -171,36 +183,20 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
             raise ex
     wall = time.perf_counter() - t_start
 
-    # --- bundle_samples: (iterations x names x chains) ---
-    P = model.D
-    nint = len(INTERNALS)
-    value = np.full((N, P + nint, n_chains), np.nan)
-    for i in range(ndev):
-        first, out, *_ = results[i]
-        lo, hi = bounds[i], bounds[i + 1]
-        row = 0
-        if first is not None:
-            value[0, :P, lo:hi] = first[0].T
-            value[0, P:P + 3, lo:hi] = first[1].T
-            row = 1
-        K = out["params"].shape[0]
-        value[row:row + K, :P, lo:hi] = out["params"]
-        value[row:row + K, P:P + 3, lo:hi] = out["logp"]
-        value[row:row + K, P + 3:P + 3 + _lib.NSTAT, lo:hi] = out["stats"]
-        value[row:row + K, P + 3 + _lib.NSTAT, lo:hi] = 1.0 if spl.algorithm == 0 else out["stats"][:, 6, :]
-        value[row:row + K, P + 4 + _lib.NSTAT, lo:hi] = out["stats"][:, 8, :]
     info = {
         "sampling_time": np.full(n_chains, wall),
         "wall_seconds": wall,
-        "device_seconds": max(r[4] for r in results),
-        "grad_evals": int(sum(r[3] for r in results)),
-        "step_size": np.concatenate([r[5] for r in results]),
+        "device_seconds": max(r[2] for r in results),
+        "grad_evals": int(sum(r[1] for r in results)),
+        "gpu_launches": int(sum(r[5] for r in results)),
+        "step_size": np.concatenate([r[3] for r in results]),
+        "algorithm": spl.algorithm,
         "nadapts": _nadapts, "discard_initial": _discard, "thinning": thinning, "seed": seed64,
     }
-    if results[0][2] is not None:
-        info["rhat"], info["ess_bulk"] = results[0][2]
+    if results[0][0] is not None:
+        info["rhat"], info["ess_bulk"] = results[0][0]
     if save_state:
-        info["samplerstate"] = {"blobs": [r[6] for r in results], "seed": seed64,
+        info["samplerstate"] = {"blobs": [r[4] for r in results], "seed": seed64,
                                 "bounds": bounds, "devices": devices}
     chain = chain_type(value, model.param_names, INTERNALS, info)
     if keep_engine:
