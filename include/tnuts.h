@@ -190,6 +190,8 @@ int tnuts_init_tries_max(const tnuts_engine *e);        /* worst chain's init at
  * broadcast by the host (torch.distributed / MPI / Distributed.jl). */
 int tnuts_comm_unique_id(void *unique_id_128);
 int tnuts_comm_init(tnuts_engine *e, const void *unique_id_128, int32_t world, int32_t rank);
+/* sum a small host vector over all ranks of the communicator (diagnostics statistics) */
+int tnuts_comm_allreduce_host(tnuts_engine *e, double *values, int64_t n);
 
 /* pinned host staging for the caller's output arrays (optional, speeds up tnuts_fetch) */
 int tnuts_host_alloc(void **p, size_t nbytes);

@@ -38,11 +38,22 @@ def golden_cases():
 
 
 def small_models():
+    rng = np.random.default_rng(11)
     return {
         "gdemo": T.gdemo_default(),
         "linreg": T.models.config1_linear_regression(),
         "eight_schools": T.EightSchools(),
+        # families / sizes that only the lock-step strategy serves
+        "linreg_n40": T.LinearRegression(rng.random(40), rng.random(40)),
+        "eight_schools_j5": T.EightSchools([3.0, -1.0, 8.0, 2.0, 0.5], [4.0, 6.0, 5.0, 3.0, 7.0]),
+        "std_normal_d7": T.StdNormal(7),
+        "logistic_small": T.models.synthetic_logistic(300, 5, seed=4),
+        "logistic_d130": T.models.synthetic_logistic(257, 130, seed=5),
+        "hier_small": T.models.synthetic_hier(7, 11, seed=6),
     }
+
+
+THREAD_MODELS = ("gdemo", "linreg", "eight_schools")
 
 
 def oracle_config(spl, n_adapts, seed, mode=1):

@@ -75,6 +75,7 @@ SYMBOLS = {
     "tnuts_init_tries_max": (C.c_int, [_H]),
     "tnuts_comm_unique_id": (C.c_int, [C.c_void_p]),
     "tnuts_comm_init": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),
+    "tnuts_comm_allreduce_host": (C.c_int, [_H, _dp, C.c_int64]),
     "tnuts_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "tnuts_host_free": (C.c_int, [C.c_void_p]),
 }

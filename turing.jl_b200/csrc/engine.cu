@@ -200,6 +200,7 @@ int tnuts_destroy(tnuts_engine *h) {
   cudaStreamSynchronize(e->stream);
   lockstep_destroy(e);
   diagnostics_destroy(e);
+  comm_destroy(e);
   free_pool(e->model_allocs);
   free_pool(e->state_allocs);
   for (double *p : {e->out.draws, e->out.theta})

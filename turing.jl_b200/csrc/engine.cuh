@@ -89,6 +89,14 @@ int lockstep_point_leapfrog(Engine *e, const double *theta_dev, const double *r_
                             const double *minv_dev, double eps, int L, long long n,
                             double *tt_dev, double *tr_dev, double *tH_dev);
 
+// comm.cu
+int comm_allreduce_sum(Engine *e, double *buf, size_t n);
+void comm_destroy(Engine *e);
+
+// comm.cu
+int comm_allreduce_sum(Engine *e, double *buf, size_t n);
+void comm_destroy(Engine *e);
+
 // diagnostics.cu
 int diagnostics_run(Engine *e, double *rhat_host, double *ess_host);
 void diagnostics_destroy(Engine *e);

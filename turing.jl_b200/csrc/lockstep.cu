@@ -1,11 +1,674 @@
-// lockstep.cu -- lock-step strategy (placeholder until implemented)
+// lockstep.cu -- host driver of the lock-step strategy: one launch per leapfrog phase for all
+// chains, the NUTS doubling schedule driven from the host (one small D2H per doubling tells it
+// whether any chain still runs), gradient kernels per family, init / step-size search,
+// point-wise LogDensityProblems entry points.
+#include "lockstep.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
 #include "engine.cuh"
+#include "lockstep_kernels.cuh"
+#include "lpgrad_kernels.cuh"
+
+#ifdef TNUTS_WITH_NCCL
+#include <nccl.h>
+#endif
+
 namespace tnuts {
-int lockstep_create(Engine *e) { return set_error(e, TNUTS_E_UNSUPPORTED, "lock-step strategy not built yet"); }
-void lockstep_destroy(Engine *) {}
-int lockstep_init(Engine *e, const double *) { return set_error(e, TNUTS_E_UNSUPPORTED, "lock-step"); }
-int lockstep_run(Engine *e) { return set_error(e, TNUTS_E_UNSUPPORTED, "lock-step"); }
-int lockstep_point_lpgrad(Engine *e, const double *, long long, double *, double *) { return set_error(e, TNUTS_E_UNSUPPORTED, "lock-step"); }
-int lockstep_point_constrain(Engine *e, const double *, long long, double *, double *) { return set_error(e, TNUTS_E_UNSUPPORTED, "lock-step"); }
-int lockstep_point_leapfrog(Engine *e, const double *, const double *, const double *, double, int, long long, double *, double *, double *) { return set_error(e, TNUTS_E_UNSUPPORTED, "lock-step"); }
+
+int comm_allreduce_sum(Engine *e, double *buf, size_t n);  // comm.cu (no-op when world == 1)
+
+template <class T>
+static int ls_alloc(Engine *e, std::vector<void *> *pool, T **p, size_t n) {
+  void *q = nullptr;
+  TN_CUDA(e, cudaMalloc(&q, (n ? n : 1) * sizeof(T)));
+  TN_CUDA(e, cudaMemsetAsync(q, 0, (n ? n : 1) * sizeof(T), e->stream));
+  pool->push_back(q);
+  *p = (T *)q;
+  return TNUTS_OK;
 }
+
+static inline int tiles(int C) { return (C + kTileC - 1) / kTileC; }
+
+// ------------------------------------------------------------------------------------------
+// gradient dispatch: lp[c], g[d][c] for the chains in the work list (NULL = all n_all columns)
+// ------------------------------------------------------------------------------------------
+struct GradWork {  // workspaces sized for `cap` columns
+  double *part = nullptr, *lik = nullptr;
+  int cap = 0, chunks = 0, rows_per_chunk = 0;
+};
+
+static int logistic_plan(const ModelDev &m, int cap, int *tr, int *tch, int *chunks, int *rpc) {
+  const int D = m.D;
+  *tr = D <= 128 ? 64 : 32;
+  *tch = D <= 128 ? 64 : 32;
+  const int ctiles = (cap + *tch - 1) / *tch;
+  int want = (2 * 148 + ctiles - 1) / ctiles;  // ~2 CTAs per SM in flight
+  long long maxchunks = (m.N + *tr - 1) / *tr;
+  if (want > maxchunks) want = (int)std::max<long long>(1, maxchunks);
+  if (want > 1024) want = 1024;
+  long long r = (m.N + want - 1) / want;
+  r = ((r + *tr - 1) / *tr) * *tr;  // whole row tiles per chunk
+  *rpc = (int)r;
+  *chunks = (int)((m.N + r - 1) / r);
+  return TNUTS_OK;
+}
+
+static int grad_launch(Engine *e, const double *th, int C, double *lp, double *g, const int *list,
+                       const int *count, int n_all, int n_max, GradWork *gw) {
+  const ModelDev &m = e->model;
+  LockstepState *ls = e->ls;
+  if (n_max <= 0) return TNUTS_OK;
+  switch (m.family) {
+    case TNUTS_GDEMO:
+    case TNUTS_LINREG:
+    case TNUTS_EIGHT_SCHOOLS:
+    case TNUTS_STD_NORMAL:
+      k_lpgrad_small<<<(n_max + 127) / 128, 128, 0, e->stream>>>(m, th, C, lp, g, list, count, n_all);
+      e->launches += 1;
+      break;
+    case TNUTS_HIER_LINREG:
+      k_hier_tile<<<tiles(n_max), kTileThreads, 0, e->stream>>>(m, *ls, th, C, list, count, n_all, lp, g);
+      e->launches += 1;
+      break;
+    case TNUTS_LOGISTIC: {
+      int tr, tch, chunks, rpc;
+      logistic_plan(m, gw->cap, &tr, &tch, &chunks, &rpc);
+      const int D = m.D;
+      const dim3 grid((n_max + tch - 1) / tch, chunks);
+      const size_t smem = sizeof(double) * ((size_t)D * tch + (size_t)tr * D + (size_t)tr * tch + tr);
+#define TN_LOGI(TR, TCH, ND)                                                                      \
+  do {                                                                                            \
+    auto kfn = k_logistic_tile<TR, TCH, ND>;                                                      \
+    TN_CUDA(e, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kfn<<<grid, 256, smem, e->stream>>>(m.X, m.y, 0, m.N, D, th, C, list, count, n_all, rpc,      \
+                                        gw->part, gw->cap);                                       \
+  } while (0)
+      if (D <= 16) TN_LOGI(64, 64, 1);
+      else if (D <= 32) TN_LOGI(64, 64, 2);
+      else if (D <= 64) TN_LOGI(64, 64, 4);
+      else if (D <= 112) TN_LOGI(64, 64, 7);
+      else if (D <= 128) TN_LOGI(64, 64, 8);
+      else if (D <= 256) TN_LOGI(32, 32, 16);
+      else return set_error(e, TNUTS_E_UNSUPPORTED, "logistic regression: D > 256 not supported");
+#undef TN_LOGI
+      const dim3 rg((n_max + 127) / 128, D + 1);
+      k_logistic_reduce<<<rg, 128, 0, e->stream>>>(gw->part, chunks, D, gw->cap, count, n_all, gw->lik);
+      if (e->world > 1 && e->cfg.row_shards > 1) {
+        int rc = comm_allreduce_sum(e, gw->lik, (size_t)(D + 1) * gw->cap);
+        if (rc) return rc;
+      }
+      k_logistic_finish<<<(n_max + 127) / 128, 128, 0, e->stream>>>(m, gw->lik, gw->cap, th, C, list,
+                                                                   count, n_all, 1.0, lp, g);
+      e->launches += 3;
+    } break;
+    default:
+      return set_error(e, TNUTS_E_UNSUPPORTED, "lock-step: unknown family");
+  }
+  TN_CUDA(e, cudaGetLastError());
+  return TNUTS_OK;
+}
+
+static int gradwork_alloc(Engine *e, GradWork *gw, int cap, std::vector<void *> *pool) {
+  gw->cap = cap;
+  if (e->model.family != TNUTS_LOGISTIC) return TNUTS_OK;
+  int tr, tch;
+  logistic_plan(e->model, cap, &tr, &tch, &gw->chunks, &gw->rows_per_chunk);
+  const size_t D1 = (size_t)e->model.D + 1;
+  void *p = nullptr;
+  TN_CUDA(e, cudaMalloc(&p, 8 * (size_t)gw->chunks * D1 * cap));
+  pool->push_back(p);
+  gw->part = (double *)p;
+  TN_CUDA(e, cudaMalloc(&p, 8 * D1 * cap));
+  TN_CUDA(e, cudaMemsetAsync(p, 0, 8 * D1 * cap, e->stream));
+  pool->push_back(p);
+  gw->lik = (double *)p;
+  return TNUTS_OK;
+}
+
+struct LockstepExt {
+  LockstepState ls;  // first member: Engine::ls points here
+  GradWork gw;
+  std::vector<void *> allocs;
+};
+static LockstepExt *ext_of(Engine *e) { return reinterpret_cast<LockstepExt *>(e->ls); }
+
+// ------------------------------------------------------------------------------------------
+int lockstep_create(Engine *e) {
+  if (e->cfg.algorithm != TNUTS_ALG_NUTS)
+    return set_error(e, TNUTS_E_UNSUPPORTED, "lock-step strategy implements NUTS only (HMC/HMCDA run on the thread-per-chain strategy)");
+  if (e->cfg.max_depth > kMaxLevels)
+    return set_error(e, TNUTS_E_UNSUPPORTED, "lock-step: max_depth too large");
+  LockstepExt *x = new LockstepExt();
+  LockstepState *ls = &x->ls;
+  e->ls = ls;
+  const size_t C = (size_t)e->st.C, D = (size_t)e->D, DC = D * C;
+  ls->C = (int)C;
+  ls->D = (int)D;
+  ls->levels = std::max(1, e->cfg.max_depth - 1);
+  int rc;
+#define A(p, n) if ((rc = ls_alloc(e, &x->allocs, &(p), (n)))) return rc
+  A(ls->zt, DC); A(ls->zr, DC); A(ls->zg, DC);
+  A(ls->edge[0], 3 * DC); A(ls->edge[1], 3 * DC);
+  A(ls->rho, DC); A(ls->rho_s, DC);
+  A(ls->thC, DC); A(ls->gC, DC); A(ls->thS, DC); A(ls->gS, DC);
+  A(ls->ck_r, ls->levels * DC); A(ls->ck_rho, ls->levels * DC);
+  TreeScalars &s = ls->ts;
+  A(s.H0, C); A(s.sum_a, C); A(s.dHmax, C); A(s.lw, C); A(s.lw_s, C); A(s.lpC, C); A(s.HC, C);
+  A(s.lpS, C); A(s.HS, C); A(s.zlp, C); A(s.zH, C); A(s.elp, 2 * C); A(s.n_a, C);
+  A(s.depth, C); A(s.active, C); A(s.sub_active, C); A(s.term_s, C); A(s.numerr, C); A(s.v, C);
+  A(ls->list, C); A(ls->count, 2);
+  A(ls->fs_eps, C); A(ls->fs_epsp, C); A(ls->fs_H, C); A(ls->fs_dir, C); A(ls->fs_phase, C);
+  A(ls->fs_iter, C); A(ls->r0, DC);
+  TN_CUDA(e, cudaMallocHost((void **)&ls->h_count, 2 * sizeof(int)));
+  if ((rc = gradwork_alloc(e, &x->gw, (int)C, &x->allocs))) return rc;
+  // hierarchical model: centred sufficient statistics per group, computed once on the host
+  if (e->model.family == TNUTS_HIER_LINREG) {
+    const int G = e->model.G;
+    const long long N = e->model.N;
+    std::vector<double> hx((size_t)N), hy((size_t)N);
+    std::vector<int> grp((size_t)N);
+    TN_CUDA(e, cudaMemcpy(hx.data(), e->model.X, 8 * (size_t)N, cudaMemcpyDeviceToHost));
+    TN_CUDA(e, cudaMemcpy(hy.data(), e->model.y, 8 * (size_t)N, cudaMemcpyDeviceToHost));
+    TN_CUDA(e, cudaMemcpy(grp.data(), e->model.group, 4 * (size_t)N, cudaMemcpyDeviceToHost));
+    std::vector<double> n(G, 0.0), xb(G, 0.0), yb(G, 0.0), sxx(G, 0.0), sxy(G, 0.0), syy(G, 0.0);
+    for (long long i = 0; i < N; ++i) {
+      const int g = grp[(size_t)i];
+      if (g < 0 || g >= G) return set_error(e, TNUTS_E_ARG, "hier: group index out of range");
+      n[g] += 1.0;
+      xb[g] += hx[(size_t)i];
+      yb[g] += hy[(size_t)i];
+    }
+    for (int g = 0; g < G; ++g)
+      if (n[g] > 0) {
+        xb[g] /= n[g];
+        yb[g] /= n[g];
+      }
+    for (long long i = 0; i < N; ++i) {
+      const int g = grp[(size_t)i];
+      const double dx = hx[(size_t)i] - xb[g], dy = hy[(size_t)i] - yb[g];
+      sxx[g] += dx * dx;
+      sxy[g] += dx * dy;
+      syy[g] += dy * dy;
+    }
+    auto up = [&](double **dst, const std::vector<double> &v) -> int {
+      int r2 = ls_alloc(e, &x->allocs, dst, v.size());
+      if (r2) return r2;
+      TN_CUDA(e, cudaMemcpy(*dst, v.data(), 8 * v.size(), cudaMemcpyHostToDevice));
+      return TNUTS_OK;
+    };
+    if ((rc = up(&ls->hs_n, n)) || (rc = up(&ls->hs_xbar, xb)) || (rc = up(&ls->hs_ybar, yb)) ||
+        (rc = up(&ls->hs_sxx, sxx)) || (rc = up(&ls->hs_sxy, sxy)) || (rc = up(&ls->hs_syy, syy)))
+      return rc;
+  }
+#undef A
+  return TNUTS_OK;
+}
+
+void lockstep_destroy(Engine *e) {
+  if (!e->ls) return;
+  LockstepExt *x = ext_of(e);
+  for (void *p : x->allocs) cudaFree(p);
+  if (x->ls.h_count) cudaFreeHost(x->ls.h_count);
+  delete x;
+  e->ls = nullptr;
+}
+
+static GradWork *gw_of(Engine *e) { return &ext_of(e)->gw; }
+
+// ------------------------------------------------------------------------------------------
+// init: initial parameters (<= 1000 tries), step-size search
+// ------------------------------------------------------------------------------------------
+__global__ void k_ls_init_draw(ChainState st, RunParams rp, int attempt) {
+  const int C = st.C, D = st.D;
+  const int npair = (D + 1) / 2;
+  const long long tot = (long long)npair * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i / C), c = (int)(i % C);
+    if (st.status[c] == 0) continue;  // already has a finite point
+    double u0, u1;
+    uniform2(rp.seed, (uint32_t)(rp.chain_offset + c), 0u, SLOT_INIT, (uint32_t)(attempt * npair + p), u0, u1);
+    st.theta[(size_t)(2 * p) * C + c] = 4.0 * u0 - 2.0;
+    if (2 * p + 1 < D) st.theta[(size_t)(2 * p + 1) * C + c] = 4.0 * u1 - 2.0;
+  }
+}
+
+__global__ void k_ls_set_theta0(ChainState st, const double *theta0 /* [C][D] */) {
+  const int C = st.C, D = st.D;
+  const long long tot = (long long)D * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i / C), c = (int)(i % C);
+    st.theta[i] = theta0[(size_t)c * D + d];
+  }
+}
+
+// status: 1 = needs a point; after the gradient: finite -> 0
+__global__ void __launch_bounds__(kTileThreads) k_ls_init_check(ChainState st, int attempt, int *n_bad) {
+  __shared__ double red[64];
+  const Tile t;
+  const int C = st.C, D = st.D;
+  const bool in = t.c < C && st.status[t.c] != 0;
+  double bad[1] = {0.0};
+  if (in)
+    for (int d = t.dl; d < D; d += kTileD) bad[0] += isfinite(st.grad[(size_t)d * C + t.c]) ? 0.0 : 1.0;
+  tile_reduce<1>(bad, red);
+  if (in && t.dl == 0) {
+    const bool ok = isfinite(st.lp[t.c]) && bad[0] == 0.0;
+    st.init_tries[t.c] = attempt + 1;
+    st.n_grad[t.c] += 1;
+    if (ok) st.status[t.c] = 0;
+    else atomicAdd(n_bad, 1);
+  }
+}
+
+__global__ void k_ls_init_state(ChainState st, double init_eps, int algorithm) {
+  const int C = st.C, D = st.D;
+  const long long tot = (long long)D * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot;
+       i += (long long)gridDim.x * blockDim.x) {
+    st.minv[i] = 1.0;
+    st.wf_mean[i] = 0.0;
+    st.wf_m2[i] = 0.0;
+    if (i < C) {
+      st.status[i] = 1;
+      st.iter[i] = 0;
+      st.n_grad[i] = 0;
+      st.wf_n[i] = 0;
+      st.da_m[i] = 0;
+      st.da_xbar[i] = 0.0;
+      st.da_hbar[i] = 0.0;
+      st.eps[i] = init_eps;
+      st.init_tries[i] = 0;
+    }
+  }
+}
+
+// step-size search, lock-step: phase 0 first trial, 1 crossing, 2 bisection, 3 done
+__global__ void __launch_bounds__(kTileThreads)
+k_ls_fs_begin(ChainState st, LockstepState ls, RunParams rp) {
+  __shared__ double red[64];
+  const Tile t;
+  const int C = st.C, D = st.D;
+  const bool in = t.c < C;
+  double acc[1] = {0.0};
+  if (in) {
+    const int npair = (D + 1) / 2;
+    const uint32_t gchain = (uint32_t)(rp.chain_offset + t.c);
+    for (int p = t.dl; p < npair; p += kTileD) {
+      double z0, z1;
+      normal2(rp.seed, gchain, 0u, SLOT_EPS_MOMENTUM, (uint32_t)p, z0, z1);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int d = 2 * p + q;
+        if (d < D) {
+          const size_t o = (size_t)d * C + t.c;
+          const double mi = st.minv[o];
+          const double r = (q ? z1 : z0) / sqrt(mi);
+          ls.r0[o] = r;
+          acc[0] += mi * r * r;
+        }
+      }
+    }
+  }
+  tile_reduce<1>(acc, red);
+  if (in && t.dl == 0) {
+    const double lp = st.lp[t.c], K = 0.5 * acc[0];
+    ls.fs_H[t.c] = (isfinite(lp) && isfinite(K)) ? (-lp + K) : CUDART_INF;
+    ls.fs_eps[t.c] = 0.1;
+    ls.fs_epsp[t.c] = 0.1;
+    ls.fs_phase[t.c] = 0;
+    ls.fs_iter[t.c] = 0;
+    ls.ts.sub_active[t.c] = 1;
+  }
+}
+
+// trial leapfrog, first half: z = (theta, r0, grad) -> kick + drift with the chain's trial eps
+__global__ void __launch_bounds__(kTileThreads)
+k_ls_fs_trial(ChainState st, LockstepState ls) {
+  const Tile t;
+  const int C = st.C, D = st.D;
+  if (t.c >= C || ls.fs_phase[t.c] >= 3) return;
+  const int ph = ls.fs_phase[t.c];
+  const double eps = ph == 2 ? 0.5 * (ls.fs_eps[t.c] + ls.fs_epsp[t.c]) : ls.fs_eps[t.c];
+  const double half = 0.5 * eps;
+  for (int d = t.dl; d < D; d += kTileD) {
+    const size_t o = (size_t)d * C + t.c;
+    const double r = ls.r0[o] + half * st.grad[o];
+    ls.zr[o] = r;
+    ls.zt[o] = st.theta[o] + eps * (st.minv[o] * r);
+  }
+}
+
+__global__ void __launch_bounds__(kTileThreads)
+k_ls_fs_decide(ChainState st, LockstepState ls, int *n_left) {
+  __shared__ double red[2 * 64];
+  const Tile t;
+  const int C = st.C, D = st.D;
+  const bool in = t.c < C && ls.fs_phase[t.c] < 3;
+  double a[2] = {0.0, 0.0};
+  int ph = 3;
+  double eps = 0, epsp = 0, tried = 0;
+  if (in) {
+    ph = ls.fs_phase[t.c];
+    eps = ls.fs_eps[t.c];
+    epsp = ls.fs_epsp[t.c];
+    tried = ph == 2 ? 0.5 * (eps + epsp) : eps;
+    const double half = 0.5 * tried;
+    for (int d = t.dl; d < D; d += kTileD) {
+      const size_t o = (size_t)d * C + t.c;
+      const double g = ls.zg[o];
+      const double r = ls.zr[o] + half * g;
+      a[0] += st.minv[o] * r * r;
+      a[1] += isfinite(g) ? 0.0 : 1.0;
+    }
+  }
+  tile_reduce<2>(a, red);
+  if (in && t.dl == 0) {
+    const double lp = ls.ts.zlp[t.c], K = 0.5 * a[0];
+    const double Hn = (isfinite(lp) && a[1] == 0.0 && isfinite(K)) ? (-lp + K) : CUDART_INF;
+    const double dH = ls.fs_H[t.c] - Hn;
+    const double lc = log(0.5);
+    int iter = ls.fs_iter[t.c];
+    st.n_grad[t.c] += 1;
+    if (ph == 0) {
+      ls.fs_dir[t.c] = dH > lc ? 1 : -1;
+      ph = 1;
+      iter = 0;
+      epsp = ls.fs_dir[t.c] == 1 ? 2.0 * eps : 0.5 * eps;  // eps' of the first crossing iteration
+    } else if (ph == 1) {
+      const int dir = ls.fs_dir[t.c];
+      bool brk = (dir == 1 && !(dH > lc)) || (dir == -1 && !(dH < lc));
+      if (!brk) {
+        eps = epsp;
+        iter += 1;
+        if (iter >= 100) brk = true;
+        else epsp = dir == 1 ? 2.0 * eps : 0.5 * eps;
+      }
+      if (brk) {
+        if (eps > epsp) {
+          const double tmp = eps;
+          eps = epsp;
+          epsp = tmp;
+        }
+        ph = 2;
+        iter = 0;
+      }
+    } else {
+      const double ea = exp(dH);
+      if (ea > 0.75) eps = tried;
+      else if (ea < 0.25) epsp = tried;
+      else {
+        eps = tried;
+        ph = 3;
+      }
+      iter += 1;
+      if (iter >= 100) ph = 3;
+    }
+    ls.fs_eps[t.c] = eps;
+    ls.fs_epsp[t.c] = epsp;
+    ls.fs_phase[t.c] = ph;
+    ls.fs_iter[t.c] = iter;
+    ls.ts.sub_active[t.c] = ph < 3 ? 1 : 0;
+    if (ph < 3) atomicAdd(n_left, 1);
+    else st.eps[t.c] = eps;
+  }
+}
+
+__global__ void k_ls_finish_init(ChainState st) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= st.C) return;
+  const double eps = st.eps[c];
+  st.da_eps[c] = eps;
+  st.da_mu[c] = log(10.0 * eps);
+}
+
+static int read_count(Engine *e, int *dev, int *host_slot) {
+  TN_CUDA(e, cudaMemcpyAsync(host_slot, dev, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  TN_CUDA(e, cudaStreamSynchronize(e->stream));
+  return TNUTS_OK;
+}
+
+int lockstep_init(Engine *e, const double *theta0_dev) {
+  LockstepState *ls = e->ls;
+  ChainState &st = e->st;
+  const int C = st.C;
+  int rc;
+  k_ls_init_state<<<148 * 4, 256, 0, e->stream>>>(st, e->cfg.init_eps, e->cfg.algorithm);
+  e->launches += 1;
+  const int max_tries = theta0_dev ? 1 : 1000;
+  int n_bad = C;
+  for (int attempt = 0; attempt < max_tries && n_bad > 0; ++attempt) {
+    if (theta0_dev) k_ls_set_theta0<<<148 * 4, 256, 0, e->stream>>>(st, theta0_dev);
+    else k_ls_init_draw<<<148 * 4, 256, 0, e->stream>>>(st, e->rp, attempt);
+    k_ls_compact<<<1, 1024, 0, e->stream>>>(st.status, C, ls->list, ls->count);
+    if ((rc = grad_launch(e, st.theta, C, st.lp, st.grad, ls->list, ls->count, C, n_bad, gw_of(e)))) return rc;
+    TN_CUDA(e, cudaMemsetAsync(ls->count + 1, 0, sizeof(int), e->stream));
+    k_ls_init_check<<<tiles(C), kTileThreads, 0, e->stream>>>(st, attempt, ls->count + 1);
+    e->launches += 3;
+    if ((rc = read_count(e, ls->count + 1, ls->h_count))) return rc;
+    n_bad = ls->h_count[0];
+  }
+  if (n_bad > 0) return TNUTS_OK;  // tnuts_init reports TNUTS_E_INIT from the status array
+  if (e->cfg.init_eps == 0.0) {
+    // find_good_stepsize for every chain
+    k_ls_fs_begin<<<tiles(C), kTileThreads, 0, e->stream>>>(st, *ls, e->rp);
+    e->launches += 1;
+    int left = C;
+    for (int iter = 0; iter < 1 + 100 + 100 + 2 && left > 0; ++iter) {
+      k_ls_fs_trial<<<tiles(C), kTileThreads, 0, e->stream>>>(st, *ls);
+      k_ls_compact<<<1, 1024, 0, e->stream>>>(ls->ts.sub_active, C, ls->list, ls->count);
+      if ((rc = grad_launch(e, ls->zt, C, ls->ts.zlp, ls->zg, ls->list, ls->count, C, left, gw_of(e)))) return rc;
+      TN_CUDA(e, cudaMemsetAsync(ls->count + 1, 0, sizeof(int), e->stream));
+      k_ls_fs_decide<<<tiles(C), kTileThreads, 0, e->stream>>>(st, *ls, ls->count + 1);
+      e->launches += 3;
+      if ((rc = read_count(e, ls->count + 1, ls->h_count))) return rc;
+      left = ls->h_count[0];
+    }
+  }
+  k_ls_finish_init<<<(C + 255) / 256, 256, 0, e->stream>>>(st);
+  e->launches += 1;
+  TN_CUDA(e, cudaGetLastError());
+  return TNUTS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// run: the mcmcsample loop, one NUTS transition at a time for all chains
+// ------------------------------------------------------------------------------------------
+int lockstep_run(Engine *e) {
+  LockstepState *ls = e->ls;
+  ChainState &st = e->st;
+  const RunParams &rp = e->rp;
+  const int C = st.C;
+  const int T = tiles(C);
+  int rc;
+  for (long long t = 1; t <= rp.n_transitions; ++t) {
+    k_ls_transition_start<<<T, kTileThreads, 0, e->stream>>>(st, *ls, rp);
+    e->launches += 1;
+    int n_active = C;
+    for (int j = 0; j < rp.max_depth && n_active > 0; ++j) {
+      k_ls_doubling_start<<<T, kTileThreads, 0, e->stream>>>(st, *ls, rp, j);
+      e->launches += 1;
+      const int nleaf = 1 << j;
+      for (int n = 0; n < nleaf; ++n) {
+        if ((n & 7) == 0) {  // refresh the work list at the start and every 8 leaves
+          k_ls_compact<<<1, 1024, 0, e->stream>>>(ls->ts.sub_active, C, ls->list, ls->count);
+          e->launches += 1;
+        }
+        if ((rc = grad_launch(e, ls->zt, C, ls->ts.zlp, ls->zg, ls->list, ls->count, C, n_active, gw_of(e))))
+          return rc;
+        k_ls_leaf<<<T, kTileThreads, 0, e->stream>>>(st, *ls, rp, j, n, nleaf);
+        e->launches += 1;
+      }
+      TN_CUDA(e, cudaMemsetAsync(ls->count + 1, 0, sizeof(int), e->stream));
+      k_ls_doubling_end<<<T, kTileThreads, 0, e->stream>>>(st, *ls, rp, j, ls->count + 1);
+      e->launches += 1;
+      if ((rc = read_count(e, ls->count + 1, ls->h_count))) return rc;
+      n_active = ls->h_count[0];
+    }
+    long long k_slot = -1;
+    if (rp.first_keep >= 1 && t >= rp.first_keep && (t - rp.first_keep) % rp.thin == 0)
+      k_slot = (t - rp.first_keep) / rp.thin;
+    k_ls_transition_end<<<T, kTileThreads, 0, e->stream>>>(st, *ls, rp, e->model, e->out, k_slot);
+    e->launches += 1;
+  }
+  TN_CUDA(e, cudaGetLastError());
+  return TNUTS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// point-wise entry points: n arbitrary points as n "chains"
+// ------------------------------------------------------------------------------------------
+__global__ void k_transpose_in(const double *rm /* [n][D] */, double *cm /* [D][n] */, long long n, int D) {
+  const long long tot = n * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long c = i % n;
+    const int d = (int)(i / n);
+    cm[i] = rm[c * D + d];
+  }
+}
+__global__ void k_transpose_out(const double *cm /* [D][n] */, double *rm /* [n][D] */, long long n, int D) {
+  const long long tot = n * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long c = i % n;
+    const int d = (int)(i / n);
+    rm[c * D + d] = cm[i];
+  }
+}
+
+struct Tmp {
+  std::vector<void *> p;
+  ~Tmp() {
+    for (void *q : p) cudaFree(q);
+  }
+  double *get(size_t n) {
+    void *q = nullptr;
+    if (cudaMalloc(&q, 8 * (n ? n : 1)) != cudaSuccess) return nullptr;
+    p.push_back(q);
+    return (double *)q;
+  }
+};
+
+int lockstep_point_lpgrad(Engine *e, const double *theta_dev, long long n, double *lp_dev,
+                          double *grad_dev) {
+  const int D = e->D;
+  Tmp tmp;
+  double *th = tmp.get((size_t)n * D), *g = tmp.get((size_t)n * D);
+  if (!th || !g) return set_error(e, TNUTS_E_CUDA, "point lpgrad: cudaMalloc failed");
+  GradWork gw;
+  int rc = gradwork_alloc(e, &gw, (int)n, &tmp.p);
+  if (rc) return rc;
+  k_transpose_in<<<148 * 2, 256, 0, e->stream>>>(theta_dev, th, n, D);
+  if ((rc = grad_launch(e, th, (int)n, lp_dev, g, nullptr, nullptr, (int)n, (int)n, &gw))) return rc;
+  if (grad_dev) k_transpose_out<<<148 * 2, 256, 0, e->stream>>>(g, grad_dev, n, D);
+  e->launches += 2;
+  TN_CUDA(e, cudaStreamSynchronize(e->stream));
+  return TNUTS_OK;
+}
+
+__global__ void __launch_bounds__(kTileThreads)
+k_ls_point_constrain(ModelDev m, const double *th /* [D][n] */, const double *lp, int n,
+                     double *params /* [n][P] */, double *logp /* [n][3] */) {
+  __shared__ double red[2 * 64];
+  const Tile t;
+  const bool in = t.c < n;
+  double prior, lik;
+  ls_user_logp(m, th, n, t, in, in ? lp[t.c] : 0.0, red, prior, lik);
+  if (!in) return;
+  for (int d = t.dl; d < m.D; d += kTileD) {
+    const double x = th[(size_t)d * n + t.c];
+    params[(size_t)t.c * m.D + d] = ls_is_positive(m, d) ? exp(x) : x;
+  }
+  if (t.dl == 0) {
+    logp[(size_t)t.c * 3 + 0] = prior;
+    logp[(size_t)t.c * 3 + 1] = lik;
+    logp[(size_t)t.c * 3 + 2] = prior + lik;
+  }
+}
+
+int lockstep_point_constrain(Engine *e, const double *theta_dev, long long n, double *params_dev,
+                             double *logp_dev) {
+  const int D = e->D;
+  Tmp tmp;
+  double *th = tmp.get((size_t)n * D), *g = tmp.get((size_t)n * D), *lp = tmp.get((size_t)n);
+  if (!th || !g || !lp) return set_error(e, TNUTS_E_CUDA, "point constrain: cudaMalloc failed");
+  GradWork gw;
+  int rc = gradwork_alloc(e, &gw, (int)n, &tmp.p);
+  if (rc) return rc;
+  k_transpose_in<<<148 * 2, 256, 0, e->stream>>>(theta_dev, th, n, D);
+  if ((rc = grad_launch(e, th, (int)n, lp, g, nullptr, nullptr, (int)n, (int)n, &gw))) return rc;
+  k_ls_point_constrain<<<tiles((int)n), kTileThreads, 0, e->stream>>>(e->model, th, lp, (int)n, params_dev, logp_dev);
+  e->launches += 2;
+  TN_CUDA(e, cudaStreamSynchronize(e->stream));
+  return TNUTS_OK;
+}
+
+// fixed-momentum trajectories: kick/drift, gradient, kick + energy, one launch each per step
+__global__ void __launch_bounds__(kTileThreads)
+k_ls_traj_step(const double *minv, int n, int D, double eps, int phase, double *th, double *r,
+               const double *g, const double *lp, int l, int L, double *tt, double *tr, double *tH) {
+  __shared__ double red[2 * 64];
+  const Tile t;
+  const bool in = t.c < n;
+  const double half = 0.5 * eps;
+  double a[2] = {0.0, 0.0};
+  if (in) {
+    for (int d = t.dl; d < D; d += kTileD) {
+      const size_t o = (size_t)d * n + t.c;
+      double rr = r[o];
+      if (phase == 1) {  // second half kick of step l (l >= 1)
+        rr += half * g[o];
+        r[o] = rr;
+      }
+      a[0] += minv[d] * rr * rr;
+      a[1] += isfinite(g[o]) ? 0.0 : 1.0;
+      // record point l
+      tt[((size_t)t.c * (L + 1) + l) * D + d] = th[o];
+      tr[((size_t)t.c * (L + 1) + l) * D + d] = rr;
+    }
+  }
+  tile_reduce<2>(a, red);
+  if (in && t.dl == 0) {
+    const double K = 0.5 * a[0];
+    tH[(size_t)t.c * (L + 1) + l] = (isfinite(lp[t.c]) && a[1] == 0.0 && isfinite(K)) ? (-lp[t.c] + K) : CUDART_INF;
+  }
+  if (in && l < L) {  // first half kick + drift of step l+1
+    for (int d = t.dl; d < D; d += kTileD) {
+      const size_t o = (size_t)d * n + t.c;
+      const double rr = r[o] + half * g[o];
+      r[o] = rr;
+      th[o] = th[o] + eps * (minv[d] * rr);
+    }
+  }
+}
+
+int lockstep_point_leapfrog(Engine *e, const double *theta_dev, const double *r_dev,
+                            const double *minv_dev, double eps, int L, long long n, double *tt_dev,
+                            double *tr_dev, double *tH_dev) {
+  const int D = e->D;
+  Tmp tmp;
+  double *th = tmp.get((size_t)n * D), *r = tmp.get((size_t)n * D), *g = tmp.get((size_t)n * D),
+         *lp = tmp.get((size_t)n);
+  if (!th || !r || !g || !lp) return set_error(e, TNUTS_E_CUDA, "point leapfrog: cudaMalloc failed");
+  GradWork gw;
+  int rc = gradwork_alloc(e, &gw, (int)n, &tmp.p);
+  if (rc) return rc;
+  k_transpose_in<<<148 * 2, 256, 0, e->stream>>>(theta_dev, th, n, D);
+  k_transpose_in<<<148 * 2, 256, 0, e->stream>>>(r_dev, r, n, D);
+  e->launches += 2;
+  for (int l = 0; l <= L; ++l) {
+    if ((rc = grad_launch(e, th, (int)n, lp, g, nullptr, nullptr, (int)n, (int)n, &gw))) return rc;
+    k_ls_traj_step<<<tiles((int)n), kTileThreads, 0, e->stream>>>(minv_dev, (int)n, D, eps, l == 0 ? 0 : 1, th, r, g,
+                                                               lp, l, L, tt_dev, tr_dev, tH_dev);
+    e->launches += 1;
+  }
+  TN_CUDA(e, cudaStreamSynchronize(e->stream));
+  return TNUTS_OK;
+}
+
+}  // namespace tnuts
