@@ -1,0 +1,51 @@
+"""GPU: multi-GPU modes.  Chain sharding needs no collective, so its invariant -- the union of
+the shards is bit-identical to one engine running all chains -- is checked on ONE GPU with two
+engines; the NCCL row-sharded path needs >= 2 GPUs and is skipped otherwise."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import turing_jl_b200 as T
+from turing_jl_b200 import distributed as D
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("strategy,model_name", [(1, "eight"), (2, "logistic")])
+def test_chain_shards_union_equals_single_engine(built, strategy, model_name):
+    model = T.EightSchools() if model_name == "eight" else T.models.synthetic_logistic(200, 6, seed=2)
+    spl = T.NUTS(20, 0.8)
+    full = T.Engine(model, spl, 40, 20, seed=3, strategy=strategy)
+    full.init()
+    full.run(30, 1, 1)
+    a = full.fetch_draws()
+    full.close()
+    parts = []
+    b = D.chain_bounds(40, 3)
+    for r in range(3):
+        e = D.make_chain_sharded_engine(model, spl, 40, 20, 3, r, 3, device=0)
+        if strategy == 2:
+            e.close()
+            e = T.Engine(model, spl, b[r + 1] - b[r], 20, 3, device=0, chain_offset=b[r], strategy=2)
+        e.init()
+        e.run(30, 1, 1)
+        parts.append(e.fetch_draws())
+        e.close()
+    assert np.array_equal(a, np.concatenate(parts, axis=2))
+
+
+def test_row_sharded_logistic_two_gpus(built):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+         "--master-addr", "127.0.0.1", "--master-port", "29611",
+         os.path.join(ROOT, "scripts", "multi_gpu_check.py"), "--rows"],
+        capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "ROWS-OK" in out.stdout

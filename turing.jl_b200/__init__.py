@@ -5,7 +5,7 @@ and a Python mirror of the reference's sampler interface for that path
 (`sample(model, NUTS(delta), MCMCThreads(), N, n_chains)`).  The directory name contains a
 dot, so import it through the repo-root shim:  `import turing_jl_b200`.
 """
-from . import _lib, build, models  # noqa: F401
+from . import _lib, build, distributed, models  # noqa: F401
 from .chains import Chains, chainscat  # noqa: F401
 from .engine import Engine  # noqa: F401
 from .inference import LogDensityFunction, loadstate, post_sample_hook, sample  # noqa: F401
