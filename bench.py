@@ -269,9 +269,13 @@ def main():
 
     # ---------------- arm 2: end to end through the public API (host buffers) ----------------
     def e2e_step(k):
+        # the user-facing call: host model in, host chain array (iterations x names x chains) out
         ch = T.sample(model, spl, T.MCMCThreads(), N, C, seed=seed + k, devices=[local],
-                      verbose=False)
-        return ch
+                      chain_offset=rank * C, verbose=False)
+        res = (ch.info["grad_evals"], ch.info["gpu_launches"], ch.value.nbytes,
+               float(ch.value[-1, 0, 0]))
+        del ch  # the chain's pinned buffer returns to the pool for the next step
+        return res
 
     for k in range(max(args.warmup, 3)):
         e2e_step(k)
@@ -280,10 +284,9 @@ def main():
     g_e2e = 0
     l_e2e = 0
     for k in range(args.steps):
-        ch = e2e_step(100 + k)
-        g_e2e += ch.info["grad_evals"]
-        l_e2e += ch.info["gpu_launches"]
-        d2h = ch.value.nbytes
+        ge, le, d2h, _ = e2e_step(100 + k)
+        g_e2e += ge
+        l_e2e += le
     barrier()
     wall_e2e = allmax(time.perf_counter() - t0)
     e2e_value = allsum(g_e2e) / wall_e2e

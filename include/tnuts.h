@@ -133,6 +133,13 @@ int tnuts_init(tnuts_engine *e, const double *theta0);
 int tnuts_run(tnuts_engine *e, int64_t n_transitions, int64_t first_keep, int64_t thin,
               int64_t *n_kept);
 
+/* tnuts_run + the device->host copy of the kept-draw array ([n_kept][ncol][n_chains], see
+ * tnuts_fetch_draws) overlapped with the computation: the run is cut into segments of
+ * chunk_draws kept draws and every finished segment is copied on a second stream while the
+ * next one computes.  host_draws should be page-locked (tnuts_host_alloc) for the overlap. */
+int tnuts_run_streamed(tnuts_engine *e, int64_t n_transitions, int64_t first_keep, int64_t thin,
+                       double *host_draws, int64_t chunk_draws, int64_t *n_kept);
+
 /* copy the draws kept by the last tnuts_run to the host.  Any pointer may be NULL.
  *   params [n_kept][P][n_chains]   constrained (user-space) parameters
  *   logp   [n_kept][3][n_chains]   logprior, loglikelihood, logjoint (no Jacobian)
@@ -184,6 +191,10 @@ int64_t tnuts_num_kernel_launches(const tnuts_engine *e);
 double tnuts_device_seconds(const tnuts_engine *e);     /* CUDA-event time of last tnuts_run */
 double tnuts_init_device_seconds(const tnuts_engine *e);/* CUDA-event time of last tnuts_init */
 int tnuts_init_tries_max(const tnuts_engine *e);        /* worst chain's init attempts  */
+
+/* measurement aid: time `reps` gradient evaluations of all chains at their current positions
+ * with CUDA events on the engine's stream (lock-step strategy) */
+int tnuts_bench_gradient(tnuts_engine *e, int32_t reps, double *seconds);
 
 /* multi-GPU: NCCL communicator for row sharding and cross-GPU diagnostics.
  * unique_id: 128-byte ncclUniqueId produced by tnuts_comm_unique_id on rank 0 and

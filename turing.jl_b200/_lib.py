@@ -53,6 +53,8 @@ SYMBOLS = {
     "tnuts_num_params": (C.c_int, [_H]),
     "tnuts_init": (C.c_int, [_H, _dp]),
     "tnuts_run": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
+    "tnuts_run_streamed": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64, _dp, C.c_int64,
+                                     C.POINTER(C.c_int64)]),
     "tnuts_fetch": (C.c_int, [_H, _dp, _dp, _dp, _dp]),
     "tnuts_num_columns": (C.c_int, [_H]),
     "tnuts_fetch_draws": (C.c_int, [_H, _dp]),
@@ -73,6 +75,7 @@ SYMBOLS = {
     "tnuts_device_seconds": (C.c_double, [_H]),
     "tnuts_init_device_seconds": (C.c_double, [_H]),
     "tnuts_init_tries_max": (C.c_int, [_H]),
+    "tnuts_bench_gradient": (C.c_int, [_H, C.c_int32, C.POINTER(C.c_double)]),
     "tnuts_comm_unique_id": (C.c_int, [C.c_void_p]),
     "tnuts_comm_init": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),
     "tnuts_comm_allreduce_host": (C.c_int, [_H, _dp, C.c_int64]),

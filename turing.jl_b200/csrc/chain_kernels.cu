@@ -43,9 +43,16 @@ int thread_init(Engine *e, const double *theta0_dev) {
 }
 
 int thread_run(Engine *e) {
-#define CALL(M)                                                                         \
-  k_chain_run<M><<<grid_for(e->st.C, kChainBlock), kChainBlock, 0, e->stream>>>(        \
-      e->small, e->st, e->out, e->rp)
+#define CALL(M)                                                                              \
+  do {                                                                                       \
+    const int g_ = grid_for(e->st.C, kChainBlock);                                           \
+    if (e->occupancy == 3)                                                                   \
+      k_chain_run<M, 3><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp);  \
+    else if (e->occupancy == 4)                                                              \
+      k_chain_run<M, 4><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp);  \
+    else                                                                                     \
+      k_chain_run<M, 2><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp);  \
+  } while (0)
   TN_DISPATCH_SMALL(e, CALL);
 #undef CALL
   e->launches += 1;

@@ -310,9 +310,9 @@ __device__ __forceinline__ void hmc_transition_d(const SmallData &md, const RunP
 // ------------------------------------------------------------------------------------------
 // run kernel: n_transitions for every chain
 // ------------------------------------------------------------------------------------------
-template <class M>
-__global__ void __launch_bounds__(kChainBlock) k_chain_run(SmallData md, ChainState st,
-                                                          DrawBuffers out, RunParams rp) {
+template <class M, int MINB>
+__global__ void __launch_bounds__(kChainBlock, MINB) k_chain_run(SmallData md, ChainState st,
+                                                                DrawBuffers out, RunParams rp) {
   constexpr int D = M::D;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int C = st.C;

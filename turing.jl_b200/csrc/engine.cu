@@ -2,6 +2,7 @@
 // device memory, model upload, strategy selection, launches, D2H of kept draws.
 #include "engine.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -205,6 +206,7 @@ int tnuts_destroy(tnuts_engine *h) {
   free_pool(e->state_allocs);
   for (double *p : {e->out.draws, e->out.theta})
     if (p) cudaFree(p);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   cudaEventDestroy(e->ev0);
   cudaEventDestroy(e->ev1);
   cudaStreamDestroy(e->stream);
@@ -348,9 +350,11 @@ int tnuts_init(tnuts_engine *h, const double *theta0) {
   return TNUTS_OK;
 }
 
-int tnuts_run(tnuts_engine *h, int64_t n_transitions, int64_t first_keep, int64_t thin,
-              int64_t *n_kept) {
-  Engine *e = (Engine *)h;
+// Runs the transitions in segments that end on kept-draw boundaries.  With host_draws != NULL
+// every finished segment's draws are copied device->host on a second stream while the next
+// segment computes (the draw index is the slowest dimension, so a segment is contiguous).
+static int run_segments(Engine *e, int64_t n_transitions, int64_t first_keep, int64_t thin,
+                        double *host_draws, int64_t chunk_draws, int64_t *n_kept) {
   if (!e || !e->inited) return set_error(e, TNUTS_E_ARG, "tnuts_run: call tnuts_init first");
   if (n_transitions < 0 || thin < 1) return set_error(e, TNUTS_E_ARG, "tnuts_run: bad n_transitions/thin");
   TN_CUDA(e, cudaSetDevice(e->device));
@@ -358,20 +362,69 @@ int tnuts_run(tnuts_engine *h, int64_t n_transitions, int64_t first_keep, int64_
   if (first_keep >= 1 && n_transitions >= first_keep) keep = (n_transitions - first_keep) / thin + 1;
   int rc = ensure_draw_capacity(e, keep > 0 ? keep : 1);
   if (rc) return rc;
-  e->rp.n_transitions = n_transitions;
-  e->rp.first_keep = first_keep;
-  e->rp.thin = thin;
+  if (host_draws && !e->copy_stream) TN_CUDA(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  const size_t C = (size_t)e->st.C, row = (size_t)e->out.ncol * C;
+  double *const base = e->out.draws, *const tbase = e->out.theta;
+  if (chunk_draws <= 0 || !host_draws) chunk_draws = keep > 0 ? keep : 1;
   TN_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-  rc = (e->strategy == STRAT_THREAD) ? thread_run(e) : lockstep_run(e);
+  long long t_done = 0, k_done = 0;
+  std::vector<cudaEvent_t> evs;
+  while (t_done < n_transitions) {
+    long long k_end = std::min<long long>(keep, k_done + chunk_draws);
+    // last transition of this segment: the one that produces draw k_end - 1 (or the very end)
+    long long t_end = (keep == 0 || k_end >= keep) ? n_transitions : first_keep + (k_end - 1) * thin;
+    if (k_done >= keep) t_end = n_transitions;
+    e->rp.n_transitions = t_end - t_done;
+    e->rp.thin = thin;
+    e->rp.first_keep = (k_done < keep) ? (first_keep + k_done * thin - t_done) : 0;
+    e->out.draws = base + (size_t)k_done * row;
+    e->out.theta = tbase ? tbase + (size_t)k_done * e->D * C : nullptr;
+    rc = (e->strategy == STRAT_THREAD) ? thread_run(e) : lockstep_run(e);
+    if (rc) break;
+    if (host_draws && k_end > k_done) {
+      cudaEvent_t ev;
+      if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventRecord(ev, e->stream) != cudaSuccess ||
+          cudaStreamWaitEvent(e->copy_stream, ev, 0) != cudaSuccess ||
+          cudaMemcpyAsync(host_draws + (size_t)k_done * row, base + (size_t)k_done * row,
+                          8 * (size_t)(k_end - k_done) * row, cudaMemcpyDeviceToHost,
+                          e->copy_stream) != cudaSuccess) {
+        rc = set_error(e, TNUTS_E_CUDA, "tnuts_run_streamed: D2H enqueue failed");
+        break;
+      }
+      evs.push_back(ev);
+    }
+    t_done = t_end;
+    k_done = k_end > k_done ? k_end : k_done;
+  }
+  e->out.draws = base;
+  e->out.theta = tbase;
+  if (!rc) {
+    cudaError_t s = cudaEventRecord(e->ev1, e->stream);
+    if (s == cudaSuccess) s = cudaStreamSynchronize(e->stream);
+    if (s == cudaSuccess && e->copy_stream) s = cudaStreamSynchronize(e->copy_stream);
+    if (s != cudaSuccess) rc = set_error(e, TNUTS_E_CUDA, std::string("tnuts_run: ") + cudaGetErrorString(s));
+  }
+  for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
   if (rc) return rc;
-  TN_CUDA(e, cudaEventRecord(e->ev1, e->stream));
-  TN_CUDA(e, cudaStreamSynchronize(e->stream));
   float ms = 0;
   TN_CUDA(e, cudaEventElapsedTime(&ms, e->ev0, e->ev1));
   e->last_run_seconds = ms * 1e-3;
   e->n_kept = keep;
   if (n_kept) *n_kept = keep;
   return TNUTS_OK;
+}
+
+int tnuts_run(tnuts_engine *h, int64_t n_transitions, int64_t first_keep, int64_t thin,
+              int64_t *n_kept) {
+  return run_segments((Engine *)h, n_transitions, first_keep, thin, nullptr, 0, n_kept);
+}
+
+int tnuts_run_streamed(tnuts_engine *h, int64_t n_transitions, int64_t first_keep, int64_t thin,
+                       double *host_draws, int64_t chunk_draws, int64_t *n_kept) {
+  Engine *e = (Engine *)h;
+  if (!host_draws) return set_error(e, TNUTS_E_ARG, "tnuts_run_streamed: host_draws is NULL");
+  return run_segments(e, n_transitions, first_keep, thin, host_draws, chunk_draws, n_kept);
 }
 
 int tnuts_num_columns(const tnuts_engine *h) {
@@ -384,6 +437,7 @@ int tnuts_set_option(tnuts_engine *h, const char *name, double value) {
   if (!e || !name) return set_error(e, TNUTS_E_ARG, "tnuts_set_option: null argument");
   const std::string n(name);
   if (n == "keep_theta") e->keep_theta = value != 0.0;
+  else if (n == "occupancy") e->occupancy = (int)value;
   else return set_error(e, TNUTS_E_ARG, "tnuts_set_option: unknown option " + n);
   return TNUTS_OK;
 }
@@ -654,20 +708,33 @@ int64_t tnuts_num_grad_evals(const tnuts_engine *h) {
   return sum_ll(e, e->st.n_grad);
 }
 
+__global__ void k_count_divergent(const double *draws, long long K, int ncol, int col, int C,
+                                  unsigned long long *out) {
+  unsigned long long n = 0;
+  const long long tot = K * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long k = i / C, c = i % C;
+    n += draws[((size_t)k * ncol + col) * C + c] != 0.0;
+  }
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, n);
+}
+
 int64_t tnuts_num_divergences(const tnuts_engine *h) {
-  const Engine *e = (const Engine *)h;
+  Engine *e = (Engine *)h;
   if (!e || !e->inited || e->n_kept == 0) return 0;
   cudaSetDevice(e->device);
-  const size_t K = (size_t)e->n_kept, C = (size_t)e->st.C;
-  std::vector<double> col(C);
-  long long s = 0;
-  for (size_t k = 0; k < K; ++k) {
-    if (cudaMemcpy(col.data(), e->out.draws + (k * e->out.ncol + e->P + 3 + ST_NUMERR) * C, 8 * C,
-                   cudaMemcpyDeviceToHost) != cudaSuccess)
-      return -1;
-    for (double v : col) s += (v != 0.0);
-  }
-  return s;
+  unsigned long long *d = nullptr, hres = 0;
+  if (cudaMalloc((void **)&d, 8) != cudaSuccess) return -1;
+  cudaMemsetAsync(d, 0, 8, e->stream);
+  k_count_divergent<<<148 * 4, 256, 0, e->stream>>>(e->out.draws, e->n_kept, e->out.ncol,
+                                                   e->P + 3 + ST_NUMERR, e->st.C, d);
+  e->launches += 1;
+  cudaMemcpyAsync(&hres, d, 8, cudaMemcpyDeviceToHost, e->stream);
+  const cudaError_t s = cudaStreamSynchronize(e->stream);
+  cudaFree(d);
+  return s == cudaSuccess ? (int64_t)hres : -1;
 }
 
 int64_t tnuts_num_kernel_launches(const tnuts_engine *h) {
@@ -688,6 +755,15 @@ int tnuts_init_tries_max(const tnuts_engine *h) {
   int m = 0;
   for (int x : v) m = x > m ? x : m;
   return m;
+}
+
+int tnuts_bench_gradient(tnuts_engine *h, int32_t reps, double *seconds) {
+  Engine *e = (Engine *)h;
+  if (!e || !e->inited || reps < 1 || !seconds) return set_error(e, TNUTS_E_ARG, "tnuts_bench_gradient: bad call");
+  if (e->strategy != STRAT_LOCKSTEP)
+    return set_error(e, TNUTS_E_UNSUPPORTED, "tnuts_bench_gradient: lock-step strategy only");
+  TN_CUDA(e, cudaSetDevice(e->device));
+  return lockstep_bench_gradient(e, reps, seconds);
 }
 
 int tnuts_host_alloc(void **p, size_t nbytes) {

@@ -21,7 +21,7 @@ struct Engine {
   tnuts_config cfg{};
   std::string err;
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool has_model = false, inited = false;
   int strategy = STRAT_THREAD;
@@ -45,6 +45,7 @@ struct Engine {
   long long launches = 0;
   double last_run_seconds = 0.0, last_init_seconds = 0.0;
   bool keep_theta = false;
+  int occupancy = 2;  // CTAs of 128 threads per SM the thread-per-chain kernel is compiled for
 
   LockstepState *ls = nullptr;
   DiagWork *diag = nullptr;
@@ -81,6 +82,7 @@ int lockstep_create(Engine *e);
 void lockstep_destroy(Engine *e);
 int lockstep_init(Engine *e, const double *theta0_dev);
 int lockstep_run(Engine *e);
+int lockstep_bench_gradient(Engine *e, int reps, double *seconds);
 int lockstep_point_lpgrad(Engine *e, const double *theta_dev, long long n, double *lp_dev,
                           double *grad_dev);
 int lockstep_point_constrain(Engine *e, const double *theta_dev, long long n, double *params_dev,

@@ -40,20 +40,52 @@ struct GradWork {  // workspaces sized for `cap` columns
   int cap = 0, chunks = 0, rows_per_chunk = 0;
 };
 
-static int logistic_plan(const ModelDev &m, int cap, int *tr, int *tch, int *chunks, int *rpc) {
+struct LogiPlan {
+  int nwn, nwm, mt, tr, tch, chunks, rpc;
+  size_t smem;
+};
+
+static int logistic_plan(const ModelDev &m, int cap, LogiPlan *p) {
   const int D = m.D;
-  *tr = D <= 128 ? 64 : 32;
-  *tch = D <= 128 ? 64 : 32;
-  const int ctiles = (cap + *tch - 1) / *tch;
-  int want = (2 * 148 + ctiles - 1) / ctiles;  // ~2 CTAs per SM in flight
-  long long maxchunks = (m.N + *tr - 1) / *tr;
-  if (want > maxchunks) want = (int)std::max<long long>(1, maxchunks);
-  if (want > 1024) want = 1024;
+  const int mtiles = (D + 7) / 8;
+  if (mtiles <= 16) {
+    p->nwn = 8;
+    p->nwm = 1;
+    p->mt = mtiles <= 1 ? 1 : mtiles <= 2 ? 2 : mtiles <= 4 ? 4 : mtiles <= 8 ? 8 : mtiles <= 13 ? 13 : 16;
+    p->tr = 64;
+  } else if (mtiles <= 32) {
+    p->nwn = 4;
+    p->nwm = 2;
+    p->mt = 16;
+    p->tr = 32;
+  } else {
+    return -1;
+  }
+  p->tch = 8 * p->nwn;
+  const int Kp = (D + 3) & ~3, LDX = ld_pad(Kp);
+  p->smem = sizeof(double) * ((size_t)Kp * (p->tch + 4) + (size_t)2 * p->tr * LDX +
+                              (size_t)p->tr * (p->tch + 4) + 2 * p->tr);
+  if (p->smem > 227 * 1024 && p->tr == 64) {  // large D with the 64-chain tiling: halve the row tile
+    p->tr = 32;
+    p->smem = sizeof(double) * ((size_t)Kp * (p->tch + 4) + (size_t)2 * p->tr * LDX +
+                                (size_t)p->tr * (p->tch + 4) + 2 * p->tr);
+  }
+  // row chunks: one CTA per SM, so make (chain tiles x row chunks) a whole number of waves of
+  // 148 CTAs (>= 4 waves when the data allow it) -- a ragged last wave idles most of the chip
+  const int ctiles = (cap + p->tch - 1) / p->tch;
+  const long long maxchunks = std::max<long long>(1, (m.N + p->tr - 1) / p->tr);
+  int want = (int)std::min<long long>(maxchunks, (4 * 148 + ctiles - 1) / ctiles);
+  for (int c = want; c <= std::min<long long>(maxchunks, want + 148); ++c)
+    if (((long long)ctiles * c) % 148 == 0) {
+      want = c;
+      break;
+    }
+  if (want > 2048) want = 2048;
   long long r = (m.N + want - 1) / want;
-  r = ((r + *tr - 1) / *tr) * *tr;  // whole row tiles per chunk
-  *rpc = (int)r;
-  *chunks = (int)((m.N + r - 1) / r);
-  return TNUTS_OK;
+  r = ((r + p->tr - 1) / p->tr) * p->tr;  // whole row tiles per chunk
+  p->rpc = (int)r;
+  p->chunks = (int)((m.N + r - 1) / r);
+  return 0;
 }
 
 static int grad_launch(Engine *e, const double *th, int C, double *lp, double *g, const int *list,
@@ -74,25 +106,27 @@ static int grad_launch(Engine *e, const double *th, int C, double *lp, double *g
       e->launches += 1;
       break;
     case TNUTS_LOGISTIC: {
-      int tr, tch, chunks, rpc;
-      logistic_plan(m, gw->cap, &tr, &tch, &chunks, &rpc);
-      const int D = m.D;
-      const dim3 grid((n_max + tch - 1) / tch, chunks);
-      const size_t smem = sizeof(double) * ((size_t)D * tch + (size_t)tr * D + (size_t)tr * tch + tr);
-#define TN_LOGI(TR, TCH, ND)                                                                      \
-  do {                                                                                            \
-    auto kfn = k_logistic_tile<TR, TCH, ND>;                                                      \
-    TN_CUDA(e, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kfn<<<grid, 256, smem, e->stream>>>(m.X, m.y, 0, m.N, D, th, C, list, count, n_all, rpc,      \
-                                        gw->part, gw->cap);                                       \
+      LogiPlan lp_;
+      if (logistic_plan(m, gw->cap, &lp_)) return set_error(e, TNUTS_E_UNSUPPORTED, "logistic regression: D > 256 not supported");
+      const int D = m.D, chunks = lp_.chunks;
+      const dim3 grid((n_max + lp_.tch - 1) / lp_.tch, chunks);
+#define TN_LOGI(NWN, NWM, MT, TR)                                                                     \
+  do {                                                                                                \
+    auto kfn = k_logistic_mma<NWN, NWM, MT, TR>;                                                      \
+    TN_CUDA(e, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp_.smem)); \
+    kfn<<<grid, 256, lp_.smem, e->stream>>>(m.X, m.y, m.N, D, th, C, list, count, n_all, lp_.rpc,     \
+                                            gw->part, gw->cap);                                       \
   } while (0)
-      if (D <= 16) TN_LOGI(64, 64, 1);
-      else if (D <= 32) TN_LOGI(64, 64, 2);
-      else if (D <= 64) TN_LOGI(64, 64, 4);
-      else if (D <= 112) TN_LOGI(64, 64, 7);
-      else if (D <= 128) TN_LOGI(64, 64, 8);
-      else if (D <= 256) TN_LOGI(32, 32, 16);
-      else return set_error(e, TNUTS_E_UNSUPPORTED, "logistic regression: D > 256 not supported");
+      if (lp_.nwm == 2) TN_LOGI(4, 2, 16, 32);
+      else if (lp_.tr == 32) {
+        if (lp_.mt == 16) TN_LOGI(8, 1, 16, 32);
+        else TN_LOGI(8, 1, 13, 32);
+      } else if (lp_.mt == 1) TN_LOGI(8, 1, 1, 64);
+      else if (lp_.mt == 2) TN_LOGI(8, 1, 2, 64);
+      else if (lp_.mt == 4) TN_LOGI(8, 1, 4, 64);
+      else if (lp_.mt == 8) TN_LOGI(8, 1, 8, 64);
+      else if (lp_.mt == 13) TN_LOGI(8, 1, 13, 64);
+      else TN_LOGI(8, 1, 16, 64);
 #undef TN_LOGI
       const dim3 rg((n_max + 127) / 128, D + 1);
       k_logistic_reduce<<<rg, 128, 0, e->stream>>>(gw->part, chunks, D, gw->cap, count, n_all, gw->lik);
@@ -114,8 +148,10 @@ static int grad_launch(Engine *e, const double *th, int C, double *lp, double *g
 static int gradwork_alloc(Engine *e, GradWork *gw, int cap, std::vector<void *> *pool) {
   gw->cap = cap;
   if (e->model.family != TNUTS_LOGISTIC) return TNUTS_OK;
-  int tr, tch;
-  logistic_plan(e->model, cap, &tr, &tch, &gw->chunks, &gw->rows_per_chunk);
+  LogiPlan lp_;
+  if (logistic_plan(e->model, cap, &lp_)) return set_error(e, TNUTS_E_UNSUPPORTED, "logistic regression: D > 256 not supported");
+  gw->chunks = lp_.chunks;
+  gw->rows_per_chunk = lp_.rpc;
   const size_t D1 = (size_t)e->model.D + 1;
   void *p = nullptr;
   TN_CUDA(e, cudaMalloc(&p, 8 * (size_t)gw->chunks * D1 * cap));
@@ -516,6 +552,25 @@ int lockstep_run(Engine *e) {
     e->launches += 1;
   }
   TN_CUDA(e, cudaGetLastError());
+  return TNUTS_OK;
+}
+
+// times `reps` gradient evaluations of ALL chains at their current positions (CUDA events on the
+// engine's stream); used by bench.py for the roofline of the gradient kernel alone
+int lockstep_bench_gradient(Engine *e, int reps, double *seconds) {
+  LockstepState *ls = e->ls;
+  ChainState &st = e->st;
+  const int C = st.C;
+  int rc;
+  if ((rc = grad_launch(e, st.theta, C, ls->ts.zlp, ls->zg, nullptr, nullptr, C, C, gw_of(e)))) return rc;
+  TN_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+  for (int i = 0; i < reps; ++i)
+    if ((rc = grad_launch(e, st.theta, C, ls->ts.zlp, ls->zg, nullptr, nullptr, C, C, gw_of(e)))) return rc;
+  TN_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+  TN_CUDA(e, cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  TN_CUDA(e, cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  *seconds = ms * 1e-3;
   return TNUTS_OK;
 }
 

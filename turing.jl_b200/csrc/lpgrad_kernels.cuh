@@ -33,6 +33,16 @@ __device__ __forceinline__ double d_logistic(double x) {
   return e / (1.0 + e);
 }
 
+// sigma(eta) and log1pexp(eta) from ONE exponential: e = exp(-|eta|),
+//   log1pexp = max(eta, 0) + log1p(e),  sigma = eta >= 0 ? 1/(1+e) : e/(1+e)
+// (agrees with StatsFuns.log1pexp / logistic to rounding on the whole real line)
+__device__ __forceinline__ void d_sigmoid_log1pexp(double x, double &sig, double &l1pe) {
+  const double e = exp(-fabs(x));
+  const double t = 1.0 / (1.0 + e);
+  sig = x >= 0.0 ? t : e * t;
+  l1pe = fmax(x, 0.0) + log1p(e);
+}
+
 // ------------------------------------------------------------------------------------------
 __global__ void k_lpgrad_small(ModelDev m, const double *th, int C, double *lp_out, double *g,
                                const int *list, const int *count, int n_all) {
@@ -109,129 +119,223 @@ __global__ void k_lpgrad_small(ModelDev m, const double *th, int C, double *lp_o
 }
 
 // ------------------------------------------------------------------------------------------
-// logistic regression: fused eta / residual / X^T R over one row chunk and one chain tile.
-//   grid = (chain tiles, row chunks), 256 threads.
-//   TR rows x TCH chains per tile; thread (ty = tid / 16, tx = tid % 16) owns the
-//   (TR/16) x (TCH/16) block of eta and, for G, the dims {ty + 16 i} x (TCH/16) chains.
+// logistic regression: fused eta / residual / X^T R over one row chunk and one chain tile on
+// the fp64 tensor path (DMMA, mma.sync.m8n8k4.f64).  tcgen05 has no f64 kind, and measured on
+// this B200 DMMA and DFMA both peak at 37.2 TFLOP/s, so DMMA is used for its 8x lower issue
+// and register-bandwidth pressure, not for a higher ceiling.
+//
+//   grid = (chain tiles, row chunks); 256 threads = 8 warps; one CTA per SM.
+//   per row tile of TR rows (X tile double-buffered in shared memory with cp.async):
+//     GEMM1  eta[TR x TCH]  = Xs[TR x D] * Bs[D x TCH]          warp grid WM1 x WN1
+//     elementwise: r = y - sigma(eta), lp += y*eta - log1pexp(eta)  -> Rs[TR x TCH]
+//     GEMM2  G[D x TCH]    += Xs^T[D x TR] * Rs[TR x TCH]       warp grid NWM x NWN,
+//            accumulators (MT m-tiles x 2 doubles) stay in registers for the whole row chunk
+//   Shared-memory leading dimensions are == 4 (mod 16) doubles, which makes every DMMA
+//   fragment load (8 rows x 4 k or 4 k x 8 cols per warp) bank-conflict free.
+//
+// Fragment layout of mma.m8n8k4.f64 (lane l): a0 = A[l>>2][l&3], b0 = B[l&3][l>>2],
+// c0,c1 = C[l>>2][2*(l&3) + {0,1}].
 // ------------------------------------------------------------------------------------------
-template <int TR, int TCH, int ND>
-__global__ void __launch_bounds__(256)
-k_logistic_tile(const double *__restrict__ X, const double *__restrict__ y, long long row0,
-                long long nrows, int D, const double *__restrict__ th, int C,
-                const int *__restrict__ list, const int *__restrict__ count, int n_all,
-                int rows_per_chunk, double *__restrict__ part /* [chunks][D+1][cap] */, int cap) {
-  constexpr int RM = TR / 16, CM = TCH / 16;
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__host__ __device__ inline int ld_pad(int n) {  // smallest m >= n with m == 4 (mod 16)
+  int m = n + ((4 - (n % 16)) + 16) % 16;
+  return m;
+}
+
+template <int NWN, int NWM, int MT, int TR>
+__global__ void __launch_bounds__(256, 1)
+k_logistic_mma(const double *__restrict__ X, const double *__restrict__ y, long long nrows, int D,
+               const double *__restrict__ th, int C, const int *__restrict__ list,
+               const int *__restrict__ count, int n_all, int rows_per_chunk,
+               double *__restrict__ part /* [chunks][D+1][cap] */, int cap) {
+  constexpr int TCH = 8 * NWN;                 // chains per CTA
+  constexpr int WN1 = (NWN >= 8) ? 4 : 2;      // GEMM1 warp grid
+  constexpr int WM1 = 8 / WN1;
+  constexpr int MT1 = (TR / 8) / WM1;          // m-tiles per warp (rows)
+  constexpr int NT1 = NWN / WN1;               // n-tiles per warp (chains)
+  static_assert(NWN * NWM == 8 && MT1 >= 1 && NT1 >= 1, "bad tiling");
+  constexpr int LDB = TCH + 4, LDR = TCH + 4;
   extern __shared__ double sm[];
-  double *Bs = sm;                       // [D][TCH]
-  double *Xs = Bs + (size_t)D * TCH;     // [TR][D]
-  double *Rs = Xs + (size_t)TR * D;      // [TR][TCH]
-  double *Ys = Rs + (size_t)TR * TCH;    // [TR]
+  const int Kp = (D + 3) & ~3;
+  const int LDX = ld_pad(Kp);
+  double *Bs = sm;                              // [Kp][LDB]
+  double *Xs = Bs + (size_t)Kp * LDB;           // [2][TR][LDX]
+  double *Rs = Xs + (size_t)2 * TR * LDX;       // [TR][LDR]
+  double *Ys = Rs + (size_t)TR * LDR;           // [2][TR]
   const int n = count ? *count : n_all;
   const int k0 = blockIdx.x * TCH;
   if (k0 >= n) return;
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
   const int chunk = blockIdx.y;
-  // B tile (gathered through the work list)
-  for (int i = tid; i < D * TCH; i += 256) {
-    const int d = i / TCH, cc = i % TCH;
-    const int k = k0 + cc;
-    double v = 0.0;
-    if (k < n) {
-      const int c = list ? list[k] : k;
-      v = th[(size_t)d * C + c];
-    }
-    Bs[i] = v;
-  }
-  double gacc[ND][CM];
-#pragma unroll
-  for (int i = 0; i < ND; ++i)
-#pragma unroll
-    for (int q = 0; q < CM; ++q) gacc[i][q] = 0.0;
-  double lpacc[CM];
-#pragma unroll
-  for (int q = 0; q < CM; ++q) lpacc[q] = 0.0;
-
   const long long rbeg = (long long)chunk * rows_per_chunk;
   long long rend = rbeg + rows_per_chunk;
   if (rend > nrows) rend = nrows;
-  for (long long r0 = rbeg; r0 < rend; r0 += TR) {
+  const int ntile = (int)((rend - rbeg + TR - 1) / TR);
+
+  auto prefetch = [&](int t, int buf) {
+    const long long r0 = rbeg + (long long)t * TR;
     const int nr = (int)((rend - r0) < TR ? (rend - r0) : TR);
-    __syncthreads();  // previous tile fully consumed (also covers the B tile on the 1st pass)
-    // X tile: TR*D contiguous doubles
-    const double *xg = X + (size_t)(row0 + r0) * D;
-    for (int i = tid; i < TR * D; i += 256) Xs[i] = (i < nr * D) ? xg[i] : 0.0;
-    if (tid < TR) Ys[tid] = (tid < nr) ? y[row0 + r0 + tid] : 0.0;
-    __syncthreads();
-    // eta micro-tile
-    double eta[RM][CM];
-#pragma unroll
-    for (int i = 0; i < RM; ++i)
-#pragma unroll
-      for (int q = 0; q < CM; ++q) eta[i][q] = 0.0;
-    for (int k = 0; k < D; ++k) {
-      double a[RM], b[CM];
-#pragma unroll
-      for (int i = 0; i < RM; ++i) a[i] = Xs[(ty * RM + i) * D + k];
-#pragma unroll
-      for (int q = 0; q < CM; ++q) b[q] = Bs[k * TCH + tx * CM + q];
-#pragma unroll
-      for (int i = 0; i < RM; ++i)
-#pragma unroll
-        for (int q = 0; q < CM; ++q) eta[i][q] += a[i] * b[q];
+    double *xb = Xs + (size_t)buf * TR * LDX;
+    const double *xg = X + (size_t)r0 * D;
+    // 8 rows per pass: thread (tid >> 5) picks the row, the 32 lanes stride along it
+    for (int r = tid >> 5; r < TR; r += 8) {
+      if (r < nr) {
+        for (int d = lane; d < D; d += 32) cp_async8(xb + r * LDX + d, xg + (size_t)r * D + d);
+      } else {
+        for (int d = lane; d < D; d += 32) xb[r * LDX + d] = 0.0;
+      }
     }
-    // residuals + log-likelihood terms
+    if (tid < TR) {
+      if (tid < nr) cp_async8(Ys + buf * TR + tid, y + r0 + tid);
+      else Ys[buf * TR + tid] = 0.0;
+    }
+  };
+
+  // zero the K padding of both X buffers once, load the B tile through the work list
+  for (int i = tid; i < 2 * TR * (LDX - D); i += 256) {
+    const int r = i / (LDX - D), d = D + i % (LDX - D);
+    Xs[(size_t)r * LDX + d] = 0.0;
+  }
+  for (int i = tid; i < Kp * TCH; i += 256) {
+    const int d = i / TCH, cc = i - d * TCH;
+    const int k = k0 + cc;
+    double v = 0.0;
+    if (k < n && d < D) {
+      const int c = list ? list[k] : k;
+      v = th[(size_t)d * C + c];
+    }
+    Bs[d * LDB + cc] = v;
+  }
+  if (ntile > 0) prefetch(0, 0);
+  cp_async_commit();
+
+  // GEMM2 accumulators: this warp's n-tile (wn2) and m-tiles {wm2 + NWM * i}
+  const int wn2 = warp % NWN, wm2 = warp / NWN;
+  double gacc[MT][2];
 #pragma unroll
-    for (int i = 0; i < RM; ++i) {
-      const int row = ty * RM + i;
-      const double yy = Ys[row];
+  for (int i = 0; i < MT; ++i) gacc[i][0] = gacc[i][1] = 0.0;
+  // GEMM1 position
+  const int wm1 = warp / WN1, wn1 = warp % WN1;
+  double lpacc[NT1][2];
+#pragma unroll
+  for (int q = 0; q < NT1; ++q) lpacc[q][0] = lpacc[q][1] = 0.0;
+
+  for (int t = 0; t < ntile; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < ntile) prefetch(t + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const double *xb = Xs + (size_t)buf * TR * LDX;
+    const long long r0 = rbeg + (long long)t * TR;
+    const int nr = (int)((rend - r0) < TR ? (rend - r0) : TR);
+    // ---- GEMM1: eta = X * B ----
+    double eta[MT1][NT1][2];
+#pragma unroll
+    for (int i = 0; i < MT1; ++i)
+#pragma unroll
+      for (int q = 0; q < NT1; ++q) eta[i][q][0] = eta[i][q][1] = 0.0;
+    for (int kk = 0; kk < Kp; kk += 4) {
+      double a[MT1], b[NT1];
+#pragma unroll
+      for (int i = 0; i < MT1; ++i) a[i] = xb[((wm1 * MT1 + i) * 8 + lr) * LDX + kk + lc];
+#pragma unroll
+      for (int q = 0; q < NT1; ++q) b[q] = Bs[(kk + lc) * LDB + (wn1 * NT1 + q) * 8 + lr];
+#pragma unroll
+      for (int i = 0; i < MT1; ++i)
+#pragma unroll
+        for (int q = 0; q < NT1; ++q) dmma884(eta[i][q][0], eta[i][q][1], a[i], b[q]);
+    }
+    // ---- residuals / log-likelihood ----
+#pragma unroll
+    for (int i = 0; i < MT1; ++i) {
+      const int row = (wm1 * MT1 + i) * 8 + lr;
+      const double yy = Ys[buf * TR + row];
       const bool live = row < nr;
 #pragma unroll
-      for (int q = 0; q < CM; ++q) {
-        const double e = eta[i][q];
-        double r = 0.0;
-        if (live) {
-          r = yy - d_logistic(e);
-          lpacc[q] += yy * e - d_log1pexp(e);
+      for (int q = 0; q < NT1; ++q) {
+        double r2[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double e = eta[i][q][h];
+          double r = 0.0;
+          if (live) {
+            double sg, l1;
+            d_sigmoid_log1pexp(e, sg, l1);
+            r = yy - sg;
+            lpacc[q][h] += yy * e - l1;
+          }
+          r2[h] = r;
         }
-        Rs[row * TCH + tx * CM + q] = r;
+        double *dst = Rs + row * LDR + (wn1 * NT1 + q) * 8 + 2 * lc;
+        dst[0] = r2[0];
+        dst[1] = r2[1];
       }
     }
     __syncthreads();
-    // G += X^T R
-    for (int row = 0; row < TR; ++row) {
-      double r[CM];
+    // ---- GEMM2: G += X^T * R ----
+    for (int kk = 0; kk < TR; kk += 4) {
+      const double b = Rs[(kk + lc) * LDR + wn2 * 8 + lr];
 #pragma unroll
-      for (int q = 0; q < CM; ++q) r[q] = Rs[row * TCH + tx * CM + q];
-#pragma unroll
-      for (int i = 0; i < ND; ++i) {
-        const int d = ty + 16 * i;
-        const double x = (d < D) ? Xs[row * D + d] : 0.0;
-#pragma unroll
-        for (int q = 0; q < CM; ++q) gacc[i][q] += x * r[q];
+      for (int i = 0; i < MT; ++i) {
+        const int d = (wm2 + NWM * i) * 8 + lr;
+        const double a = (d < D) ? xb[(kk + lc) * LDX + d] : 0.0;
+        dmma884(gacc[i][0], gacc[i][1], a, b);
       }
     }
+    __syncthreads();  // Rs and this X buffer are free for the next iteration
   }
-  // epilogue: partial gradient of this row chunk, and the lp partial (fixed-order over ty)
+  cp_async_wait<0>();
+  // ---- epilogue ----
   double *pc = part + (size_t)chunk * (D + 1) * cap;
 #pragma unroll
-  for (int i = 0; i < ND; ++i) {
-    const int d = ty + 16 * i;
+  for (int i = 0; i < MT; ++i) {
+    const int d = (wm2 + NWM * i) * 8 + lr;
     if (d < D) {
 #pragma unroll
-      for (int q = 0; q < CM; ++q) {
-        const int k = k0 + tx * CM + q;
-        if (k < n) pc[(size_t)d * cap + k] = gacc[i][q];
+      for (int h = 0; h < 2; ++h) {
+        const int k = k0 + wn2 * 8 + 2 * lc + h;
+        if (k < n) pc[(size_t)d * cap + k] = gacc[i][h];
       }
     }
   }
-  __syncthreads();
-  double *Ls = Rs;  // [16][TCH]
+  // lp: sum over the 8 row-lanes of the warp, then over the WM1 warps sharing the columns
 #pragma unroll
-  for (int q = 0; q < CM; ++q) Ls[ty * TCH + tx * CM + q] = lpacc[q];
+  for (int q = 0; q < NT1; ++q)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double v = lpacc[q][h];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      lpacc[q][h] = v;
+    }
+  double *Ls = Rs;  // [WM1][TCH]
+  if (lr == 0) {
+#pragma unroll
+    for (int q = 0; q < NT1; ++q)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) Ls[wm1 * TCH + (wn1 * NT1 + q) * 8 + 2 * lc + h] = lpacc[q][h];
+  }
   __syncthreads();
   if (tid < TCH) {
     double s = 0.0;
-    for (int w = 0; w < 16; ++w) s += Ls[w * TCH + tid];
+    for (int w = 0; w < WM1; ++w) s += Ls[w * TCH + tid];
     const int k = k0 + tid;
     if (k < n) pc[(size_t)D * cap + k] = s;
   }

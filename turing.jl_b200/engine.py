@@ -69,6 +69,16 @@ class Engine:
         self.n_kept = k.value
         return self.n_kept
 
+    def run_streamed(self, n_transitions, first_keep, thin, out, chunk_draws=100):
+        """run + overlapped D2H of the kept draws straight into `out` [n_kept, ncol, C]"""
+        k = C.c_int64(0)
+        assert out.flags.c_contiguous and out.dtype == np.float64
+        check(self.h, self.L.tnuts_run_streamed(self.h, int(n_transitions), int(first_keep),
+                                                int(thin), _dp(out), int(chunk_draws), C.byref(k)))
+        self.n_kept = k.value
+        assert out.shape[0] >= self.n_kept
+        return self.n_kept
+
     def set_option(self, name, value):
         check(self.h, self.L.tnuts_set_option(self.h, name.encode(), float(value)))
 
@@ -167,6 +177,11 @@ class Engine:
         e = np.empty(self.P)
         check(self.h, self.L.tnuts_diagnostics(self.h, _dp(r), _dp(e)))
         return r, e
+
+    def bench_gradient(self, reps=5):
+        s = C.c_double(0.0)
+        check(self.h, self.L.tnuts_bench_gradient(self.h, int(reps), C.byref(s)))
+        return s.value / reps
 
     def comm_init(self, unique_id, world, rank):
         check(self.h, self.L.tnuts_comm_init(self.h, unique_id, world, rank))

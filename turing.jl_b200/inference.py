@@ -72,7 +72,7 @@ def _resolve_initial_params(model, initial_params, n_chains):
 def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_params=None,
            initial_state=None, nadapts=None, discard_adapt=True, discard_initial=-1, thinning=1,
            save_state=False, progress=False, verbose=True, check_model=True, devices=None,
-           diagnostics=False, strategy=0, keep_engine=False):
+           diagnostics=False, strategy=0, keep_engine=False, chain_offset=0, chunk_draws=None):
     """sample(model, spl, N) | sample(model, spl, ensemble, N, n_chains)."""
     if len(args) == 1:
         N, n_chains, single = int(args[0]), 1, True
@@ -115,11 +115,13 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
         devices, ndev = devices[:n_chains], n_chains
     bounds = [n_chains * i // ndev for i in range(ndev + 1)]
 
+    if chunk_draws is None:
+        chunk_draws = max(1, -(-N // 10))
     t_start = time.perf_counter()
     engines = []
     for i, dev in enumerate(devices):
         engines.append(Engine(model, spl, bounds[i + 1] - bounds[i], _nadapts, seed64, device=dev,
-                              chain_offset=bounds[i], strategy=strategy))
+                              chain_offset=chain_offset + bounds[i], strategy=strategy))
     results = [None] * ndev
     errors = [None] * ndev
     # bundle_samples target: (iterations x names x chains); the engine's device layout is
@@ -153,16 +155,18 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
                 value[0, :P, lo:hi] = first[0].T
                 value[0, P:P + 3, lo:hi] = first[1].T
             if n_tr > 0:
-                e.run(n_tr, first_keep, thinning)
-                if ndev == 1 and row == 0:
-                    e.fetch_draws(value)  # straight into the chain array: one contiguous D2H
+                if ndev == 1:
+                    # straight into the chain array, D2H overlapped with the computation
+                    e.run_streamed(n_tr, first_keep, thinning, value[row:], chunk_draws)
                 else:
+                    e.run(n_tr, first_keep, thinning)
                     value[row:row + e.n_kept, :, lo:hi] = e.fetch_draws()
             else:
                 e.n_kept = 0
             diag = e.diagnostics() if (diagnostics and ndev == 1 and e.n_kept >= 4) else None
+            ndiv = e.divergences if e.n_kept else 0
             results[i] = (diag, e.grad_evals, e.device_seconds, e.stepsize(),
-                          e.get_state() if save_state else None, e.launches)
+                          e.get_state() if save_state else None, e.launches, ndiv)
         except Exception as ex:  # re-raised on the caller's thread
             errors[i] = ex
 
@@ -191,6 +195,7 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
         "gpu_launches": int(sum(r[5] for r in results)),
         "step_size": np.concatenate([r[3] for r in results]),
         "algorithm": spl.algorithm,
+        "n_divergent": int(sum(r[6] for r in results)),
         "nadapts": _nadapts, "discard_initial": _discard, "thinning": thinning, "seed": seed64,
     }
     if results[0][0] is not None:
@@ -210,7 +215,9 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
 
 def post_sample_hook(chain, spl, verbose=True):
     """src/mcmc/hmc.jl:476-486"""
-    n_div = int(np.nansum(chain["numerical_error"]))
+    n_div = chain.info.get("n_divergent")
+    if n_div is None:  # chains not produced by the engine: count on the host like the reference
+        n_div = int(np.nansum(chain["numerical_error"]))
     if verbose and n_div > 0:
         warnings.warn("There were %d divergent transitions. Consider reparameterising your model or "
                       "using a smaller step size. For adaptive samplers such as NUTS and HMCDA, "
