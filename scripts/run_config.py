@@ -1,0 +1,61 @@
+"""Full-job measurement of the big BASELINE.json configs (too long for the default bench.py run):
+  python scripts/run_config.py logistic   # configs[2]: N=100k, D=100, 4096 chains, NUTS(0.8), 1000 draws
+  python scripts/run_config.py hier       # configs[3]: 1000 groups x 100 obs, D=2005, 1024 chains
+Prints one JSON line (same keys as bench.py where they apply)."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import turing_jl_b200 as T
+
+def main():
+    which = sys.argv[1]
+    scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+    N = 1000
+    if which == "logistic":
+        model, C, name = T.models.config3_logistic(), int(4096 * scale), "BASELINE.json configs[2]: logistic regression N=100000 D=100 fp64"
+        flops_per_grad = 4.0 * model.N * model.D
+    else:
+        model, C, name = T.models.config4_hier(), int(1024 * scale), "BASELINE.json configs[3]: hierarchical regression 1000 groups x 100 obs, D=2005"
+        flops_per_grad = None
+    spl = T.NUTS(0.8)
+    nad = 500
+    t0 = time.perf_counter()
+    eng = T.Engine(model, spl, C, nad, seed=11)
+    t_create = time.perf_counter() - t0
+    t0 = time.perf_counter(); eng.init(); t_init = time.perf_counter() - t0
+    g_init = eng.grad_evals
+    grad_ms = eng.bench_gradient(5) * 1e3
+    out = T.pinned.empty((N, eng.ncol, C))
+    t0 = time.perf_counter()
+    eng.run_streamed(nad + N - 1, nad, 1, out, 100)
+    t_run = time.perf_counter() - t0
+    grads = eng.grad_evals
+    t0 = time.perf_counter(); rhat, ess = eng.diagnostics(); t_diag = time.perf_counter() - t0
+    P = model.D
+    st = out[:, P + 3:, :]
+    line = {
+        "config": {"workload": name + ", NUTS(0.8), %d chains, %d draws + %d warm-up" % (C, N, nad)},
+        "metric": "grad_evals_per_sec", "value": grads / (t_init + t_run), "unit": "grad_evals/s",
+        "e2e_seconds": t_create + t_init + t_run, "init_seconds": t_init, "run_seconds": t_run,
+        "grad_evals": grads, "grad_evals_init": g_init,
+        "ess_bulk_min": float(ess.min()), "ess_bulk_min_per_sec": float(ess.min() / (t_create + t_init + t_run)),
+        "rhat_max": float(rhat.max()), "diag_seconds": t_diag,
+        "tree_depth_mean": float(st[:, 6].mean()), "tree_depth_max": float(st[:, 6].max()),
+        "n_steps_mean": float(st[:, 0].mean()), "acceptance_mean": float(st[:, 1].mean()),
+        "divergent": int(st[:, 7].sum()), "step_size_mean": float(eng.stepsize().mean()),
+        "gradient_kernel_ms_all_chains": grad_ms, "gpu_launches": int(eng.launches),
+    }
+    if flops_per_grad:
+        line["roofline"] = {"bound": "tensor", "unit": "TFLOP/s", "achieved": flops_per_grad * C / (grad_ms * 1e-3) / 1e12,
+                            "peak": 37.19, "peak_source": "measured here: mma.sync f64 (scripts/fp64_peak.cu); tcgen05 has no f64 kind",
+                            "kernel": "k_logistic_mma"}
+        line["roofline"]["frac"] = line["roofline"]["achieved"] / 37.19
+        line["sustained_tflops_whole_job"] = grads * flops_per_grad / (t_init + t_run) / 1e12
+    else:
+        line["roofline"] = {"bound": "hbm", "unit": "GB/s", "achieved": 6 * model.D * 8 * grads / t_run / 1e9, "peak": 6545.9}
+        line["roofline"]["frac"] = line["roofline"]["achieved"] / 6545.9
+    print(json.dumps(line))
+    eng.close()
+
+if __name__ == "__main__":
+    main()

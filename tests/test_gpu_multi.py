@@ -19,15 +19,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_chain_shards_union_equals_single_engine(built, strategy, model_name):
     model = T.EightSchools() if model_name == "eight" else T.models.synthetic_logistic(200, 6, seed=2)
     spl = T.NUTS(20, 0.8)
-    full = T.Engine(model, spl, 40, 20, seed=3, strategy=strategy)
+    nch = 40 if strategy == 1 else 150     # lock-step: more than one 64-chain tile per engine
+    full = T.Engine(model, spl, nch, 20, seed=3, strategy=strategy)
     full.init()
     full.run(30, 1, 1)
     a = full.fetch_draws()
     full.close()
     parts = []
-    b = D.chain_bounds(40, 3)
+    b = D.chain_bounds(nch, 3)
     for r in range(3):
-        e = D.make_chain_sharded_engine(model, spl, 40, 20, 3, r, 3, device=0)
+        e = D.make_chain_sharded_engine(model, spl, nch, 20, 3, r, 3, device=0)
         if strategy == 2:
             e.close()
             e = T.Engine(model, spl, b[r + 1] - b[r], 20, 3, device=0, chain_offset=b[r], strategy=2)

@@ -438,6 +438,7 @@ int tnuts_set_option(tnuts_engine *h, const char *name, double value) {
   const std::string n(name);
   if (n == "keep_theta") e->keep_theta = value != 0.0;
   else if (n == "occupancy") e->occupancy = (int)value;
+
   else return set_error(e, TNUTS_E_ARG, "tnuts_set_option: unknown option " + n);
   return TNUTS_OK;
 }

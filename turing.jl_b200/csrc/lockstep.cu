@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "engine.cuh"
@@ -37,11 +38,15 @@ static inline int tiles(int C) { return (C + kTileC - 1) / kTileC; }
 // ------------------------------------------------------------------------------------------
 struct GradWork {  // workspaces sized for `cap` columns
   double *part = nullptr, *lik = nullptr;
-  int cap = 0, chunks = 0, rows_per_chunk = 0;
+  size_t part_elems = 0;
+  int cap = 0, chunks = 0, rows_per_chunk = 0, stride = 0;
 };
 
+// tuning knob for experiments: TNUTS_LOGISTIC_GROUPS=1 selects the single-group kernel
+int g_logistic_groups = [] { const char *v = getenv("TNUTS_LOGISTIC_GROUPS"); return v ? atoi(v) : 2; }();
+
 struct LogiPlan {
-  int nwn, nwm, mt, tr, tch, chunks, rpc;
+  int nwn, nwm, mt, tr, tch, chunks, rpc, ng;
   size_t smem;
 };
 
@@ -63,24 +68,30 @@ static int logistic_plan(const ModelDev &m, int cap, LogiPlan *p) {
   }
   p->tch = 8 * p->nwn;
   const int Kp = (D + 3) & ~3, LDX = ld_pad(Kp);
-  p->smem = sizeof(double) * ((size_t)Kp * (p->tch + 4) + (size_t)2 * p->tr * LDX +
-                              (size_t)p->tr * (p->tch + 4) + 2 * p->tr);
-  if (p->smem > 227 * 1024 && p->tr == 64) {  // large D with the 64-chain tiling: halve the row tile
-    p->tr = 32;
-    p->smem = sizeof(double) * ((size_t)Kp * (p->tch + 4) + (size_t)2 * p->tr * LDX +
-                                (size_t)p->tr * (p->tch + 4) + 2 * p->tr);
-  }
-  // row chunks: one CTA per SM, so make (chain tiles x row chunks) a whole number of waves of
-  // 148 CTAs (>= 4 waves when the data allow it) -- a ragged last wave idles most of the chip
-  const int ctiles = (cap + p->tch - 1) / p->tch;
-  const long long maxchunks = std::max<long long>(1, (m.N + p->tr - 1) / p->tr);
-  int want = (int)std::min<long long>(maxchunks, (4 * 148 + ctiles - 1) / ctiles);
-  for (int c = want; c <= std::min<long long>(maxchunks, want + 148); ++c)
-    if (((long long)ctiles * c) % 148 == 0) {
-      want = c;
-      break;
+  auto smem_of = [&](int tr, int ng) {
+    return sizeof(double) * ((size_t)Kp * (p->tch + 4) +
+                             (size_t)ng * ((size_t)2 * tr * LDX + (size_t)tr * (p->tch + 4) + 2 * tr));
+  };
+  // preferred: two ping-pong groups of 8 warps with 32-row tiles (16 warps per SM)
+  p->ng = 2;
+  p->tr = 32;
+  p->smem = smem_of(32, 2);
+  if (p->smem > 227 * 1024 || p->nwm == 2 || p->mt > 13 || g_logistic_groups == 1) {
+    p->ng = 1;
+    p->tr = (p->nwm == 2) ? 32 : 64;
+    p->smem = smem_of(p->tr, 1);
+    if (p->smem > 227 * 1024 && p->tr == 64) {
+      p->tr = 32;
+      p->smem = smem_of(32, 1);
     }
-  if (want > 2048) want = 2048;
+  }
+  // row chunks: a FIXED cut of the rows (a function of N and the tile height only), so the
+  // summation order of a chain's gradient never depends on how many chains run beside it:
+  // same seed => bit-identical chains for any chain count / sharding.  296 chunks = 148 CTAs
+  // of two groups: a single chain tile already fills the chip, 64 tiles make 64 full waves.
+  (void)cap;
+  const long long maxchunks = std::max<long long>(1, (m.N + p->tr - 1) / p->tr);
+  int want = (int)std::min<long long>(maxchunks, 296);
   long long r = (m.N + want - 1) / want;
   r = ((r + p->tr - 1) / p->tr) * p->tr;  // whole row tiles per chunk
   p->rpc = (int)r;
@@ -108,28 +119,35 @@ static int grad_launch(Engine *e, const double *th, int C, double *lp, double *g
     case TNUTS_LOGISTIC: {
       LogiPlan lp_;
       if (logistic_plan(m, gw->cap, &lp_)) return set_error(e, TNUTS_E_UNSUPPORTED, "logistic regression: D > 256 not supported");
+      const int stride = gw->stride;
       const int D = m.D, chunks = lp_.chunks;
-      const dim3 grid((n_max + lp_.tch - 1) / lp_.tch, chunks);
-#define TN_LOGI(NWN, NWM, MT, TR)                                                                     \
+      const dim3 grid((n_max + lp_.tch - 1) / lp_.tch, (chunks + lp_.ng - 1) / lp_.ng);
+#define TN_LOGI(NWN, NWM, MT, TR, NG)                                                                 \
   do {                                                                                                \
-    auto kfn = k_logistic_mma<NWN, NWM, MT, TR>;                                                      \
+    auto kfn = k_logistic_mma<NWN, NWM, MT, TR, NG>;                                                  \
     TN_CUDA(e, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp_.smem)); \
-    kfn<<<grid, 256, lp_.smem, e->stream>>>(m.X, m.y, m.N, D, th, C, list, count, n_all, lp_.rpc,     \
-                                            gw->part, gw->cap);                                       \
+    kfn<<<grid, 256 * NG, lp_.smem, e->stream>>>(m.X, m.y, m.N, D, th, C, list, count, n_all,         \
+                                                 lp_.rpc, gw->part, stride);                          \
   } while (0)
-      if (lp_.nwm == 2) TN_LOGI(4, 2, 16, 32);
+      if (lp_.ng == 2) {
+        if (lp_.mt == 1) TN_LOGI(8, 1, 1, 32, 2);
+        else if (lp_.mt == 2) TN_LOGI(8, 1, 2, 32, 2);
+        else if (lp_.mt == 4) TN_LOGI(8, 1, 4, 32, 2);
+        else if (lp_.mt == 8) TN_LOGI(8, 1, 8, 32, 2);
+        else TN_LOGI(8, 1, 13, 32, 2);
+      } else if (lp_.nwm == 2) TN_LOGI(4, 2, 16, 32, 1);
       else if (lp_.tr == 32) {
-        if (lp_.mt == 16) TN_LOGI(8, 1, 16, 32);
-        else TN_LOGI(8, 1, 13, 32);
-      } else if (lp_.mt == 1) TN_LOGI(8, 1, 1, 64);
-      else if (lp_.mt == 2) TN_LOGI(8, 1, 2, 64);
-      else if (lp_.mt == 4) TN_LOGI(8, 1, 4, 64);
-      else if (lp_.mt == 8) TN_LOGI(8, 1, 8, 64);
-      else if (lp_.mt == 13) TN_LOGI(8, 1, 13, 64);
-      else TN_LOGI(8, 1, 16, 64);
+        if (lp_.mt == 16) TN_LOGI(8, 1, 16, 32, 1);
+        else TN_LOGI(8, 1, 13, 32, 1);
+      } else if (lp_.mt == 1) TN_LOGI(8, 1, 1, 64, 1);
+      else if (lp_.mt == 2) TN_LOGI(8, 1, 2, 64, 1);
+      else if (lp_.mt == 4) TN_LOGI(8, 1, 4, 64, 1);
+      else if (lp_.mt == 8) TN_LOGI(8, 1, 8, 64, 1);
+      else if (lp_.mt == 13) TN_LOGI(8, 1, 13, 64, 1);
+      else TN_LOGI(8, 1, 16, 64, 1);
 #undef TN_LOGI
       const dim3 rg((n_max + 127) / 128, D + 1);
-      k_logistic_reduce<<<rg, 128, 0, e->stream>>>(gw->part, chunks, D, gw->cap, count, n_all, gw->lik);
+      k_logistic_reduce<<<rg, 128, 0, e->stream>>>(gw->part, chunks, D, stride, count, n_all, gw->lik, gw->cap);
       if (e->world > 1 && e->cfg.row_shards > 1) {
         int rc = comm_allreduce_sum(e, gw->lik, (size_t)(D + 1) * gw->cap);
         if (rc) return rc;
@@ -152,9 +170,11 @@ static int gradwork_alloc(Engine *e, GradWork *gw, int cap, std::vector<void *> 
   if (logistic_plan(e->model, cap, &lp_)) return set_error(e, TNUTS_E_UNSUPPORTED, "logistic regression: D > 256 not supported");
   gw->chunks = lp_.chunks;
   gw->rows_per_chunk = lp_.rpc;
+  gw->stride = ((cap + lp_.tch - 1) / lp_.tch) * lp_.tch;
+  gw->part_elems = (size_t)lp_.chunks * gw->stride * ((size_t)e->model.D + 1);
   const size_t D1 = (size_t)e->model.D + 1;
   void *p = nullptr;
-  TN_CUDA(e, cudaMalloc(&p, 8 * (size_t)gw->chunks * D1 * cap));
+  TN_CUDA(e, cudaMalloc(&p, 8 * gw->part_elems));
   pool->push_back(p);
   gw->part = (double *)p;
   TN_CUDA(e, cudaMalloc(&p, 8 * D1 * cap));

@@ -156,8 +156,8 @@ __host__ __device__ inline int ld_pad(int n) {  // smallest m >= n with m == 4 (
   return m;
 }
 
-template <int NWN, int NWM, int MT, int TR>
-__global__ void __launch_bounds__(256, 1)
+template <int NWN, int NWM, int MT, int TR, int NG>
+__global__ void __launch_bounds__(256 * NG, 1)
 k_logistic_mma(const double *__restrict__ X, const double *__restrict__ y, long long nrows, int D,
                const double *__restrict__ th, int C, const int *__restrict__ list,
                const int *__restrict__ count, int n_all, int rows_per_chunk,
@@ -172,17 +172,25 @@ k_logistic_mma(const double *__restrict__ X, const double *__restrict__ y, long 
   extern __shared__ double sm[];
   const int Kp = (D + 3) & ~3;
   const int LDX = ld_pad(Kp);
-  double *Bs = sm;                              // [Kp][LDB]
-  double *Xs = Bs + (size_t)Kp * LDB;           // [2][TR][LDX]
+  // NG independent groups of 8 warps share the B tile and work on different row chunks; their
+  // GEMM / elementwise phases drift apart, so one group's DMMAs overlap the other's exp/log
+  const int grp = threadIdx.x >> 8;
+  double *Bs = sm;                              // [Kp][LDB]                (shared by the groups)
+  double *Xs = Bs + (size_t)Kp * LDB + (size_t)grp * ((size_t)2 * TR * LDX + (size_t)TR * LDR + 2 * TR);
   double *Rs = Xs + (size_t)2 * TR * LDX;       // [TR][LDR]
   double *Ys = Rs + (size_t)TR * LDR;           // [2][TR]
   const int n = count ? *count : n_all;
   const int k0 = blockIdx.x * TCH;
   if (k0 >= n) return;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x & 255, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lc = lane & 3;
-  const int chunk = blockIdx.y;
-  const long long rbeg = (long long)chunk * rows_per_chunk;
+  const int chunk = blockIdx.y * NG + grp;
+  auto group_sync = [&]() {
+    if (NG == 1) __syncthreads();
+    else asm volatile("bar.sync %0, 256;\n" ::"r"(1 + grp));
+  };
+  long long rbeg = (long long)chunk * rows_per_chunk;
+  if (rbeg > nrows) rbeg = nrows;
   long long rend = rbeg + rows_per_chunk;
   if (rend > nrows) rend = nrows;
   const int ntile = (int)((rend - rbeg + TR - 1) / TR);
@@ -211,7 +219,7 @@ k_logistic_mma(const double *__restrict__ X, const double *__restrict__ y, long 
     const int r = i / (LDX - D), d = D + i % (LDX - D);
     Xs[(size_t)r * LDX + d] = 0.0;
   }
-  for (int i = tid; i < Kp * TCH; i += 256) {
+  for (int i = threadIdx.x; i < Kp * TCH; i += 256 * NG) {
     const int d = i / TCH, cc = i - d * TCH;
     const int k = k0 + cc;
     double v = 0.0;
@@ -223,6 +231,7 @@ k_logistic_mma(const double *__restrict__ X, const double *__restrict__ y, long 
   }
   if (ntile > 0) prefetch(0, 0);
   cp_async_commit();
+  if (NG > 1) __syncthreads();  // the B tile is complete before the groups go their own way
 
   // GEMM2 accumulators: this warp's n-tile (wn2) and m-tiles {wm2 + NWM * i}
   const int wn2 = warp % NWN, wm2 = warp / NWN;
@@ -240,7 +249,7 @@ k_logistic_mma(const double *__restrict__ X, const double *__restrict__ y, long 
     if (t + 1 < ntile) prefetch(t + 1, buf ^ 1);
     cp_async_commit();
     cp_async_wait<1>();
-    __syncthreads();
+    group_sync();
     const double *xb = Xs + (size_t)buf * TR * LDX;
     const long long r0 = rbeg + (long long)t * TR;
     const int nr = (int)((rend - r0) < TR ? (rend - r0) : TR);
@@ -287,7 +296,7 @@ k_logistic_mma(const double *__restrict__ X, const double *__restrict__ y, long 
         dst[1] = r2[1];
       }
     }
-    __syncthreads();
+    group_sync();
     // ---- GEMM2: G += X^T * R ----
     for (int kk = 0; kk < TR; kk += 4) {
       const double b = Rs[(kk + lc) * LDR + wn2 * 8 + lr];
@@ -298,10 +307,11 @@ k_logistic_mma(const double *__restrict__ X, const double *__restrict__ y, long 
         dmma884(gacc[i][0], gacc[i][1], a, b);
       }
     }
-    __syncthreads();  // Rs and this X buffer are free for the next iteration
+    group_sync();  // Rs and this X buffer are free for the next iteration
   }
   cp_async_wait<0>();
   // ---- epilogue ----
+  if (rbeg >= nrows && chunk > 0) return;  // a group without rows (its chunk slot does not exist)
   double *pc = part + (size_t)chunk * (D + 1) * cap;
 #pragma unroll
   for (int i = 0; i < MT; ++i) {
@@ -332,7 +342,7 @@ k_logistic_mma(const double *__restrict__ X, const double *__restrict__ y, long 
 #pragma unroll
       for (int h = 0; h < 2; ++h) Ls[wm1 * TCH + (wn1 * NT1 + q) * 8 + 2 * lc + h] = lpacc[q][h];
   }
-  __syncthreads();
+  group_sync();
   if (tid < TCH) {
     double s = 0.0;
     for (int w = 0; w < WM1; ++w) s += Ls[w * TCH + tid];
@@ -342,14 +352,14 @@ k_logistic_mma(const double *__restrict__ X, const double *__restrict__ y, long 
 }
 
 // sum the row-chunk partials in a fixed order -> lik[D+1][cap] (compact, by work-list slot)
-__global__ void k_logistic_reduce(const double *part, int chunks, int D, int cap, const int *count,
-                                  int n_all, double *lik) {
+__global__ void k_logistic_reduce(const double *part, int chunks, int D, int stride, const int *count,
+                                  int n_all, double *lik, int cap) {
   const int n = count ? *count : n_all;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int d = blockIdx.y;
   if (k >= n) return;
   double s = 0.0;
-  for (int ch = 0; ch < chunks; ++ch) s += part[((size_t)ch * (D + 1) + d) * cap + k];
+  for (int ch = 0; ch < chunks; ++ch) s += part[((size_t)ch * (D + 1) + d) * stride + k];
   lik[(size_t)d * cap + k] = s;
 }
 
