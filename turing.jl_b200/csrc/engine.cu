@@ -365,7 +365,9 @@ static int run_segments(Engine *e, int64_t n_transitions, int64_t first_keep, in
   if (host_draws && !e->copy_stream) TN_CUDA(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   const size_t C = (size_t)e->st.C, row = (size_t)e->out.ncol * C;
   double *const base = e->out.draws, *const tbase = e->out.theta;
-  if (chunk_draws <= 0 || !host_draws) chunk_draws = keep > 0 ? keep : 1;
+  // the lock-step strategy advances chains asynchronously (each at its own transition), so a
+  // prefix of the draws is not complete before the end: one segment, one copy
+  if (chunk_draws <= 0 || !host_draws || e->strategy != STRAT_THREAD) chunk_draws = keep > 0 ? keep : 1;
   TN_CUDA(e, cudaEventRecord(e->ev0, e->stream));
   long long t_done = 0, k_done = 0;
   std::vector<cudaEvent_t> evs;

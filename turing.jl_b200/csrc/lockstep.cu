@@ -215,6 +215,7 @@ int lockstep_create(Engine *e) {
   A(s.H0, C); A(s.sum_a, C); A(s.dHmax, C); A(s.lw, C); A(s.lw_s, C); A(s.lpC, C); A(s.HC, C);
   A(s.lpS, C); A(s.HS, C); A(s.zlp, C); A(s.zH, C); A(s.elp, 2 * C); A(s.n_a, C);
   A(s.depth, C); A(s.active, C); A(s.sub_active, C); A(s.term_s, C); A(s.numerr, C); A(s.v, C);
+  A(s.n, C); A(s.phase, C); A(s.iter0, C); A(s.iter_end, C);
   A(ls->list, C); A(ls->count, 2);
   A(ls->fs_eps, C); A(ls->fs_epsp, C); A(ls->fs_H, C); A(ls->fs_dir, C); A(ls->fs_phase, C);
   A(ls->fs_iter, C); A(ls->r0, DC);
@@ -532,7 +533,10 @@ int lockstep_init(Engine *e, const double *theta0_dev) {
 }
 
 // ------------------------------------------------------------------------------------------
-// run: the mcmcsample loop, one NUTS transition at a time for all chains
+// run: the host pumps "one leapfrog for every unfinished chain" until all chains have done
+// their transitions.  No host<->device synchronisation on the way: the pump kernel mirrors its
+// finished-chain counter into mapped pinned memory, the host polls that word and only bounds
+// how far it runs ahead of the GPU (an event every 64 pumps).
 // ------------------------------------------------------------------------------------------
 int lockstep_run(Engine *e) {
   LockstepState *ls = e->ls;
@@ -541,36 +545,42 @@ int lockstep_run(Engine *e) {
   const int C = st.C;
   const int T = tiles(C);
   int rc;
-  for (long long t = 1; t <= rp.n_transitions; ++t) {
-    k_ls_transition_start<<<T, kTileThreads, 0, e->stream>>>(st, *ls, rp);
-    e->launches += 1;
-    int n_active = C;
-    for (int j = 0; j < rp.max_depth && n_active > 0; ++j) {
-      k_ls_doubling_start<<<T, kTileThreads, 0, e->stream>>>(st, *ls, rp, j);
-      e->launches += 1;
-      const int nleaf = 1 << j;
-      for (int n = 0; n < nleaf; ++n) {
-        if ((n & 7) == 0) {  // refresh the work list at the start and every 8 leaves
-          k_ls_compact<<<1, 1024, 0, e->stream>>>(ls->ts.sub_active, C, ls->list, ls->count);
-          e->launches += 1;
-        }
-        if ((rc = grad_launch(e, ls->zt, C, ls->ts.zlp, ls->zg, ls->list, ls->count, C, n_active, gw_of(e))))
-          return rc;
-        k_ls_leaf<<<T, kTileThreads, 0, e->stream>>>(st, *ls, rp, j, n, nleaf);
-        e->launches += 1;
-      }
-      TN_CUDA(e, cudaMemsetAsync(ls->count + 1, 0, sizeof(int), e->stream));
-      k_ls_doubling_end<<<T, kTileThreads, 0, e->stream>>>(st, *ls, rp, j, ls->count + 1);
-      e->launches += 1;
-      if ((rc = read_count(e, ls->count + 1, ls->h_count))) return rc;
-      n_active = ls->h_count[0];
+  volatile int *h_done = ls->h_count;
+  TN_CUDA(e, cudaStreamSynchronize(e->stream));  // no pump of an earlier run may still write the mirror
+  *h_done = 0;
+  TN_CUDA(e, cudaMemsetAsync(ls->count + 1, 0, sizeof(int), e->stream));
+  k_ls_begin_run<<<(C + 255) / 256, 256, 0, e->stream>>>(st, *ls, rp.n_transitions, ls->count + 1);
+  e->launches += 1;
+  cudaEvent_t ev[2];
+  TN_CUDA(e, cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  TN_CUDA(e, cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  const long long max_pumps = rp.n_transitions * ((1LL << rp.max_depth) + 2) + 64;
+  int listed_done = -1, n_max = C;
+  rc = TNUTS_OK;
+  for (long long pump = 0; pump < max_pumps; ++pump) {
+    const int done = *h_done;
+    if (done >= C) break;
+    if (done != listed_done && (pump % 8 == 0)) {  // refresh the gradient work list
+      k_ls_running_flags<<<(C + 255) / 256, 256, 0, e->stream>>>(*ls, C, ls->ts.sub_active);
+      k_ls_compact<<<1, 1024, 0, e->stream>>>(ls->ts.sub_active, C, ls->list, ls->count);
+      e->launches += 2;
+      listed_done = done;
+      n_max = C - done;
     }
-    long long k_slot = -1;
-    if (rp.first_keep >= 1 && t >= rp.first_keep && (t - rp.first_keep) % rp.thin == 0)
-      k_slot = (t - rp.first_keep) / rp.thin;
-    k_ls_transition_end<<<T, kTileThreads, 0, e->stream>>>(st, *ls, rp, e->model, e->out, k_slot);
+    if (pump > 0) {  // on the first pump no leaf is pending yet
+      if ((rc = grad_launch(e, ls->zt, C, ls->ts.zlp, ls->zg, ls->list, ls->count, C, n_max, gw_of(e)))) break;
+    }
+    k_ls_pump<<<T, kTileThreads, 0, e->stream>>>(st, *ls, rp, e->model, e->out, ls->count + 1, ls->h_count);
     e->launches += 1;
+    if (pump % 64 == 63) {
+      const int slot = (int)((pump / 64) & 1);
+      if (pump >= 127) cudaEventSynchronize(ev[slot]);  // the event recorded 128 pumps ago
+      cudaEventRecord(ev[slot], e->stream);
+    }
   }
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  if (rc) return rc;
   TN_CUDA(e, cudaGetLastError());
   return TNUTS_OK;
 }

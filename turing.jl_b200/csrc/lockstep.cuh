@@ -24,6 +24,9 @@ struct TreeScalars {  // [C] each
   int *term_s;        // current doubling terminated (U-turn or divergence)
   int *numerr;        // divergence seen in this transition
   int *v;             // direction of the current doubling: 0 = left, 1 = right
+  int *n;             // leaf index inside the current doubling
+  int *phase;         // 0 start a transition, 1 leaf pending, 2 done with this run
+  long long *iter0, *iter_end;  // transition window of the current run
 };
 
 struct LockstepState {

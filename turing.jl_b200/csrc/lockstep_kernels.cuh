@@ -54,308 +54,6 @@ __device__ __forceinline__ void tile_reduce(double (&v)[NR], double *smem /* [NR
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// transition start: momentum refresh, H0, tree initialisation
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTileThreads)
-k_ls_transition_start(ChainState st, LockstepState ls, RunParams rp) {
-  __shared__ double red[1 * 64];
-  const Tile t;
-  const int C = st.C, D = st.D;
-  const bool in = t.c < C && st.status[t.c] == 0;
-  const uint32_t gchain = (uint32_t)(rp.chain_offset + t.c);
-  const uint32_t it = in ? (uint32_t)(st.iter[t.c] + 1) : 0u;
-  double acc[1] = {0.0};
-  if (in) {
-    const int npair = (D + 1) / 2;
-    for (int p = t.dl; p < npair; p += kTileD) {
-      double z0, z1;
-      normal2(rp.seed, gchain, it, SLOT_MOMENTUM, (uint32_t)p, z0, z1);
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int d = 2 * p + q;
-        if (d < D) {
-          const size_t o = (size_t)d * C + t.c;
-          const double mi = st.minv[o];
-          const double r = (q ? z1 : z0) / sqrt(mi);
-          const double th = st.theta[o], g = st.grad[o];
-          acc[0] += mi * r * r;
-          ls.rho[o] = r;
-          ls.thC[o] = th;
-          ls.gC[o] = g;
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            double *e = ls.edge[s];
-            e[o] = th;
-            e[(size_t)D * C + o] = r;
-            e[2 * (size_t)D * C + o] = g;
-          }
-        }
-      }
-    }
-  }
-  tile_reduce<1>(acc, red);
-  if (in && t.dl == 0) {
-    const double lp = st.lp[t.c];
-    const double K = 0.5 * acc[0];
-    const double H0 = (isfinite(lp) && isfinite(K)) ? (-lp + K) : CUDART_INF;
-    TreeScalars &s = ls.ts;
-    s.H0[t.c] = H0;
-    s.sum_a[t.c] = 0.0;
-    s.n_a[t.c] = 0;
-    s.dHmax[t.c] = 0.0;
-    s.lw[t.c] = 0.0;
-    s.lpC[t.c] = lp;
-    s.HC[t.c] = H0;
-    s.elp[t.c] = lp;
-    s.elp[C + t.c] = lp;
-    s.depth[t.c] = 0;
-    s.active[t.c] = 1;
-    s.numerr[t.c] = 0;
-  }
-  if (t.c < C && !in && t.dl == 0) ls.ts.active[t.c] = 0;
-}
-
-// ------------------------------------------------------------------------------------------
-// doubling start: direction, load the edge, first half kick + drift of leaf 0
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTileThreads)
-k_ls_doubling_start(ChainState st, LockstepState ls, RunParams rp, int j) {
-  const Tile t;
-  const int C = st.C, D = st.D;
-  if (t.c >= C) return;
-  TreeScalars &s = ls.ts;
-  const bool act = s.active[t.c] != 0;
-  if (!act) {
-    if (t.dl == 0) s.sub_active[t.c] = 0;
-    return;
-  }
-  const uint32_t gchain = (uint32_t)(rp.chain_offset + t.c);
-  const uint32_t it = (uint32_t)(st.iter[t.c] + 1);
-  const int v = (uniform1(rp.seed, gchain, it, SLOT_DIRECTION, (uint32_t)j) < 0.5) ? 0 : 1;
-  const double eps = st.eps[t.c];
-  const double se = v ? eps : -eps, half = 0.5 * se;
-  const double *e = ls.edge[v];
-  const size_t DC = (size_t)D * C;
-  for (int d = t.dl; d < D; d += kTileD) {
-    const size_t o = (size_t)d * C + t.c;
-    const double g = e[2 * DC + o];
-    const double r = e[DC + o] + half * g;
-    ls.zr[o] = r;
-    ls.zg[o] = g;
-    ls.zt[o] = e[o] + se * (st.minv[o] * r);
-    ls.rho_s[o] = 0.0;
-  }
-  if (t.dl == 0) {
-    s.v[t.c] = v;
-    s.sub_active[t.c] = 1;
-    s.term_s[t.c] = 0;
-    s.lw_s[t.c] = -CUDART_INF;
-    s.zlp[t.c] = s.elp[v * C + t.c];
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// leaf: finish leapfrog n of doubling j (second half kick, energy), leaf statistics,
-// streaming multinomial candidate, checkpointed sub-tree U-turn checks; then, when the
-// doubling continues, the first half kick + drift of leaf n+1.
-// The gradient at the drifted position was written to zg / zlp by the family's kernel.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTileThreads)
-k_ls_leaf(ChainState st, LockstepState ls, RunParams rp, int j, int n, int nleaf) {
-  __shared__ double red[2 * 64];
-  const Tile t;
-  const int C = st.C, D = st.D;
-  TreeScalars &s = ls.ts;
-  const bool in = t.c < C && s.sub_active[t.c] != 0;
-  double eps = 0, se = 0, half = 0;
-  if (in) {
-    eps = st.eps[t.c];
-    se = s.v[t.c] ? eps : -eps;
-    half = 0.5 * se;
-  }
-  // pass 1: second half kick, kinetic energy, finiteness of the gradient
-  double a1[2] = {0.0, 0.0};
-  if (in) {
-    for (int d = t.dl; d < D; d += kTileD) {
-      const size_t o = (size_t)d * C + t.c;
-      const double g = ls.zg[o];
-      const double r = ls.zr[o] + half * g;
-      ls.zr[o] = r;
-      a1[0] += st.minv[o] * r * r;
-      a1[1] += isfinite(g) ? 0.0 : 1.0;
-    }
-  }
-  tile_reduce<2>(a1, red);
-  // per-chain leaf logic, computed identically by the 32 threads of the chain
-  bool accept = false, divergent = false;
-  if (in) {
-    const uint32_t gchain = (uint32_t)(rp.chain_offset + t.c);
-    const uint32_t it = (uint32_t)(st.iter[t.c] + 1);
-    const double lp = s.zlp[t.c];
-    const double K = 0.5 * a1[0];
-    const bool ok = isfinite(lp) && a1[1] == 0.0 && isfinite(K);
-    const double H = ok ? (-lp + K) : CUDART_INF;
-    const double dH = H - s.H0[t.c];
-    const double a = exp(fmin(0.0, -dH));
-    const double lw_leaf = -dH;
-    const double lw_s = s.lw_s[t.c];
-    const double lw_new = ls_logaddexp(lw_s, lw_leaf);
-    const double p = (lw_leaf == -CUDART_INF) ? 0.0 : exp(lw_leaf - lw_new);
-    const double u = uniform1(rp.seed, gchain, it, SLOT_LEAF, (1u << j) + (uint32_t)n);
-    accept = u < p;
-    divergent = !(dH < rp.delta_max);
-    if (t.dl == 0) {
-      s.sum_a[t.c] += a;
-      s.n_a[t.c] += 1;
-      if (fabs(dH) > fabs(s.dHmax[t.c])) s.dHmax[t.c] = dH;
-      s.lw_s[t.c] = lw_new;
-      s.zH[t.c] = H;
-      if (accept) {
-        s.lpS[t.c] = lp;
-        s.HS[t.c] = H;
-      }
-      if (divergent) {
-        s.numerr[t.c] = 1;
-        s.term_s[t.c] = 1;
-        s.sub_active[t.c] = 0;
-      }
-      st.n_grad[t.c] += 1;
-    }
-  }
-  // pass 2: rho_s, candidate copy, checkpoints / U-turn partial dot products
-  const int idx_max = __popc((unsigned)n >> 1);
-  const bool odd = (n & 1) != 0;
-  const int ntrail = __ffs(~(unsigned)n) - 1;
-  const int idx_min = idx_max - ntrail + 1;
-  const int nlev = odd ? (idx_max - idx_min + 1) : 0;
-  double dots[2 * kMaxLevels];
-#pragma unroll
-  for (int q = 0; q < 2 * kMaxLevels; ++q) dots[q] = 0.0;
-  const size_t DC = (size_t)D * C;
-  if (in) {
-    for (int d = t.dl; d < D; d += kTileD) {
-      const size_t o = (size_t)d * C + t.c;
-      const double r = ls.zr[o];
-      const double rs = ls.rho_s[o] + r;
-      ls.rho_s[o] = rs;
-      if (accept) {
-        ls.thS[o] = ls.zt[o];
-        ls.gS[o] = ls.zg[o];
-      }
-      if (!divergent) {
-        if (!odd) {
-          ls.ck_r[idx_max * DC + o] = r;
-          ls.ck_rho[idx_max * DC + o] = rs;
-        } else {
-          const double mi = st.minv[o];
-          for (int q = 0; q < nlev; ++q) {
-            const int i = idx_max - q;
-            const double cr = ls.ck_r[i * DC + o];
-            const double sr = rs - ls.ck_rho[i * DC + o] + cr;
-            dots[2 * q] += sr * (mi * cr);
-            dots[2 * q + 1] += sr * (mi * r);
-          }
-        }
-      }
-    }
-  }
-  bool term_s = divergent;
-  if (odd) {  // uniform across the grid: every CTA takes part in the reductions
-    // reduce only the levels in use (nlev is grid-uniform)
-    for (int q = 0; q < nlev; ++q) {
-      double pr[2] = {dots[2 * q], dots[2 * q + 1]};
-      tile_reduce<2>(pr, red);
-      if (in && !divergent && ((pr[0] <= 0.0) || (pr[1] <= 0.0))) term_s = true;
-    }
-    if (in && term_s && !divergent && t.dl == 0) {
-      s.term_s[t.c] = 1;
-      s.sub_active[t.c] = 0;
-    }
-  }
-  // pass 3: first half kick + drift of the next leaf
-  if (in && !term_s && n + 1 < nleaf) {
-    for (int d = t.dl; d < D; d += kTileD) {
-      const size_t o = (size_t)d * C + t.c;
-      const double r = ls.zr[o] + half * ls.zg[o];
-      ls.zr[o] = r;
-      ls.zt[o] = ls.zt[o] + se * (st.minv[o] * r);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// doubling end: combine the new sub-tree into the tree, biased progressive sampling,
-// tree-level U-turn, depth cap; counts the chains whose transition continues.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTileThreads)
-k_ls_doubling_end(ChainState st, LockstepState ls, RunParams rp, int j, int *n_active) {
-  __shared__ double red[2 * 64];
-  const Tile t;
-  const int C = st.C, D = st.D;
-  TreeScalars &s = ls.ts;
-  const bool in = t.c < C && s.active[t.c] != 0;
-  const size_t DC = (size_t)D * C;
-  bool take = false, term_s = false;
-  int v = 0;
-  if (in) {
-    v = s.v[t.c];
-    term_s = s.term_s[t.c] != 0;
-    if (!term_s) {
-      const uint32_t gchain = (uint32_t)(rp.chain_offset + t.c);
-      const uint32_t it = (uint32_t)(st.iter[t.c] + 1);
-      const double u = uniform1(rp.seed, gchain, it, SLOT_MH, (uint32_t)j);
-      const double dl = s.lw_s[t.c] - s.lw[t.c];
-      take = u < (dl < 0.0 ? exp(dl) : 1.0);
-    }
-  }
-  double dots[2] = {0.0, 0.0};
-  if (in) {
-    double *e = ls.edge[v];
-    const double *eo = ls.edge[1 - v];
-    for (int d = t.dl; d < D; d += kTileD) {
-      const size_t o = (size_t)d * C + t.c;
-      const double r = ls.zr[o];
-      e[o] = ls.zt[o];
-      e[DC + o] = r;
-      e[2 * DC + o] = ls.zg[o];
-      if (take) {
-        ls.thC[o] = ls.thS[o];
-        ls.gC[o] = ls.gS[o];
-      }
-      const double rho = ls.rho[o] + ls.rho_s[o];
-      ls.rho[o] = rho;
-      const double mi = st.minv[o];
-      const double ro = eo[DC + o];
-      // left edge is edge[0], right edge is edge[1]
-      dots[v] += rho * (mi * r);
-      dots[1 - v] += rho * (mi * ro);
-    }
-  }
-  tile_reduce<2>(dots, red);
-  if (in && t.dl == 0) {
-    s.elp[v * C + t.c] = s.zlp[t.c];
-    int depth = s.depth[t.c];
-    if (!term_s) {
-      depth += 1;
-      s.depth[t.c] = depth;
-      if (take) {
-        s.lpC[t.c] = s.lpS[t.c];
-        s.HC[t.c] = s.HS[t.c];
-      }
-    }
-    s.lw[t.c] = ls_logaddexp(s.lw[t.c], s.lw_s[t.c]);
-    const bool uturn = (dots[0] <= 0.0) || (dots[1] <= 0.0);
-    const bool cont = !(term_s || uturn) && depth < rp.max_depth;
-    s.active[t.c] = cont ? 1 : 0;
-    if (cont) atomicAdd(n_active, 1);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// transition end: stats, move to the candidate, AHMC.adapt! (dual averaging, Welford,
-// window ends), and -- for kept transitions -- constrained parameters / log-probs / stats
-// ------------------------------------------------------------------------------------------
 struct RecordInfo {
   long long k;  // draw slot, or -1 when the transition is not kept
 };
@@ -471,123 +169,442 @@ __device__ __forceinline__ void ls_user_logp(const ModelDev &m, const double *th
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_ls_pump -- the whole per-chain NUTS state machine as ONE kernel that the host "pumps":
+// every launch advances EVERY unfinished chain by exactly one leapfrog (the gradient at the
+// drifted position was written to zg / zlp by the family's kernel just before).  Chains are
+// NOT in lock step with each other: each carries its own (transition, doubling j, leaf n),
+// so a chain whose tree ends starts its next transition in the same launch while its
+// neighbours keep extending theirs -- no chain ever waits for the deepest tree of the batch.
+//
+//   phase 0: start a transition (momentum refresh, H0, tree init, doubling 0)
+//   phase 1: a leaf is pending: [A] finish the leapfrog, leaf statistics, streaming
+//            multinomial candidate, checkpointed sub-tree U-turn checks;
+//            [B] at the end of a doubling: combine, biased progressive sampling, tree U-turn;
+//            [T] at the end of a transition: stats, move to the candidate, AHMC.adapt!,
+//                kept draw (constrained parameters, user-space log-probs, stats);
+//            [S] start of the next transition;  [D] first half kick + drift of the next leaf.
+//   phase 2: the chain has done all its transitions of this run.
+// Per-chain scalar logic is computed redundantly by the chain's 32 threads (identical inputs
+// => identical results); every reduction over d is executed CTA-uniformly.
+// ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTileThreads)
-k_ls_transition_end(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers out,
-                    long long k_slot) {
+k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers out, int *n_done,
+          int *h_done /* mapped pinned host word */) {
   __shared__ double red[2 * 64];
+  __shared__ int s_maxlev;
   const Tile t;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *(volatile int *)h_done = *(volatile int *)n_done;
   const int C = st.C, D = st.D;
   TreeScalars &s = ls.ts;
+  const size_t DC = (size_t)D * C;
+  // distinct arrays never alias: tell the compiler so that it can batch the loads of the
+  // unrolled d-loops (memory-level parallelism is what these streaming passes live on)
+  double *__restrict__ const zt_ = ls.zt, *__restrict__ const zr_ = ls.zr, *__restrict__ const zg_ = ls.zg;
+  double *__restrict__ const rhos_ = ls.rho_s, *__restrict__ const rho_ = ls.rho;
+  double *__restrict__ const thS_ = ls.thS, *__restrict__ const gS_ = ls.gS;
+  double *__restrict__ const thC_ = ls.thC, *__restrict__ const gC_ = ls.gC;
+  double *__restrict__ const ckr_ = ls.ck_r, *__restrict__ const ckrho_ = ls.ck_rho;
+  double *__restrict__ const minv_ = st.minv, *__restrict__ const theta_ = st.theta,
+                              *__restrict__ const grad_ = st.grad;
   const bool in = t.c < C && st.status[t.c] == 0;
-  long long iter = 0, wf_n = 0;
-  bool adapt = false, in_window = false, wend = false;
-  double eps_used = 0.0;
-  if (in) {
-    iter = st.iter[t.c] + 1;
-    wf_n = st.wf_n[t.c];
-    eps_used = st.eps[t.c];
-    adapt = rp.algorithm != TNUTS_ALG_HMC && iter <= rp.n_adapts;
-    if (adapt) {
-      for (int q = 0; q < rp.n_splits; ++q) wend = wend || (rp.splits[q] == iter);
-      in_window = iter >= rp.window_start && iter <= rp.window_end;
-    }
+  int phase = in ? s.phase[t.c] : 2;
+  const uint32_t gchain = (uint32_t)(rp.chain_offset + t.c);
+  // chain scalars (registers, redundantly in the chain's 32 threads)
+  double eps = 0, H0 = 0, lw = 0, lw_s = 0, sum_a = 0, dHmax = 0, lpC = 0, HC = 0, lpS = 0, HS = 0,
+         zlp = 0, elp0 = 0, elp1 = 0;
+  long long n_a = 0, iter = 0;
+  int v = 0, j = 0, n = 0, numerr = 0;
+  if (phase != 2) {
+    eps = st.eps[t.c];
+    iter = st.iter[t.c];
   }
-  // move to the candidate; Welford push; mass-matrix refresh at a window end
-  if (in) {
-    const double n = (double)(wf_n + 1);
+  if (phase == 1) {
+    H0 = s.H0[t.c]; lw = s.lw[t.c]; lw_s = s.lw_s[t.c]; sum_a = s.sum_a[t.c]; dHmax = s.dHmax[t.c];
+    lpC = s.lpC[t.c]; HC = s.HC[t.c]; lpS = s.lpS[t.c]; HS = s.HS[t.c]; zlp = s.zlp[t.c];
+    elp0 = s.elp[t.c]; elp1 = s.elp[C + t.c]; n_a = s.n_a[t.c];
+    v = s.v[t.c]; j = s.depth[t.c]; n = s.n[t.c]; numerr = s.numerr[t.c];
+  }
+  const bool leaf = phase == 1;
+  bool start_transition = phase == 0;
+  uint32_t it = (uint32_t)(iter + 1);
+
+  // ================= [A] leaf finish =================
+  double se = v ? eps : -eps, half = 0.5 * se;
+  double a1[2] = {0.0, 0.0};
+  if (leaf) {
+#pragma unroll 4
     for (int d = t.dl; d < D; d += kTileD) {
       const size_t o = (size_t)d * C + t.c;
-      const double th = ls.thC[o];
-      st.theta[o] = th;
-      st.grad[o] = ls.gC[o];
-      if (in_window) {
-        double mean = st.wf_mean[o], m2 = st.wf_m2[o];
-        const double delta = th - mean;
-        mean += delta / n;
-        m2 += delta * (th - mean);
-        if (wend) {
-          if (wf_n + 1 >= 10)
-            st.minv[o] = n / ((n + 5.0) * (n - 1.0)) * m2 + 1e-3 * (5.0 / (n + 5.0));
-          mean = 0.0;
-          m2 = 0.0;
+      const double g = zg_[o];
+      const double r = zr_[o] + half * g;
+      zr_[o] = r;
+      a1[0] += minv_[o] * r * r;
+      a1[1] += isfinite(g) ? 0.0 : 1.0;
+    }
+  }
+  tile_reduce<2>(a1, red);
+  bool accept = false, divergent = false, term_s = false, sub_done = false;
+  double zH = 0.0;
+  if (leaf) {
+    const double K = 0.5 * a1[0];
+    const bool ok = isfinite(zlp) && a1[1] == 0.0 && isfinite(K);
+    zH = ok ? (-zlp + K) : CUDART_INF;
+    const double dH = zH - H0;
+    const double a = exp(fmin(0.0, -dH));
+    const double lw_leaf = -dH;
+    const double lw_new = ls_logaddexp(lw_s, lw_leaf);
+    const double p = (lw_leaf == -CUDART_INF) ? 0.0 : exp(lw_leaf - lw_new);
+    const double u = uniform1(rp.seed, gchain, it, SLOT_LEAF, (1u << j) + (uint32_t)n);
+    accept = u < p;
+    divergent = !(dH < rp.delta_max);
+    sum_a += a;
+    n_a += 1;
+    if (fabs(dH) > fabs(dHmax)) dHmax = dH;
+    lw_s = lw_new;
+    if (accept) {
+      lpS = zlp;
+      HS = zH;
+    }
+    if (divergent) {
+      numerr = 1;
+      term_s = true;
+    }
+  }
+  // checkpoints / sub-tree U-turn partial dot products (leaf index n is per chain)
+  const int idx_max = __popc((unsigned)n >> 1);
+  const bool odd = (n & 1) != 0;
+  const int ntrail = __ffs(~(unsigned)n) - 1;
+  const int idx_min = idx_max - ntrail + 1;
+  const int nlev = (leaf && odd && !divergent) ? (idx_max - idx_min + 1) : 0;
+  if (threadIdx.x == 0) s_maxlev = 0;
+  __syncthreads();
+  if (t.dl == 0 && nlev > 0) atomicMax(&s_maxlev, nlev);
+  __syncthreads();
+  const int maxlev = s_maxlev;
+  double dots[2 * kMaxLevels];
+#pragma unroll
+  for (int q = 0; q < 2 * kMaxLevels; ++q) dots[q] = 0.0;
+  if (leaf) {
+#pragma unroll 4
+    for (int d = t.dl; d < D; d += kTileD) {
+      const size_t o = (size_t)d * C + t.c;
+      const double r = zr_[o];
+      const double rs = rhos_[o] + r;
+      rhos_[o] = rs;
+      if (accept) {
+        thS_[o] = zt_[o];
+        gS_[o] = zg_[o];
+      }
+      if (!divergent) {
+        if (!odd) {
+          ckr_[idx_max * DC + o] = r;
+          ckrho_[idx_max * DC + o] = rs;
+        } else {
+          const double mi = minv_[o];
+          for (int q = 0; q < nlev; ++q) {
+            const int i = idx_max - q;
+            const double cr = ckr_[i * DC + o];
+            const double sr = rs - ckrho_[i * DC + o] + cr;
+            dots[2 * q] += sr * (mi * cr);
+            dots[2 * q + 1] += sr * (mi * r);
+          }
         }
-        st.wf_mean[o] = mean;
-        st.wf_m2[o] = m2;
       }
     }
   }
-  double stats[TNUTS_NSTAT];
-  if (in) {
-    const double na = (double)s.n_a[t.c];
-    stats[ST_NSTEPS] = na;
-    stats[ST_ACC] = s.sum_a[t.c] / na;
-    stats[ST_LP] = s.lpC[t.c];
-    stats[ST_H] = s.HC[t.c];
-    stats[ST_HERR] = s.HC[t.c] - s.H0[t.c];
-    stats[ST_MAXHERR] = s.dHmax[t.c];
-    stats[ST_DEPTH] = (double)s.depth[t.c];
-    stats[ST_NUMERR] = (double)s.numerr[t.c];
-    stats[ST_EPS] = eps_used;
+  for (int q = 0; q < maxlev; ++q) {  // CTA-uniform trip count
+    double pr[2] = {dots[2 * q], dots[2 * q + 1]};
+    tile_reduce<2>(pr, red);
+    if (q < nlev && ((pr[0] <= 0.0) || (pr[1] <= 0.0))) term_s = true;
   }
-  // kept draw
-  if (k_slot >= 0) {
-    double prior, lik;
-    ls_user_logp(m, ls.thC, C, t, in, in ? s.lpC[t.c] : 0.0, red, prior, lik);
-    if (in) {
-      double *row = out.draws + (size_t)k_slot * out.ncol * C + t.c;
-      for (int d = t.dl; d < D; d += kTileD) {
-        const double th = ls.thC[(size_t)d * C + t.c];
-        row[(size_t)d * C] = ls_is_positive(m, d) ? exp(th) : th;
-        if (out.theta) out.theta[((size_t)k_slot * D + d) * C + t.c] = th;
+  if (leaf) {
+    sub_done = term_s || (n + 1 == (1 << j));
+    if (!sub_done) n += 1;
+  }
+
+  // ================= [B] end of a doubling =================
+  bool trans_end = false;
+  if (__syncthreads_or(leaf && sub_done)) {
+    const bool me = leaf && sub_done;
+    bool take = false;
+    if (me && !term_s) {
+      const double u = uniform1(rp.seed, gchain, it, SLOT_MH, (uint32_t)j);
+      const double dl = lw_s - lw;
+      take = u < (dl < 0.0 ? exp(dl) : 1.0);
+    }
+    double d2[2] = {0.0, 0.0};
+    if (me) {
+      double *e = ls.edge[v];
+      const double *eo = ls.edge[1 - v];
+  #pragma unroll 4
+    for (int d = t.dl; d < D; d += kTileD) {
+        const size_t o = (size_t)d * C + t.c;
+        const double r = zr_[o];
+        e[o] = zt_[o];
+        e[DC + o] = r;
+        e[2 * DC + o] = zg_[o];
+        if (take) {
+          thC_[o] = thS_[o];
+          gC_[o] = gS_[o];
+        }
+        const double rho = rho_[o] + rhos_[o];
+        rho_[o] = rho;
+        const double mi = minv_[o];
+        d2[v] += rho * (mi * r);
+        d2[1 - v] += rho * (mi * eo[DC + o]);
+      }
+    }
+    tile_reduce<2>(d2, red);
+    if (me) {
+      if (v) elp1 = zlp; else elp0 = zlp;
+      if (!term_s) {
+        j += 1;
+        if (take) {
+          lpC = lpS;
+          HC = HS;
+        }
+      }
+      lw = ls_logaddexp(lw, lw_s);
+      const bool uturn = (d2[0] <= 0.0) || (d2[1] <= 0.0);
+      const bool cont = !(term_s || uturn) && j < rp.max_depth;
+      if (cont) {  // next doubling
+        v = (uniform1(rp.seed, gchain, it, SLOT_DIRECTION, (uint32_t)j) < 0.5) ? 0 : 1;
+        const double *en = ls.edge[v];
+    #pragma unroll 4
+    for (int d = t.dl; d < D; d += kTileD) {
+          const size_t o = (size_t)d * C + t.c;
+          zt_[o] = en[o];
+          zr_[o] = en[DC + o];
+          zg_[o] = en[2 * DC + o];
+          rhos_[o] = 0.0;
+        }
+        zlp = v ? elp1 : elp0;
+        lw_s = -CUDART_INF;
+        n = 0;
+      } else {
+        trans_end = true;
+      }
+    }
+  }
+
+  // ================= [T] end of a transition =================
+  if (__syncthreads_or(trans_end)) {
+    long long k_slot = -1;
+    bool adapt = false, in_window = false, wend = false;
+    long long wf_n = 0;
+    double stats[TNUTS_NSTAT];
+    if (trans_end) {
+      iter += 1;
+      const long long tt = iter - s.iter0[t.c];  // 1-based transition number inside this run
+      if (rp.first_keep >= 1 && tt >= rp.first_keep && (tt - rp.first_keep) % rp.thin == 0)
+        k_slot = (tt - rp.first_keep) / rp.thin;
+      wf_n = st.wf_n[t.c];
+      adapt = rp.algorithm != TNUTS_ALG_HMC && iter <= rp.n_adapts;
+      if (adapt) {
+        for (int q = 0; q < rp.n_splits; ++q) wend = wend || (rp.splits[q] == iter);
+        in_window = iter >= rp.window_start && iter <= rp.window_end;
+      }
+      const double nw = (double)(wf_n + 1);
+  #pragma unroll 4
+    for (int d = t.dl; d < D; d += kTileD) {
+        const size_t o = (size_t)d * C + t.c;
+        const double th = thC_[o];
+        theta_[o] = th;
+        grad_[o] = gC_[o];
+        if (in_window) {
+          double mean = st.wf_mean[o], m2 = st.wf_m2[o];
+          const double delta = th - mean;
+          mean += delta / nw;
+          m2 += delta * (th - mean);
+          if (wend) {
+            if (wf_n + 1 >= 10)
+              minv_[o] = nw / ((nw + 5.0) * (nw - 1.0)) * m2 + 1e-3 * (5.0 / (nw + 5.0));
+            mean = 0.0;
+            m2 = 0.0;
+          }
+          st.wf_mean[o] = mean;
+          st.wf_m2[o] = m2;
+        }
+      }
+      const double na = (double)n_a;
+      stats[ST_NSTEPS] = na;
+      stats[ST_ACC] = sum_a / na;
+      stats[ST_LP] = lpC;
+      stats[ST_H] = HC;
+      stats[ST_HERR] = HC - H0;
+      stats[ST_MAXHERR] = dHmax;
+      stats[ST_DEPTH] = (double)j;
+      stats[ST_NUMERR] = (double)numerr;
+      stats[ST_EPS] = eps;
+    }
+    if (__syncthreads_or(trans_end && k_slot >= 0)) {
+      const bool rec = trans_end && k_slot >= 0;
+      double prior, lik;
+      ls_user_logp(m, thC_, C, t, rec, rec ? lpC : 0.0, red, prior, lik);
+      if (rec) {
+        double *row = out.draws + (size_t)k_slot * out.ncol * C + t.c;
+    #pragma unroll 4
+    for (int d = t.dl; d < D; d += kTileD) {
+          const double th = thC_[(size_t)d * C + t.c];
+          row[(size_t)d * C] = ls_is_positive(m, d) ? exp(th) : th;
+          if (out.theta) out.theta[((size_t)k_slot * D + d) * C + t.c] = th;
+        }
+        if (t.dl == 0) {
+          row[(size_t)(D + 0) * C] = prior;
+          row[(size_t)(D + 1) * C] = lik;
+          row[(size_t)(D + 2) * C] = prior + lik;
+#pragma unroll
+          for (int q = 0; q < TNUTS_NSTAT; ++q) row[(size_t)(D + 3 + q) * C] = stats[q];
+        }
+      }
+    }
+    if (trans_end) {
+      if (adapt) {  // Nesterov dual averaging + window bookkeeping (all 32 threads agree)
+        double da_mu = st.da_mu[t.c], da_xbar = st.da_xbar[t.c], da_hbar = st.da_hbar[t.c],
+               da_eps = st.da_eps[t.c];
+        long long da_m = st.da_m[t.c];
+        const double alpha = fmin(stats[ST_ACC], 1.0);
+        const long long mm = da_m + 1;
+        const double eta_h = 1.0 / ((double)mm + 10.0);
+        const double hbar = (1.0 - eta_h) * da_hbar + eta_h * (rp.delta - alpha);
+        const double x = da_mu - hbar * sqrt((double)mm) / 0.05;
+        const double eta_x = pow((double)mm, -0.75);
+        const double xbar = (1.0 - eta_x) * da_xbar + eta_x * x;
+        const double e = exp(x);
+        da_m = mm;
+        if (isfinite(e)) {
+          da_hbar = hbar;
+          da_xbar = xbar;
+          da_eps = e;
+        }
+        long long wn = in_window ? wf_n + 1 : wf_n;
+        if (wend) {
+          da_mu = log(10.0 * da_eps);
+          da_m = 0;
+          da_xbar = 0.0;
+          da_hbar = 0.0;
+          wn = 0;
+        }
+        if (iter == rp.n_adapts) da_eps = exp(da_xbar);
+        eps = da_eps;
+        if (t.dl == 0) {
+          st.da_mu[t.c] = da_mu;
+          st.da_xbar[t.c] = da_xbar;
+          st.da_hbar[t.c] = da_hbar;
+          st.da_eps[t.c] = da_eps;
+          st.da_m[t.c] = da_m;
+          st.wf_n[t.c] = wn;
+          st.eps[t.c] = da_eps;
+        }
       }
       if (t.dl == 0) {
-        row[(size_t)(D + 0) * C] = prior;
-        row[(size_t)(D + 1) * C] = lik;
-        row[(size_t)(D + 2) * C] = prior + lik;
-#pragma unroll
-        for (int q = 0; q < TNUTS_NSTAT; ++q) row[(size_t)(D + 3 + q) * C] = stats[q];
+        st.lp[t.c] = lpC;
+        st.iter[t.c] = iter;
       }
+      if (iter >= s.iter_end[t.c]) {
+        phase = 2;
+        if (t.dl == 0) atomicAdd(n_done, 1);
+      } else {
+        start_transition = true;
+        it = (uint32_t)(iter + 1);
+      }
+    }
+  }
+
+  // ================= [S] start of a transition =================
+  if (__syncthreads_or(start_transition)) {
+    double acc[1] = {0.0};
+    double lp0 = 0.0;
+    if (start_transition) {
+      lp0 = st.lp[t.c];
+      if (trans_end) lp0 = lpC;  // just written by the dl == 0 thread of this chain
+  #pragma unroll 4
+    for (int d = t.dl; d < D; d += kTileD) {
+        const size_t o = (size_t)d * C + t.c;
+        double z0, z1;
+        normal2(rp.seed, gchain, it, SLOT_MOMENTUM, (uint32_t)(d >> 1), z0, z1);
+        const double mi = minv_[o];
+        const double r = ((d & 1) ? z1 : z0) / sqrt(mi);
+        const double th = theta_[o], g = grad_[o];
+        acc[0] += mi * r * r;
+        rho_[o] = r;
+        thC_[o] = th;
+        gC_[o] = g;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          double *e = ls.edge[q];
+          e[o] = th;
+          e[DC + o] = r;
+          e[2 * DC + o] = g;
+        }
+        zt_[o] = th;
+        zr_[o] = r;
+        zg_[o] = g;
+        rhos_[o] = 0.0;
+      }
+    }
+    tile_reduce<1>(acc, red);
+    if (start_transition) {
+      const double K = 0.5 * acc[0];
+      H0 = (isfinite(lp0) && isfinite(K)) ? (-lp0 + K) : CUDART_INF;
+      sum_a = 0.0;
+      n_a = 0;
+      dHmax = 0.0;
+      lw = 0.0;
+      lpC = lp0;
+      HC = H0;
+      elp0 = elp1 = lp0;
+      j = 0;
+      numerr = 0;
+      v = (uniform1(rp.seed, gchain, it, SLOT_DIRECTION, 0u) < 0.5) ? 0 : 1;
+      zlp = lp0;
+      lw_s = -CUDART_INF;
+      n = 0;
+      phase = 1;
+    }
+  }
+
+  // ================= [D] first half kick + drift of the next leaf =================
+  if (phase == 1) {
+    se = v ? eps : -eps;
+    half = 0.5 * se;
+#pragma unroll 4
+    for (int d = t.dl; d < D; d += kTileD) {
+      const size_t o = (size_t)d * C + t.c;
+      const double r = zr_[o] + half * zg_[o];
+      zr_[o] = r;
+      zt_[o] = zt_[o] + se * (minv_[o] * r);
     }
   }
   if (in && t.dl == 0) {
-    st.lp[t.c] = s.lpC[t.c];
-    st.iter[t.c] = iter;
-    if (adapt) {
-      double da_mu = st.da_mu[t.c], da_xbar = st.da_xbar[t.c], da_hbar = st.da_hbar[t.c],
-             da_eps = st.da_eps[t.c];
-      long long da_m = st.da_m[t.c];
-      const double alpha = fmin(stats[ST_ACC], 1.0);
-      const long long mm = da_m + 1;
-      const double eta_h = 1.0 / ((double)mm + 10.0);
-      const double hbar = (1.0 - eta_h) * da_hbar + eta_h * (rp.delta - alpha);
-      const double x = da_mu - hbar * sqrt((double)mm) / 0.05;
-      const double eta_x = pow((double)mm, -0.75);
-      const double xbar = (1.0 - eta_x) * da_xbar + eta_x * x;
-      const double e = exp(x);
-      da_m = mm;
-      if (isfinite(e)) {
-        da_hbar = hbar;
-        da_xbar = xbar;
-        da_eps = e;
-      }
-      long long wn = in_window ? wf_n + 1 : wf_n;
-      if (wend) {
-        da_mu = log(10.0 * da_eps);
-        da_m = 0;
-        da_xbar = 0.0;
-        da_hbar = 0.0;
-        wn = 0;
-      }
-      if (iter == rp.n_adapts) da_eps = exp(da_xbar);
-      st.da_mu[t.c] = da_mu;
-      st.da_xbar[t.c] = da_xbar;
-      st.da_hbar[t.c] = da_hbar;
-      st.da_eps[t.c] = da_eps;
-      st.da_m[t.c] = da_m;
-      st.wf_n[t.c] = wn;
-      st.eps[t.c] = da_eps;
+    s.phase[t.c] = phase;
+    if (phase == 1) {
+      s.H0[t.c] = H0; s.lw[t.c] = lw; s.lw_s[t.c] = lw_s; s.sum_a[t.c] = sum_a; s.dHmax[t.c] = dHmax;
+      s.lpC[t.c] = lpC; s.HC[t.c] = HC; s.lpS[t.c] = lpS; s.HS[t.c] = HS; s.zlp[t.c] = zlp;
+      s.elp[t.c] = elp0; s.elp[C + t.c] = elp1; s.n_a[t.c] = n_a;
+      s.v[t.c] = v; s.depth[t.c] = j; s.n[t.c] = n; s.numerr[t.c] = numerr;
     }
+    if (leaf) st.n_grad[t.c] += 1;
   }
+}
+
+// arm a run: every chain gets its transition window [iter0, iter_end) and phase 0
+__global__ void k_ls_begin_run(ChainState st, LockstepState ls, long long n_transitions, int *n_done) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= st.C) return;
+  const long long it0 = st.iter[c];
+  ls.ts.iter0[c] = it0;
+  ls.ts.iter_end[c] = it0 + n_transitions;
+  const bool idle = st.status[c] != 0 || n_transitions <= 0;
+  ls.ts.phase[c] = idle ? 2 : 0;
+  if (idle) atomicAdd(n_done, 1);
+}
+
+// work-list flag for the gradient kernels: chains that still run
+__global__ void k_ls_running_flags(LockstepState ls, int C, int *flag) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) flag[c] = ls.ts.phase[c] != 2;
 }
 
 // ------------------------------------------------------------------------------------------
