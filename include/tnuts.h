@@ -104,7 +104,7 @@ typedef struct {
   int32_t device;       /* CUDA device ordinal                                       */
   int32_t row_shards;   /* >1: data rows sharded over ranks (needs tnuts_comm_init)  */
   int32_t row_rank;
-  int32_t strategy;     /* 0 auto, 1 one-thread-per-chain, 2 lock-step               */
+  int32_t strategy;     /* 0 auto, 1 one-thread-per-chain, 2 lock-step pump, 3 one-CTA-per-chain */
   int32_t reserved[5];
 } tnuts_config;
 

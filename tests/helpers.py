@@ -50,6 +50,8 @@ def small_models():
         "logistic_small": T.models.synthetic_logistic(300, 5, seed=4),
         "logistic_d130": T.models.synthetic_logistic(257, 130, seed=5),
         "hier_small": T.models.synthetic_hier(7, 11, seed=6),
+        "hier_g150": T.models.synthetic_hier(150, 9, seed=7),     # D = 305: two dims per thread
+        "std_normal_d600": T.StdNormal(600),
     }
 
 

@@ -90,13 +90,15 @@ def test_leapfrog_trajectories(golden):
 
 CHAIN_CASES = ([(n, 1) for n in ("gdemo", "linreg", "eight_schools")]
                + [(n, 2) for n in ("gdemo", "linreg", "eight_schools", "linreg_n40", "eight_schools_j5",
-                                   "std_normal_d7", "logistic_small", "logistic_d130", "hier_small")])
+                                   "std_normal_d7", "logistic_small", "logistic_d130", "hier_small")]
+               + [(n, 3) for n in ("hier_small", "hier_g150", "std_normal_d7", "std_normal_d600")])
 
 
 @pytest.mark.parametrize("name,strategy", CHAIN_CASES)
 @pytest.mark.parametrize("n_adapts", [0, 30])
 def test_nuts_chains_match_oracle(built, name, strategy, n_adapts):
-    """strategy 1 = one thread per chain, 2 = lock-step; both must reproduce the oracle"""
+    """strategy 1 = one thread per chain, 2 = lock-step pump, 3 = one CTA per chain; every
+    strategy must reproduce the oracle"""
     model = small_models()[name]
     spl = T.NUTS(n_adapts, 0.8)
     C, n_tr = 96, n_adapts + 12

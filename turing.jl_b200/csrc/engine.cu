@@ -278,7 +278,12 @@ int tnuts_set_model(tnuts_engine *h, const tnuts_model *m) {
   const bool thread_ok = thread_strategy_supported(e);
   if (e->cfg.strategy == STRAT_THREAD && !thread_ok)
     return set_error(e, TNUTS_E_UNSUPPORTED, "thread-per-chain strategy not available for this model");
-  e->strategy = (e->cfg.strategy == STRAT_LOCKSTEP || !thread_ok) ? STRAT_LOCKSTEP : STRAT_THREAD;
+  const bool block_ok = block_strategy_supported(e);
+  if (e->cfg.strategy == STRAT_BLOCK && !block_ok)
+    return set_error(e, TNUTS_E_UNSUPPORTED, "one-CTA-per-chain strategy not available for this model");
+  if (e->cfg.strategy == STRAT_THREAD || (e->cfg.strategy == STRAT_AUTO && thread_ok)) e->strategy = STRAT_THREAD;
+  else if (e->cfg.strategy == STRAT_BLOCK || (e->cfg.strategy == STRAT_AUTO && block_ok)) e->strategy = STRAT_BLOCK;
+  else e->strategy = STRAT_LOCKSTEP;
 
   // chain state
   const size_t C = (size_t)e->cfg.n_chains, D = (size_t)m->D;
@@ -303,7 +308,7 @@ int tnuts_set_model(tnuts_engine *h, const tnuts_model *m) {
   if ((rc = dev_alloc(e, pool, &st.n_grad, C))) return rc;
   if ((rc = dev_alloc(e, pool, &st.init_tries, C))) return rc;
   if ((rc = dev_alloc(e, pool, &st.status, C))) return rc;
-  if (e->strategy == STRAT_LOCKSTEP) {
+  if (e->strategy != STRAT_THREAD) {  // the block strategy shares init / point-wise kernels
     if ((rc = lockstep_create(e))) return rc;
   }
   TN_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -381,7 +386,8 @@ static int run_segments(Engine *e, int64_t n_transitions, int64_t first_keep, in
     e->rp.first_keep = (k_done < keep) ? (first_keep + k_done * thin - t_done) : 0;
     e->out.draws = base + (size_t)k_done * row;
     e->out.theta = tbase ? tbase + (size_t)k_done * e->D * C : nullptr;
-    rc = (e->strategy == STRAT_THREAD) ? thread_run(e) : lockstep_run(e);
+    rc = (e->strategy == STRAT_THREAD) ? thread_run(e)
+         : (e->strategy == STRAT_BLOCK) ? block_run(e) : lockstep_run(e);
     if (rc) break;
     if (host_draws && k_end > k_done) {
       cudaEvent_t ev;
@@ -763,8 +769,8 @@ int tnuts_init_tries_max(const tnuts_engine *h) {
 int tnuts_bench_gradient(tnuts_engine *h, int32_t reps, double *seconds) {
   Engine *e = (Engine *)h;
   if (!e || !e->inited || reps < 1 || !seconds) return set_error(e, TNUTS_E_ARG, "tnuts_bench_gradient: bad call");
-  if (e->strategy != STRAT_LOCKSTEP)
-    return set_error(e, TNUTS_E_UNSUPPORTED, "tnuts_bench_gradient: lock-step strategy only");
+  if (e->strategy == STRAT_THREAD)
+    return set_error(e, TNUTS_E_UNSUPPORTED, "tnuts_bench_gradient: not available for the thread-per-chain strategy");
   TN_CUDA(e, cudaSetDevice(e->device));
   return lockstep_bench_gradient(e, reps, seconds);
 }

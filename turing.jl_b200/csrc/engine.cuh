@@ -15,7 +15,7 @@ namespace tnuts {
 struct LockstepState;  // lockstep.cu
 struct DiagWork;       // diagnostics.cu
 
-enum Strategy { STRAT_AUTO = 0, STRAT_THREAD = 1, STRAT_LOCKSTEP = 2 };
+enum Strategy { STRAT_AUTO = 0, STRAT_THREAD = 1, STRAT_LOCKSTEP = 2, STRAT_BLOCK = 3 };
 
 struct Engine {
   tnuts_config cfg{};
@@ -76,6 +76,10 @@ int thread_point_constrain(Engine *e, const double *theta_dev, long long n, doub
 int thread_point_leapfrog(Engine *e, const double *theta_dev, const double *r_dev,
                           const double *minv_dev, double eps, int L, long long n, double *tt_dev,
                           double *tr_dev, double *tH_dev);
+
+// one-CTA-per-chain strategy, block.cu
+bool block_strategy_supported(const Engine *e);
+int block_run(Engine *e);
 
 // lock-step strategy, lockstep.cu
 int lockstep_create(Engine *e);

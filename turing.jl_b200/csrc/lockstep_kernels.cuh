@@ -74,7 +74,7 @@ __device__ __forceinline__ bool ls_is_positive(const ModelDev &m, int d) {
 // likelihood directly (lik_direct = true); the others derive it as lp - prior - logjac.
 // Called by the dl == 0 thread for the small families; the D-parallel sums for logistic /
 // hierarchical are passed in (q0..q2).
-__device__ void ls_prior_small(const ModelDev &m, const double *th, int C, int c, double &prior,
+static __device__ void ls_prior_small(const ModelDev &m, const double *th, int C, int c, double &prior,
                                double &lik) {
   auto T = [&](int d) { return th[(size_t)d * C + c]; };
   switch (m.family) {
@@ -188,7 +188,7 @@ __device__ __forceinline__ void ls_user_logp(const ModelDev &m, const double *th
 // Per-chain scalar logic is computed redundantly by the chain's 32 threads (identical inputs
 // => identical results); every reduction over d is executed CTA-uniformly.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTileThreads)
+static __global__ void __launch_bounds__(kTileThreads)
 k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers out, int *n_done,
           int *h_done /* mapped pinned host word */) {
   __shared__ double red[2 * 64];
@@ -590,7 +590,7 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
 }
 
 // arm a run: every chain gets its transition window [iter0, iter_end) and phase 0
-__global__ void k_ls_begin_run(ChainState st, LockstepState ls, long long n_transitions, int *n_done) {
+static __global__ void k_ls_begin_run(ChainState st, LockstepState ls, long long n_transitions, int *n_done) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= st.C) return;
   const long long it0 = st.iter[c];
@@ -602,7 +602,7 @@ __global__ void k_ls_begin_run(ChainState st, LockstepState ls, long long n_tran
 }
 
 // work-list flag for the gradient kernels: chains that still run
-__global__ void k_ls_running_flags(LockstepState ls, int C, int *flag) {
+static __global__ void k_ls_running_flags(LockstepState ls, int C, int *flag) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) flag[c] = ls.ts.phase[c] != 2;
 }
@@ -610,7 +610,7 @@ __global__ void k_ls_running_flags(LockstepState ls, int C, int *flag) {
 // ------------------------------------------------------------------------------------------
 // compaction of the active chains for the gradient kernels (ordered, deterministic)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_ls_compact(const int *flag, int C, int *list, int *count) {
+static __global__ void __launch_bounds__(1024) k_ls_compact(const int *flag, int C, int *list, int *count) {
   __shared__ int wsum[32];
   __shared__ int base;
   if (threadIdx.x == 0) base = 0;
