@@ -274,6 +274,8 @@ def main():
                       chain_offset=rank * C, verbose=False)
         res = (ch.info["grad_evals"], ch.info["gpu_launches"], ch.value.nbytes,
                float(ch.value[-1, 0, 0]))
+        if os.environ.get("TNUTS_BENCH_VERBOSE"):
+            sys.stderr.write("e2e step %d: wall %.3f host_timing %s\n" % (k, ch.info["wall_seconds"], ch.info["host_timing"]))
         del ch  # the chain's pinned buffer returns to the pool for the next step
         return res
 

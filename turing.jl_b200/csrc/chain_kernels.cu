@@ -1,4 +1,6 @@
 // chain_kernels.cu -- launchers of the one-thread-per-chain strategy (chain_kernels.cuh).
+#include <cub/cub.cuh>
+
 #include "chain_kernels.cuh"
 #include "engine.cuh"
 
@@ -31,6 +33,11 @@ bool thread_strategy_supported(const Engine *e) {
 
 static inline int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
 
+__global__ void k_iota(int *p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
 int thread_init(Engine *e, const double *theta0_dev) {
 #define CALL(M)                                                                          \
   k_chain_init<M><<<grid_for(e->st.C, kChainBlock), kChainBlock, 0, e->stream>>>(        \
@@ -46,17 +53,38 @@ int thread_run(Engine *e) {
 #define CALL(M)                                                                              \
   do {                                                                                       \
     const int g_ = grid_for(e->st.C, kChainBlock);                                           \
+    const int *pm_ = e->perm_valid ? e->perm : nullptr;                                      \
     if (e->occupancy == 3)                                                                   \
-      k_chain_run<M, 3><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp);  \
+      k_chain_run<M, 3><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_);  \
     else if (e->occupancy == 4)                                                              \
-      k_chain_run<M, 4><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp);  \
+      k_chain_run<M, 4><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_);  \
     else                                                                                     \
-      k_chain_run<M, 2><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp);  \
+      k_chain_run<M, 2><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_);  \
   } while (0)
   TN_DISPATCH_SMALL(e, CALL);
 #undef CALL
   e->launches += 1;
   TN_CUDA(e, cudaGetLastError());
+  return TNUTS_OK;
+}
+
+// sort chains by step size (ascending) -> e->perm; cub radix sort on the engine's stream
+int thread_sort_chains(Engine *e) {
+  const int C = e->st.C;
+  if (!e->perm) {
+    TN_CUDA(e, cudaMalloc((void **)&e->perm, sizeof(int) * (size_t)C * 2));
+    TN_CUDA(e, cudaMalloc((void **)&e->perm_keys, sizeof(double) * (size_t)C));
+    e->perm_tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, e->perm_tmp_bytes, (const double *)nullptr, e->perm_keys,
+                                    (const int *)nullptr, e->perm, C, 0, 64, e->stream);
+    TN_CUDA(e, cudaMalloc(&e->perm_tmp, e->perm_tmp_bytes));
+  }
+  int *iota = e->perm + C;
+  k_iota<<<grid_for(C, 256), 256, 0, e->stream>>>(iota, C);
+  TN_CUDA(e, cub::DeviceRadixSort::SortPairs(e->perm_tmp, e->perm_tmp_bytes, e->st.eps, e->perm_keys, iota,
+                                             e->perm, C, 0, 64, e->stream));
+  e->launches += 2;
+  e->perm_valid = true;
   return TNUTS_OK;
 }
 

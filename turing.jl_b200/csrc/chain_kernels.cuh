@@ -312,11 +312,16 @@ __device__ __forceinline__ void hmc_transition_d(const SmallData &md, const RunP
 // ------------------------------------------------------------------------------------------
 template <class M, int MINB>
 __global__ void __launch_bounds__(kChainBlock, MINB) k_chain_run(SmallData md, ChainState st,
-                                                                DrawBuffers out, RunParams rp) {
+                                                                DrawBuffers out, RunParams rp,
+                                                                const int *__restrict__ perm) {
   constexpr int D = M::D;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   const int C = st.C;
-  if (c >= C) return;
+  if (slot >= C) return;
+  // lane -> chain map: after warm-up the chains are sorted by step size so that the 32 chains
+  // of a warp build trees of similar length (a chain's own result does not depend on its lane:
+  // every random draw is addressed by the chain id)
+  const int c = perm ? perm[slot] : slot;
   if (st.status[c] != 0) return;
   const uint32_t gchain = (uint32_t)(rp.chain_offset + c);
 

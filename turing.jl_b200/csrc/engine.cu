@@ -70,17 +70,20 @@ static void window_schedule(long long n, RunParams &rp) {
 static int ensure_draw_capacity(Engine *e, long long keep) {
   const bool want_theta = e->keep_theta;
   if (keep <= e->out.capacity && (!want_theta || e->out.theta)) return TNUTS_OK;
+  // stream-ordered allocations from the device's default pool (release threshold raised in
+  // tnuts_create): a 10+ GB draw buffer is recycled by the next engine instead of paying
+  // cudaMalloc/cudaFree (hundreds of ms, and a device-wide synchronisation) per sampling job
   for (double **p : {&e->out.draws, &e->out.theta}) {
-    if (*p) cudaFree(*p);
+    if (*p) cudaFreeAsync(*p, e->stream);
     *p = nullptr;
   }
   const size_t C = (size_t)e->st.C;
   e->out.capacity = 0;
   e->out.P = e->P;
   e->out.ncol = e->P + 3 + TNUTS_NSTAT;
-  TN_CUDA(e, cudaMalloc((void **)&e->out.draws, sizeof(double) * (size_t)keep * e->out.ncol * C));
+  TN_CUDA(e, cudaMallocAsync((void **)&e->out.draws, sizeof(double) * (size_t)keep * e->out.ncol * C, e->stream));
   if (want_theta)
-    TN_CUDA(e, cudaMalloc((void **)&e->out.theta, sizeof(double) * (size_t)keep * e->D * C));
+    TN_CUDA(e, cudaMallocAsync((void **)&e->out.theta, sizeof(double) * (size_t)keep * e->D * C, e->stream));
   e->out.capacity = keep;
   return TNUTS_OK;
 }
@@ -179,6 +182,13 @@ int tnuts_create(const tnuts_config *cfg, tnuts_engine **out) {
     delete e;
     return set_error(nullptr, TNUTS_E_CUDA, "tnuts_create: stream/event creation failed");
   }
+  {  // keep freed pool memory cached for the next engine of this process
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, e->device) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   RunParams &rp = e->rp;
   rp.algorithm = cfg->algorithm;
   rp.delta = cfg->delta;
@@ -205,7 +215,11 @@ int tnuts_destroy(tnuts_engine *h) {
   free_pool(e->model_allocs);
   free_pool(e->state_allocs);
   for (double *p : {e->out.draws, e->out.theta})
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, e->stream);
+  cudaStreamSynchronize(e->stream);
+  if (e->perm) cudaFree(e->perm);
+  if (e->perm_keys) cudaFree(e->perm_keys);
+  if (e->perm_tmp) cudaFree(e->perm_tmp);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   cudaEventDestroy(e->ev0);
   cudaEventDestroy(e->ev1);
@@ -352,6 +366,8 @@ int tnuts_init(tnuts_engine *h, const double *theta0) {
     if (v != 0) return set_error(e, TNUTS_E_INIT, kInitFailMsg);
   e->inited = true;
   e->n_kept = 0;
+  e->host_iter = 0;
+  e->perm_valid = false;
   return TNUTS_OK;
 }
 
@@ -381,6 +397,18 @@ static int run_segments(Engine *e, int64_t n_transitions, int64_t first_keep, in
     // last transition of this segment: the one that produces draw k_end - 1 (or the very end)
     long long t_end = (keep == 0 || k_end >= keep) ? n_transitions : first_keep + (k_end - 1) * thin;
     if (k_done >= keep) t_end = n_transitions;
+    if (e->strategy == STRAT_THREAD && e->sort_chains && e->cfg.algorithm == TNUTS_ALG_NUTS) {
+      // thread-per-chain: once the step sizes are final, sort the chains by step size so
+      // that a warp's 32 chains grow trees of similar length; cut the segment at that point
+      const long long to_adapt_end = e->cfg.n_adapts - (e->host_iter + t_done);
+      if (!e->perm_valid && to_adapt_end <= 0) {
+        if ((rc = thread_sort_chains(e))) break;
+      } else if (!e->perm_valid && t_done + to_adapt_end < t_end) {
+        t_end = t_done + to_adapt_end;
+        // draws kept up to and including t_end
+        k_end = (t_end >= first_keep && keep > 0) ? std::min<long long>(keep, (t_end - first_keep) / thin + 1) : k_done;
+      }
+    }
     e->rp.n_transitions = t_end - t_done;
     e->rp.thin = thin;
     e->rp.first_keep = (k_done < keep) ? (first_keep + k_done * thin - t_done) : 0;
@@ -419,6 +447,7 @@ static int run_segments(Engine *e, int64_t n_transitions, int64_t first_keep, in
   TN_CUDA(e, cudaEventElapsedTime(&ms, e->ev0, e->ev1));
   e->last_run_seconds = ms * 1e-3;
   e->n_kept = keep;
+  e->host_iter += n_transitions;
   if (n_kept) *n_kept = keep;
   return TNUTS_OK;
 }
@@ -446,6 +475,7 @@ int tnuts_set_option(tnuts_engine *h, const char *name, double value) {
   const std::string n(name);
   if (n == "keep_theta") e->keep_theta = value != 0.0;
   else if (n == "occupancy") e->occupancy = (int)value;
+  else if (n == "sort_chains") e->sort_chains = value != 0.0;
 
   else return set_error(e, TNUTS_E_ARG, "tnuts_set_option: unknown option " + n);
   return TNUTS_OK;
@@ -689,6 +719,12 @@ int tnuts_set_state(tnuts_engine *h, const void *blob, size_t nbytes) {
     p += 8 * C;
   }
   TN_CUDA(e, cudaMemset(st.status, 0, sizeof(int) * C));
+  {
+    long long it0 = 0;
+    TN_CUDA(e, cudaMemcpy(&it0, st.iter, sizeof(long long), cudaMemcpyDeviceToHost));
+    e->host_iter = it0;
+    e->perm_valid = false;
+  }
   e->inited = true;
   e->n_kept = 0;
   return TNUTS_OK;

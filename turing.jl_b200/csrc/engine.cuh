@@ -45,6 +45,13 @@ struct Engine {
   long long launches = 0;
   double last_run_seconds = 0.0, last_init_seconds = 0.0;
   bool keep_theta = false;
+  // lane -> chain permutation of the thread-per-chain strategy (chains sorted by step size)
+  int *perm = nullptr;
+  double *perm_keys = nullptr;
+  void *perm_tmp = nullptr;
+  size_t perm_tmp_bytes = 0;
+  bool perm_valid = false, sort_chains = true;
+  long long host_iter = 0;  // transitions done since init (identical for every chain)
   int occupancy = 2;  // CTAs of 128 threads per SM the thread-per-chain kernel is compiled for
 
   LockstepState *ls = nullptr;
@@ -69,6 +76,7 @@ int set_error(Engine *e, int code, const std::string &msg);
 bool thread_strategy_supported(const Engine *e);
 int thread_init(Engine *e, const double *theta0_dev);
 int thread_run(Engine *e);
+int thread_sort_chains(Engine *e);
 int thread_point_lpgrad(Engine *e, const double *theta_dev, long long n, double *lp_dev,
                         double *grad_dev);
 int thread_point_constrain(Engine *e, const double *theta_dev, long long n, double *params_dev,

@@ -118,10 +118,12 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
     if chunk_draws is None:
         chunk_draws = max(1, -(-N // 10))
     t_start = time.perf_counter()
+    tm = {}
     engines = []
     for i, dev in enumerate(devices):
         engines.append(Engine(model, spl, bounds[i + 1] - bounds[i], _nadapts, seed64, device=dev,
                               chain_offset=chain_offset + bounds[i], strategy=strategy))
+    tm["create"] = time.perf_counter() - t_start
     results = [None] * ndev
     errors = [None] * ndev
     # bundle_samples target: (iterations x names x chains); the engine's device layout is
@@ -131,6 +133,7 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
     value = pinned.empty((N, P + nint, n_chains))
     if _discard == 0 and initial_state is None:
         value[0, P + 3:, :] = np.nan
+    tm["alloc"] = time.perf_counter() - t_start - tm["create"]
 
     def work(i):
         try:
@@ -186,6 +189,7 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
                 raise RuntimeError(ex.message) from None
             raise ex
     wall = time.perf_counter() - t_start
+    tm["work"] = wall - tm["create"] - tm["alloc"]
 
     info = {
         "sampling_time": np.full(n_chains, wall),
@@ -194,7 +198,7 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
         "grad_evals": int(sum(r[1] for r in results)),
         "gpu_launches": int(sum(r[5] for r in results)),
         "step_size": np.concatenate([r[3] for r in results]),
-        "algorithm": spl.algorithm,
+        "algorithm": spl.algorithm, "host_timing": tm,
         "n_divergent": int(sum(r[6] for r in results)),
         "nadapts": _nadapts, "discard_initial": _discard, "thinning": thinning, "seed": seed64,
     }
@@ -204,11 +208,13 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
         info["samplerstate"] = {"blobs": [r[4] for r in results], "seed": seed64,
                                 "bounds": bounds, "devices": devices}
     chain = chain_type(value, model.param_names, INTERNALS, info)
+    t_c = time.perf_counter()
     if keep_engine:
         chain.info["engines"] = engines
     else:
         for e in engines:
             e.close()
+    tm["close"] = time.perf_counter() - t_c
     post_sample_hook(chain, spl, verbose=verbose)
     return chain
 
