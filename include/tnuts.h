@@ -119,6 +119,10 @@ const char *tnuts_last_error(const tnuts_engine *e); /* e may be NULL: last crea
 int tnuts_create(const tnuts_config *cfg, tnuts_engine **out);
 int tnuts_destroy(tnuts_engine *e);
 int tnuts_set_model(tnuts_engine *e, const tnuts_model *model);
+/* same, but X / y / group are DEVICE pointers on the engine's device; they are adopted, not
+ * copied (a 12.8 GB row shard is not duplicated): the caller keeps them alive until
+ * tnuts_destroy.  Data-parallel families only (logistic, hierarchical). */
+int tnuts_set_model_device(tnuts_engine *e, const tnuts_model *model_dev);
 int tnuts_dimension(const tnuts_engine *e);
 int tnuts_num_params(const tnuts_engine *e);
 

@@ -49,6 +49,7 @@ SYMBOLS = {
     "tnuts_create": (C.c_int, [C.POINTER(TnutsConfig), C.POINTER(_H)]),
     "tnuts_destroy": (C.c_int, [_H]),
     "tnuts_set_model": (C.c_int, [_H, C.POINTER(TnutsModel)]),
+    "tnuts_set_model_device": (C.c_int, [_H, C.POINTER(TnutsModel)]),
     "tnuts_dimension": (C.c_int, [_H]),
     "tnuts_num_params": (C.c_int, [_H]),
     "tnuts_init": (C.c_int, [_H, _dp]),

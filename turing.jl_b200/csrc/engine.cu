@@ -228,7 +228,18 @@ int tnuts_destroy(tnuts_engine *h) {
   return TNUTS_OK;
 }
 
-int tnuts_set_model(tnuts_engine *h, const tnuts_model *m) {
+static int set_model_impl(tnuts_engine *h, const tnuts_model *m, bool device_ptrs);
+
+int tnuts_set_model(tnuts_engine *h, const tnuts_model *m) { return set_model_impl(h, m, false); }
+
+int tnuts_set_model_device(tnuts_engine *h, const tnuts_model *m) {
+  Engine *e = (Engine *)h;
+  if (m && m->family != TNUTS_LOGISTIC && m->family != TNUTS_HIER_LINREG)
+    return set_error(e, TNUTS_E_UNSUPPORTED, "tnuts_set_model_device: data-parallel families only");
+  return set_model_impl(h, m, true);
+}
+
+static int set_model_impl(tnuts_engine *h, const tnuts_model *m, bool device_ptrs) {
   Engine *e = (Engine *)h;
   if (!e || !m) return set_error(e, TNUTS_E_ARG, "tnuts_set_model: null argument");
   if (e->has_model) return set_error(e, TNUTS_E_ARG, "tnuts_set_model: model already set");
@@ -244,6 +255,10 @@ int tnuts_set_model(tnuts_engine *h, const tnuts_model *m) {
   std::memcpy(md.hyper, m->hyper, sizeof(md.hyper));
   auto upload = [&](const void *src, size_t bytes, const void **dst) -> int {
     if (!src || bytes == 0) return TNUTS_OK;
+    if (device_ptrs) {  // adopted, not copied: the caller keeps the device arrays alive
+      *dst = src;
+      return TNUTS_OK;
+    }
     void *q = nullptr;
     TN_CUDA(e, cudaMalloc(&q, bytes));
     e->model_allocs.push_back(q);

@@ -37,7 +37,10 @@ class Engine:
             raise _lib.TnutsError(rc, (self.L.tnuts_last_error(None) or b"").decode())
         self._cm = model.c_struct()
         try:
-            check(self.h, self.L.tnuts_set_model(self.h, C.byref(self._cm)))
+            if getattr(model, "on_device", False):
+                check(self.h, self.L.tnuts_set_model_device(self.h, C.byref(self._cm)))
+            else:
+                check(self.h, self.L.tnuts_set_model(self.h, C.byref(self._cm)))
         except Exception:
             self.close()
             raise

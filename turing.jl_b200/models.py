@@ -210,3 +210,32 @@ def synthetic_hier(G, n_per, seed=2):
 
 def config4_hier(G=1000, n_per=100, seed=2):
     return synthetic_hier(G, n_per, seed)
+
+
+class DeviceLogisticRegression(Model):
+    """Logistic regression whose X [N, D] (row-major fp64) and y [N] already live on the GPU
+    (torch CUDA tensors): used for row shards that are generated on the device
+    (BASELINE.json configs[4]: 6.25 M rows x 256 per GPU = 12.8 GB, never staged on the host)."""
+    family = LOGISTIC
+    on_device = True
+
+    def __init__(self, X_cuda, y_cuda, prior_sd=1.0):
+        super().__init__()
+        assert X_cuda.is_cuda and X_cuda.is_contiguous() and str(X_cuda.dtype) == "torch.float64"
+        assert y_cuda.is_cuda and y_cuda.is_contiguous() and str(y_cuda.dtype) == "torch.float64"
+        self._X, self._y = X_cuda, y_cuda
+        self.N, d = X_cuda.shape
+        self.hyper = (prior_sd,)
+        self.param_names = tuple("β[%d]" % (j + 1) for j in range(d))
+
+    def c_struct(self):
+        m = _lib.TnutsModel()
+        m.family, m.D, m.N, m.G = self.family, self.D, int(self.N), 0
+        dp = C.POINTER(C.c_double)
+        m.X = C.cast(self._X.data_ptr(), dp)
+        m.y = C.cast(self._y.data_ptr(), dp)
+        m.hyper[0] = float(self.hyper[0])
+        return m
+
+    def data_nbytes(self):
+        return self._X.numel() * 8 + self._y.numel() * 8
