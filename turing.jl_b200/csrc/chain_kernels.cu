@@ -1,6 +1,7 @@
 // chain_kernels.cu -- launchers of the one-thread-per-chain strategy (chain_kernels.cuh).
 #include <cub/cub.cuh>
 
+#include "chain_flat.cuh"
 #include "chain_kernels.cuh"
 #include "engine.cuh"
 
@@ -54,7 +55,9 @@ int thread_run(Engine *e) {
   do {                                                                                       \
     const int g_ = grid_for(e->st.C, kChainBlock);                                           \
     const int *pm_ = e->perm_valid ? e->perm : nullptr;                                      \
-    if (e->occupancy == 3)                                                                   \
+    if (e->flat && e->cfg.algorithm == TNUTS_ALG_NUTS)                                       \
+      k_chain_run_flat<M, 2><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_); \
+    else if (e->occupancy == 3)                                                              \
       k_chain_run<M, 3><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_);  \
     else if (e->occupancy == 4)                                                              \
       k_chain_run<M, 4><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_);  \

@@ -89,6 +89,7 @@ struct RunParams {
   long long splits[24];
   // this call
   long long n_transitions, first_keep, thin;
+  int flat_batch;  // lanes that must wait before a warp runs a transition boundary (flat kernel)
 };
 
 }  // namespace tnuts

@@ -199,6 +199,7 @@ int tnuts_create(const tnuts_config *cfg, tnuts_engine **out) {
   rp.lambda = cfg->lambda;
   rp.seed = cfg->seed;
   rp.chain_offset = cfg->chain_offset;
+  rp.flat_batch = 12;
   window_schedule(cfg->n_adapts, rp);
   *out = (tnuts_engine *)e;
   return TNUTS_OK;
@@ -491,6 +492,8 @@ int tnuts_set_option(tnuts_engine *h, const char *name, double value) {
   if (n == "keep_theta") e->keep_theta = value != 0.0;
   else if (n == "occupancy") e->occupancy = (int)value;
   else if (n == "sort_chains") e->sort_chains = value != 0.0;
+  else if (n == "flat") e->flat = value != 0.0;
+  else if (n == "flat_batch") e->rp.flat_batch = (int)value;
 
   else return set_error(e, TNUTS_E_ARG, "tnuts_set_option: unknown option " + n);
   return TNUTS_OK;

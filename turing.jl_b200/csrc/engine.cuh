@@ -52,6 +52,7 @@ struct Engine {
   size_t perm_tmp_bytes = 0;
   bool perm_valid = false, sort_chains = true;
   long long host_iter = 0;  // transitions done since init (identical for every chain)
+  bool flat = false;  // flat-scheduled thread-per-chain kernel (chain_flat.cuh)
   int occupancy = 2;  // CTAs of 128 threads per SM the thread-per-chain kernel is compiled for
 
   LockstepState *ls = nullptr;
