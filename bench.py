@@ -230,6 +230,9 @@ def main():
 
     # ---------------- arm 1: device-resident (value) ----------------
     eng = T.Engine(model, spl, C, nad, seed, device=local, chain_offset=rank * C)
+    if dist is not None:
+        # chains shard over the ranks; the communicator is only used by the pooled diagnostics
+        T.distributed.attach_comm(eng, dist, device="cuda:%d" % local)
 
     def step():
         eng.init()
@@ -260,9 +263,9 @@ def main():
     grads_all = allsum(grads)
     value = grads_all / dev_total
     # diagnostics of the last step's draws (outside the timed region: measurement, not sampling)
-    rhat, ess = eng.diagnostics()
-    ess_min_all = allsum(float(ess.min()))  # independent chains: ESS adds over shards
-    rhat_max = allmax(float(rhat.max()))
+    rhat, ess = eng.diagnostics()   # multi-GPU: pooled over all ranks' chains (NCCL exchange)
+    ess_min_all = float(ess.min())
+    rhat_max = float(rhat.max())
     ess_per_sec = ess_min_all / (dev_total / args.steps)
     div = eng.divergences
     eng.close()

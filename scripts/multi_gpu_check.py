@@ -15,10 +15,42 @@ import turing_jl_b200 as T
 from turing_jl_b200 import distributed as D
 
 
+def diag_mode(rank, world, local):
+    """chains sharded over the ranks: pooled (cross-GPU) R-hat / bulk ESS == single-engine values"""
+    model = T.EightSchools()
+    spl = T.NUTS(100, 0.8)
+    C = 96
+    eng = D.make_chain_sharded_engine(model, spl, C, 100, 5, rank, world, local)
+    D.attach_comm(eng, dist, device="cuda:%d" % local)
+    eng.init()
+    eng.run(100 + 299, 100, 1)
+    rhat, ess = eng.diagnostics()          # collective: every rank gets the pooled values
+    ok = True
+    if rank == 0:
+        single = T.Engine(model, spl, C, 100, 5, device=local)
+        single.init()
+        single.run(100 + 299, 100, 1)
+        r1, e1 = single.diagnostics()
+        single.close()
+        dr, de = np.abs(rhat - r1).max(), np.abs(ess / e1 - 1).max()
+        print("pooled diagnostics over %d ranks vs one engine: max |d rhat| %.2e, max rel d ess %.2e" % (world, dr, de))
+        ok = dr < 1e-9 and de < 1e-6
+    eng.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0 and flag.item() == 1:
+        print("DIAG-OK")
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if "--diag" in sys.argv:
+        return diag_mode(rank, world, local)
     big = "--big" in sys.argv
     N, Dm, C = (2_000_000, 256, 256) if big else (4001, 24, 64)
     model = T.models.synthetic_logistic(N, Dm, seed=3)

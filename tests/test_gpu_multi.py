@@ -50,3 +50,18 @@ def test_row_sharded_logistic_two_gpus(built):
         capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "ROWS-OK" in out.stdout
+
+
+def test_pooled_diagnostics_two_gpus(built):
+    """chains sharded over 2 GPUs: the NCCL parameter-parallel diagnostics equal the single-engine
+    R-hat / bulk ESS of the same chains"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+         "--master-addr", "127.0.0.1", "--master-port", "29614",
+         os.path.join(ROOT, "scripts", "multi_gpu_check.py"), "--diag"],
+        capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "DIAG-OK" in out.stdout

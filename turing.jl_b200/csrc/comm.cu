@@ -20,6 +20,24 @@ int comm_allreduce_sum(Engine *e, double *buf, size_t n) {
   return TNUTS_OK;
 }
 
+// one grouped exchange: send slab q to rank q (when send_elems[q] > 0); when do_recv, receive
+// rank q's slab at recv + recv_off[q]
+int comm_exchange_slabs(Engine *e, const double *const *send, const size_t *send_elems, bool do_recv,
+                        double *recv, const size_t *recv_off, const size_t *recv_elems) {
+  if (!e->comm) return set_error(e, TNUTS_E_NCCL, "comm_exchange_slabs: no communicator");
+  ncclComm_t c = (ncclComm_t)e->comm;
+  ncclResult_t r = ncclGroupStart();
+  for (int q = 0; q < e->world && r == ncclSuccess; ++q) {
+    if (send_elems[q] > 0) r = ncclSend(send[q], send_elems[q], ncclDouble, q, c, e->stream);
+    if (r == ncclSuccess && do_recv && recv_elems[q] > 0)
+      r = ncclRecv(recv + recv_off[q], recv_elems[q], ncclDouble, q, c, e->stream);
+  }
+  ncclResult_t r2 = ncclGroupEnd();
+  if (r != ncclSuccess || r2 != ncclSuccess)
+    return set_error(e, TNUTS_E_NCCL, std::string("comm_exchange_slabs: ") + ncclGetErrorString(r != ncclSuccess ? r : r2));
+  return TNUTS_OK;
+}
+
 void comm_destroy(Engine *e) {
   if (e->comm) {
     ncclCommDestroy((ncclComm_t)e->comm);

@@ -153,12 +153,17 @@ struct LagSource {
   }
 };
 
-static int rank_normalise(Engine *e, DiagWork *w, int p, long long K, long long n, bool fold,
-                          double center, double *median_out) {
-  const int C = e->st.C;
+struct DiagSrc {  // where the draws of one parameter live: draws[(k * ncol + col) * C + c]
+  const double *draws;
+  int ncol, col, C;
+};
+
+static int rank_normalise(Engine *e, DiagWork *w, const DiagSrc &src, long long K, long long n,
+                          bool fold, double center, double *median_out) {
+  const int C = src.C;
   const long long S = 2LL * C * n;
   const int grid = 148 * 8;
-  k_diag_gather<<<grid, 256, 0, e->stream>>>(e->out.draws, e->out.ncol, C, K, n, p, w->keys, w->idx,
+  k_diag_gather<<<grid, 256, 0, e->stream>>>(src.draws, src.ncol, C, K, n, src.col, w->keys, w->idx,
                                              center, fold ? 1 : 0);
   cub::DoubleBuffer<double> dk(w->keys, w->keys_alt);
   cub::DoubleBuffer<uint32_t> dv(w->idx, w->idx_alt);
@@ -195,9 +200,9 @@ static void within_between(const std::vector<double> &mean_h, const std::vector<
   *var_plus = w * (double)(n - 1) / (double)n + (H > 1 ? b : 0.0);
 }
 
-int diagnostics_run(Engine *e, double *rhat_host, double *ess_host) {
-  const int C = e->st.C, P = e->P, H = 2 * C;
-  const long long K = e->n_kept, n = K / 2;
+static int ensure_work(Engine *e, int C, long long K) {
+  const int H = 2 * C;
+  const long long n = K / 2;
   if (n < 2) return set_error(e, TNUTS_E_ARG, "diagnostics: need at least 4 kept draws");
   const long long S = (long long)H * n;
   if (S >= (1LL << 31)) return set_error(e, TNUTS_E_UNSUPPORTED, "diagnostics: more than 2^31 draws per parameter");
@@ -218,10 +223,19 @@ int diagnostics_run(Engine *e, double *rhat_host, double *ess_host) {
     TN_CUDA(e, cudaMalloc(&w->cub_tmp, w->cub_bytes));
     w->S = (size_t)S;
   }
+  return TNUTS_OK;
+}
+
+// rank-normalised split R-hat (max of bulk and folded) and bulk ESS of ONE parameter
+static int diag_one_param(Engine *e, const DiagSrc &src, long long K, double *rhat_out, double *ess_out) {
+  DiagWork *w = e->diag;
+  const int C = src.C, H = 2 * C;
+  const long long n = K / 2;
+  const long long S = (long long)H * n;
   std::vector<double> mean_h((size_t)H), var_h((size_t)H);
-  for (int p = 0; p < P; ++p) {
+  {
     double median = 0.0;
-    int rc = rank_normalise(e, w, p, K, n, false, 0.0, &median);
+    int rc = rank_normalise(e, w, src, K, n, false, 0.0, &median);
     if (rc) return rc;
     TN_CUDA(e, cudaMemcpyAsync(mean_h.data(), w->mean_h, 8 * (size_t)H, cudaMemcpyDeviceToHost, e->stream));
     TN_CUDA(e, cudaMemcpyAsync(var_h.data(), w->var_h, 8 * (size_t)H, cudaMemcpyDeviceToHost, e->stream));
@@ -267,10 +281,10 @@ int diagnostics_run(Engine *e, double *rhat_host, double *ess_host) {
     if (rho_even > 0) tau += rho[(size_t)max_t + 1];
     const double floor_tau = 1.0 / std::log10((double)S);
     if (tau < floor_tau) tau = floor_tau;
-    ess_host[p] = (double)S / tau;
+    *ess_out = (double)S / tau;
 
     // folded (tail) R-hat
-    rc = rank_normalise(e, w, p, K, n, true, median, nullptr);
+    rc = rank_normalise(e, w, src, K, n, true, median, nullptr);
     if (rc) return rc;
     TN_CUDA(e, cudaMemcpyAsync(mean_h.data(), w->mean_h, 8 * (size_t)H, cudaMemcpyDeviceToHost, e->stream));
     TN_CUDA(e, cudaMemcpyAsync(var_h.data(), w->var_h, 8 * (size_t)H, cudaMemcpyDeviceToHost, e->stream));
@@ -278,7 +292,135 @@ int diagnostics_run(Engine *e, double *rhat_host, double *ess_host) {
     double mv2, vp2;
     within_between(mean_h, var_h, n, &mv2, &vp2);
     const double rhat_tail = std::sqrt(vp2 / mv2);
-    rhat_host[p] = rhat_bulk > rhat_tail ? rhat_bulk : rhat_tail;
+    *rhat_out = rhat_bulk > rhat_tail ? rhat_bulk : rhat_tail;
+  }
+  return TNUTS_OK;
+}
+
+int diagnostics_run_distributed(Engine *e, double *rhat_host, double *ess_host);  // below
+
+int diagnostics_run(Engine *e, double *rhat_host, double *ess_host) {
+  if (e->comm && e->world > 1 && e->cfg.row_shards <= 1) return diagnostics_run_distributed(e, rhat_host, ess_host);
+  const int C = e->st.C, P = e->P;
+  const long long K = e->n_kept;
+  int rc = ensure_work(e, C, K);
+  if (rc) return rc;
+  for (int p = 0; p < P; ++p) {
+    DiagSrc src{e->out.draws, e->out.ncol, p, C};
+    if ((rc = diag_one_param(e, src, K, &rhat_host[p], &ess_host[p]))) return rc;
+  }
+  return TNUTS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// chains sharded over GPUs: the rank normalisation needs the pooled draws of ALL chains, so
+// the parameters are dealt out to the ranks (parameter p is diagnosed by rank p mod W):
+// every rank packs its [K][C_local] slab of each parameter and ncclSend's it to the owner,
+// the owner assembles [K][C_total] and runs the single-GPU diagnostic on it; the [P] results
+// are combined with one small all-reduce.  Traffic: the kept parameter draws cross NVLink once.
+// ------------------------------------------------------------------------------------------
+__global__ void k_diag_pack(const double *draws, int ncol, int col, int C, long long K, double *dst) {
+  const long long tot = K * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long k = i / C;
+    const int c = (int)(i % C);
+    dst[i] = draws[((size_t)k * ncol + col) * C + c];
+  }
+}
+
+// stacked [q][K][Cq] -> [K][Ctot]
+__global__ void k_diag_unstack(const double *src, long long K, int Cq, int off, int Ctot, double *dst) {
+  const long long tot = K * Cq;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long k = i / Cq;
+    const int c = (int)(i % Cq);
+    dst[(size_t)k * Ctot + off + c] = src[i];
+  }
+}
+
+int comm_exchange_slabs(Engine *e, const double *const *send, const size_t *send_elems, bool do_recv,
+                        double *recv, const size_t *recv_off, const size_t *recv_elems);  // comm.cu
+
+int diagnostics_run_distributed(Engine *e, double *rhat_host, double *ess_host) {
+  const int W = e->world, R = e->rank, C = e->st.C, P = e->P;
+  const long long K = e->n_kept;
+  int rc;
+  // chain counts of every rank
+  std::vector<double> cnt((size_t)W, 0.0);
+  cnt[(size_t)R] = (double)C;
+  {
+    double *d = nullptr;
+    TN_CUDA(e, cudaMalloc((void **)&d, 8 * (size_t)W));
+    TN_CUDA(e, cudaMemcpyAsync(d, cnt.data(), 8 * (size_t)W, cudaMemcpyHostToDevice, e->stream));
+    rc = comm_allreduce_sum(e, d, (size_t)W);
+    if (!rc) {
+      cudaMemcpyAsync(cnt.data(), d, 8 * (size_t)W, cudaMemcpyDeviceToHost, e->stream);
+      cudaStreamSynchronize(e->stream);
+    }
+    cudaFree(d);
+    if (rc) return rc;
+  }
+  std::vector<size_t> off((size_t)W + 1, 0), relems((size_t)W), roff((size_t)W), selems((size_t)W);
+  for (int q = 0; q < W; ++q) off[(size_t)q + 1] = off[(size_t)q] + (size_t)cnt[(size_t)q];
+  const int Ctot = (int)off[(size_t)W];
+  for (int q = 0; q < W; ++q) {
+    relems[(size_t)q] = (size_t)K * (size_t)cnt[(size_t)q];
+    roff[(size_t)q] = (size_t)K * off[(size_t)q];
+  }
+  if ((rc = ensure_work(e, Ctot, K))) return rc;
+  double *sendbuf = nullptr, *stack = nullptr, *pooled = nullptr;
+  TN_CUDA(e, cudaMalloc((void **)&sendbuf, 8 * (size_t)W * K * C));
+  TN_CUDA(e, cudaMalloc((void **)&stack, 8 * (size_t)K * Ctot));
+  TN_CUDA(e, cudaMalloc((void **)&pooled, 8 * (size_t)K * Ctot));
+  std::vector<double> res(2 * (size_t)P, 0.0);
+  rc = TNUTS_OK;
+  for (int r0 = 0; r0 < P && !rc; r0 += W) {
+    std::vector<const double *> sp((size_t)W, nullptr);
+    for (int q = 0; q < W; ++q) {
+      const int p = r0 + q;
+      selems[(size_t)q] = 0;
+      if (p < P) {
+        double *dst = sendbuf + (size_t)q * K * C;
+        k_diag_pack<<<148 * 4, 256, 0, e->stream>>>(e->out.draws, e->out.ncol, p, C, K, dst);
+        sp[(size_t)q] = dst;
+        selems[(size_t)q] = (size_t)K * C;
+        e->launches += 1;
+      }
+    }
+    const int mine = r0 + R;
+    rc = comm_exchange_slabs(e, sp.data(), selems.data(), mine < P, stack, roff.data(), relems.data());
+    if (rc) break;
+    if (mine < P) {
+      for (int q = 0; q < W; ++q)
+        k_diag_unstack<<<148 * 4, 256, 0, e->stream>>>(stack + roff[(size_t)q], K, (int)cnt[(size_t)q],
+                                                       (int)off[(size_t)q], Ctot, pooled);
+      e->launches += W;
+      DiagSrc src{pooled, 1, 0, Ctot};
+      rc = diag_one_param(e, src, K, &res[(size_t)mine], &res[(size_t)P + mine]);
+    }
+  }
+  cudaStreamSynchronize(e->stream);
+  cudaFree(sendbuf);
+  cudaFree(stack);
+  cudaFree(pooled);
+  if (rc) return rc;
+  {
+    double *d = nullptr;
+    TN_CUDA(e, cudaMalloc((void **)&d, 8 * res.size()));
+    TN_CUDA(e, cudaMemcpyAsync(d, res.data(), 8 * res.size(), cudaMemcpyHostToDevice, e->stream));
+    rc = comm_allreduce_sum(e, d, res.size());
+    if (!rc) {
+      cudaMemcpyAsync(res.data(), d, 8 * res.size(), cudaMemcpyDeviceToHost, e->stream);
+      cudaStreamSynchronize(e->stream);
+    }
+    cudaFree(d);
+    if (rc) return rc;
+  }
+  for (int p = 0; p < P; ++p) {
+    rhat_host[p] = res[(size_t)p];
+    ess_host[p] = res[(size_t)P + p];
   }
   return TNUTS_OK;
 }
