@@ -47,7 +47,7 @@ def test_row_sharded_logistic_two_gpus(built):
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
          "--master-addr", "127.0.0.1", "--master-port", "29611",
          os.path.join(ROOT, "scripts", "multi_gpu_check.py"), "--rows"],
-        capture_output=True, text=True, timeout=900)
+        capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "ROWS-OK" in out.stdout
 
@@ -62,6 +62,6 @@ def test_pooled_diagnostics_two_gpus(built):
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
          "--master-addr", "127.0.0.1", "--master-port", "29614",
          os.path.join(ROOT, "scripts", "multi_gpu_check.py"), "--diag"],
-        capture_output=True, text=True, timeout=900)
+        capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "DIAG-OK" in out.stdout

@@ -557,8 +557,19 @@ int lockstep_run(Engine *e) {
   const long long max_pumps = rp.n_transitions * ((1LL << rp.max_depth) + 2) + 64;
   int listed_done = -1, n_max = C;
   rc = TNUTS_OK;
+  // Rows sharded over ranks: every pump contains an NCCL all-reduce, so all ranks must issue
+  // exactly the same launch sequence.  The chains are bit-identical on every rank, hence so is
+  // the finished-chain counter after a given pump: read it with a stream synchronisation at
+  // fixed pump numbers instead of polling the (timing-dependent) mirror.
+  const bool lockstep_ranks = e->world > 1 && e->cfg.row_shards > 1;
+  int done = 0;
   for (long long pump = 0; pump < max_pumps; ++pump) {
-    const int done = *h_done;
+    if (!lockstep_ranks) {
+      done = *h_done;
+    } else if (pump % 16 == 0 && pump > 0) {
+      if ((rc = read_count(e, ls->count + 1, ls->h_count + 1))) break;
+      done = ls->h_count[1];
+    }
     if (done >= C) break;
     if (done != listed_done && (pump % 8 == 0)) {  // refresh the gradient work list
       k_ls_running_flags<<<(C + 255) / 256, 256, 0, e->stream>>>(*ls, C, ls->ts.sub_active);
@@ -572,7 +583,7 @@ int lockstep_run(Engine *e) {
     }
     k_ls_pump<<<T, kTileThreads, 0, e->stream>>>(st, *ls, rp, e->model, e->out, ls->count + 1, ls->h_count);
     e->launches += 1;
-    if (pump % 64 == 63) {
+    if (!lockstep_ranks && pump % 64 == 63) {
       const int slot = (int)((pump / 64) & 1);
       if (pump >= 127) cudaEventSynchronize(ev[slot]);  // the event recorded 128 pumps ago
       cudaEventRecord(ev[slot], e->stream);
