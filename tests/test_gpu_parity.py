@@ -179,19 +179,26 @@ def test_strategies_agree_bitwise_on_tree_stats(built):
     np.testing.assert_allclose(outs[0]["theta"][:10], outs[1]["theta"][:10], atol=1e-8)
 
 
-def test_hmc_and_hmcda_match_oracle(built):
-    model = T.gdemo_default()
-    for spl, nad in ((T.HMC(0.1, 7), 0), (T.HMCDA(40, 0.65, 0.5), 40)):
+@pytest.mark.parametrize("name,strategy", [("gdemo", 1), ("gdemo", 2), ("logistic_small", 2),
+                                           ("hier_small", 2), ("hier_small", 3), ("hier_g150", 3)])
+def test_hmc_and_hmcda_match_oracle(built, name, strategy):
+    """HMC (fixed L) and HMCDA (fixed integration time) on every execution strategy
+    (src/mcmc/hmc.jl:59-80, 285-327, 425-434)"""
+    model = small_models()[name]
+    for spl, nad in ((T.HMC(0.02, 7), 0), (T.HMCDA(40, 0.65, 0.15), 40)):
         C, n_tr = 64, nad + 10
-        eng = T.Engine(model, spl, C, nad, seed=9)
+        eng = T.Engine(model, spl, C, nad, seed=9, strategy=strategy)
         eng.set_option("keep_theta", 1)
         eng.init()
         eng.run(n_tr, 1, 1)
         out = eng.fetch(theta=True)
         ref = O.sample_chains(oracle_of(model), oracle_config(spl, nad, 9), C, n_tr)
         th = out["theta"].transpose(2, 0, 1)
-        np.testing.assert_allclose(th[:, :8], ref["theta"][:, :8], atol=1e-8)
-        np.testing.assert_array_equal(out["stats"].transpose(2, 0, 1)[:, :8, 0], ref["stats"][:, :8, 0])
+        st = out["stats"].transpose(2, 0, 1)
+        np.testing.assert_allclose(th[:, :8], ref["theta"][:, :8], atol=1e-7)
+        np.testing.assert_array_equal(st[:, :8, 0], ref["stats"][:, :8, 0])      # n_steps
+        np.testing.assert_array_equal(st[:, :8, 6], ref["stats"][:, :8, 6])      # is_accept
+        np.testing.assert_allclose(st[:, :8, 1], ref["stats"][:, :8, 1], atol=1e-7)
         eng.close()
 
 

@@ -6,7 +6,6 @@ namespace tnuts {
 
 bool block_strategy_supported(const Engine *e) {
   const int f = e->model.family, D = e->D;
-  if (e->cfg.algorithm != TNUTS_ALG_NUTS) return false;
   if (e->cfg.max_depth > kBlockCk + 1) return false;
   if (D > 8 * kBlockThreads) return false;
   return f == TNUTS_HIER_LINREG || f == TNUTS_STD_NORMAL;

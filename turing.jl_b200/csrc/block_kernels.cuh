@@ -268,165 +268,221 @@ k_block_run(ModelDev m, HierStatsDev hs, ChainState st, RunParams rp, double *dr
     block_reduce<2>(e0, red);
     const double K0 = 0.5 * e0[0];
     const double H0 = (isfinite(lp) && e0[1] == 0.0 && isfinite(K0)) ? (-lp + K0) : CUDART_INF;
-    // ---- tree ----
-    double edge[2][3 * KD], elp[2];
-#pragma unroll
-    for (int k = 0; k < KD; ++k) {
-      edge[0][k] = edge[1][k] = th[k];
-      edge[0][KD + k] = edge[1][KD + k] = r[k];
-      edge[0][2 * KD + k] = edge[1][2 * KD + k] = g[k];
-    }
-    elp[0] = elp[1] = lp;
-    double rho[KD], thC[KD], gC[KD];
-#pragma unroll
-    for (int k = 0; k < KD; ++k) {
-      rho[k] = r[k];
-      thC[k] = th[k];
-      gC[k] = g[k];
-    }
-    double sum_a = 0.0, dHmax = 0.0, lw = 0.0, lpC = lp, HC = H0;
-    long long n_a = 0;
-    double ck_r[kBlockCk][KD], ck_rho[kBlockCk][KD];
-    int j = 0;
-    bool term = false, numerr = false;
-    while (!term && j < rp.max_depth) {
-      const int v = (uniform1(rp.seed, gchain, it, SLOT_DIRECTION, (uint32_t)j) < 0.5) ? 0 : 1;
-      const double se = v ? eps : -eps, half = 0.5 * se;
-      double zt[KD], zr[KD], zg[KD], zlp = elp[v], zH = 0.0;
+    double stats[TNUTS_NSTAT];
+    if (rp.algorithm != TNUTS_ALG_NUTS) {
+      // ---- HMC / HMCDA: static trajectory + Metropolis accept (src/mcmc/hmc.jl:425-434) ----
+      int L = rp.n_leapfrog;
+      if (rp.algorithm == TNUTS_ALG_HMCDA) {
+        L = (int)floor(rp.lambda / eps);
+        if (L < 1) L = 1;
+      }
+      double zt[KD], zg[KD], zlp = lp, zH = H0;
 #pragma unroll
       for (int k = 0; k < KD; ++k) {
-        zt[k] = edge[v][k];
-        zr[k] = edge[v][KD + k];
-        zg[k] = edge[v][2 * KD + k];
+        zt[k] = th[k];
+        zg[k] = g[k];
       }
-      double rho_s[KD], thS[KD], gS[KD], lpS = 0.0, HS = 0.0;
-#pragma unroll
-      for (int k = 0; k < KD; ++k) rho_s[k] = 0.0;
-      double lw_s = -CUDART_INF;
-      bool term_s = false;
-      const int nleaf = 1 << j;
-      for (int n = 0; n < nleaf; ++n) {
-        // leapfrog
+      const double half = 0.5 * eps;
+      int nsteps = 0;
+      for (int l = 0; l < L; ++l) {
 #pragma unroll
         for (int k = 0; k < KD; ++k) {
-          zr[k] = zr[k] + half * zg[k];
-          zt[k] = zt[k] + se * (minv[k] * zr[k]);
+          r[k] = r[k] + half * zg[k];
+          zt[k] = zt[k] + eps * (minv[k] * r[k]);
         }
         zlp = M::lpgrad(m, hs, sth, red, zt, zg);
         ++ngrad;
 #pragma unroll
-        for (int k = 0; k < KD; ++k) zr[k] = zr[k] + half * zg[k];
-        // one block reduction: kinetic energy, finiteness, and the sub-tree U-turn dots
-        const int idx_max = __popc((unsigned)n >> 1);
-        const bool odd = (n & 1) != 0;
-        const int ntrail = __ffs(~(unsigned)n) - 1;
-        const int idx_min = idx_max - ntrail + 1;
-        const int nlev = odd ? (idx_max - idx_min + 1) : 0;
-        double rv[2 + 2 * kBlockCk];
-        kin_parts<KD>(zr, zg, minv, D, rv[0], rv[1]);
-#pragma unroll
-        for (int k = 0; k < KD; ++k) rho_s[k] += zr[k];
-        for (int q = 0; q < nlev; ++q) {
-          const int i = idx_max - q;
-          double a = 0.0, b = 0.0;
-#pragma unroll
-          for (int k = 0; k < KD; ++k) {
-            const double cr = ck_r[i][k];
-            const double sr = rho_s[k] - ck_rho[i][k] + cr;
-            a += sr * (minv[k] * cr);
-            b += sr * (minv[k] * zr[k]);
-          }
-          rv[2 + 2 * q] = a;
-          rv[3 + 2 * q] = b;
-        }
-        block_reduce_n(rv, 2 + 2 * nlev, red);
-        const double K = 0.5 * rv[0];
-        const bool ok = isfinite(zlp) && rv[1] == 0.0 && isfinite(K);
-        zH = ok ? (-zlp + K) : CUDART_INF;
-        const double dH = zH - H0;
-        const double a = exp(fmin(0.0, -dH));
-        sum_a += a;
-        ++n_a;
-        if (fabs(dH) > fabs(dHmax)) dHmax = dH;
-        const double lw_leaf = -dH;
-        const double lw_new = ls_logaddexp(lw_s, lw_leaf);
-        const double p = (lw_leaf == -CUDART_INF) ? 0.0 : exp(lw_leaf - lw_new);
-        const double u = uniform1(rp.seed, gchain, it, SLOT_LEAF, (1u << j) + (uint32_t)n);
-        if (u < p) {
-#pragma unroll
-          for (int k = 0; k < KD; ++k) {
-            thS[k] = zt[k];
-            gS[k] = zg[k];
-          }
-          lpS = zlp;
-          HS = zH;
-        }
-        lw_s = lw_new;
-        if (!(dH < rp.delta_max)) {
-          numerr = true;
-          term_s = true;
-          break;
-        }
-        if (!odd) {
-#pragma unroll
-          for (int k = 0; k < KD; ++k) {
-            ck_r[idx_max][k] = zr[k];
-            ck_rho[idx_max][k] = rho_s[k];
-          }
-        } else {
-          for (int q = 0; q < nlev; ++q)
-            if ((rv[2 + 2 * q] <= 0.0) || (rv[3 + 2 * q] <= 0.0)) term_s = true;
-          if (term_s) break;
-        }
+        for (int k = 0; k < KD; ++k) r[k] = r[k] + half * zg[k];
+        double ev[2];
+        kin_parts<KD>(r, zg, minv, D, ev[0], ev[1]);
+        block_reduce<2>(ev, red);
+        const double K = 0.5 * ev[0];
+        zH = (isfinite(zlp) && ev[1] == 0.0 && isfinite(K)) ? (-zlp + K) : CUDART_INF;
+        ++nsteps;
+        if (!isfinite(zH)) break;
       }
+      const double dH = zH - H0;
+      const double alpha = exp(fmin(0.0, -dH));
+      const double u = uniform1(rp.seed, gchain, it, SLOT_MH, 0u);
+      const bool accept = u < alpha;
+      if (accept) {
+#pragma unroll
+        for (int k = 0; k < KD; ++k) {
+          th[k] = zt[k];
+          g[k] = zg[k];
+        }
+        lp = zlp;
+      }
+      stats[ST_NSTEPS] = (double)nsteps;
+      stats[ST_ACC] = alpha;
+      stats[ST_LP] = lp;
+      stats[ST_H] = accept ? zH : H0;
+      stats[ST_HERR] = accept ? dH : 0.0;
+      stats[ST_MAXHERR] = dH;
+      stats[ST_DEPTH] = accept ? 1.0 : 0.0;
+      stats[ST_NUMERR] = isfinite(zH) ? 0.0 : 1.0;
+      stats[ST_EPS] = eps;
+    } else {
+    // ---- tree ----
+      double edge[2][3 * KD], elp[2];
 #pragma unroll
       for (int k = 0; k < KD; ++k) {
-        edge[v][k] = zt[k];
-        edge[v][KD + k] = zr[k];
-        edge[v][2 * KD + k] = zg[k];
+        edge[0][k] = edge[1][k] = th[k];
+        edge[0][KD + k] = edge[1][KD + k] = r[k];
+        edge[0][2 * KD + k] = edge[1][2 * KD + k] = g[k];
       }
-      elp[v] = zlp;
-      if (!term_s) {
-        const double u = uniform1(rp.seed, gchain, it, SLOT_MH, (uint32_t)j);
-        ++j;
-        const double dl = lw_s - lw;
-        if (u < (dl < 0.0 ? exp(dl) : 1.0)) {
-#pragma unroll
-          for (int k = 0; k < KD; ++k) {
-            thC[k] = thS[k];
-            gC[k] = gS[k];
-          }
-          lpC = lpS;
-          HC = HS;
-        }
-      }
-      double d2[2] = {0.0, 0.0};
+      elp[0] = elp[1] = lp;
+      double rho[KD], thC[KD], gC[KD];
 #pragma unroll
       for (int k = 0; k < KD; ++k) {
-        rho[k] += rho_s[k];
-        d2[0] += rho[k] * (minv[k] * edge[0][KD + k]);
-        d2[1] += rho[k] * (minv[k] * edge[1][KD + k]);
+        rho[k] = r[k];
+        thC[k] = th[k];
+        gC[k] = g[k];
       }
-      block_reduce<2>(d2, red);
-      lw = ls_logaddexp(lw, lw_s);
-      term = term_s || (d2[0] <= 0.0) || (d2[1] <= 0.0);
-    }
-    double stats[TNUTS_NSTAT];
-    stats[ST_NSTEPS] = (double)n_a;
-    stats[ST_ACC] = sum_a / (double)n_a;
-    stats[ST_LP] = lpC;
-    stats[ST_H] = HC;
-    stats[ST_HERR] = HC - H0;
-    stats[ST_MAXHERR] = dHmax;
-    stats[ST_DEPTH] = (double)j;
-    stats[ST_NUMERR] = numerr ? 1.0 : 0.0;
-    stats[ST_EPS] = eps;
+      double sum_a = 0.0, dHmax = 0.0, lw = 0.0, lpC = lp, HC = H0;
+      long long n_a = 0;
+      double ck_r[kBlockCk][KD], ck_rho[kBlockCk][KD];
+      int j = 0;
+      bool term = false, numerr = false;
+      while (!term && j < rp.max_depth) {
+        const int v = (uniform1(rp.seed, gchain, it, SLOT_DIRECTION, (uint32_t)j) < 0.5) ? 0 : 1;
+        const double se = v ? eps : -eps, half = 0.5 * se;
+        double zt[KD], zr[KD], zg[KD], zlp = elp[v], zH = 0.0;
 #pragma unroll
-    for (int k = 0; k < KD; ++k) {
-      th[k] = thC[k];
-      g[k] = gC[k];
+        for (int k = 0; k < KD; ++k) {
+          zt[k] = edge[v][k];
+          zr[k] = edge[v][KD + k];
+          zg[k] = edge[v][2 * KD + k];
+        }
+        double rho_s[KD], thS[KD], gS[KD], lpS = 0.0, HS = 0.0;
+#pragma unroll
+        for (int k = 0; k < KD; ++k) rho_s[k] = 0.0;
+        double lw_s = -CUDART_INF;
+        bool term_s = false;
+        const int nleaf = 1 << j;
+        for (int n = 0; n < nleaf; ++n) {
+          // leapfrog
+#pragma unroll
+          for (int k = 0; k < KD; ++k) {
+            zr[k] = zr[k] + half * zg[k];
+            zt[k] = zt[k] + se * (minv[k] * zr[k]);
+          }
+          zlp = M::lpgrad(m, hs, sth, red, zt, zg);
+          ++ngrad;
+#pragma unroll
+          for (int k = 0; k < KD; ++k) zr[k] = zr[k] + half * zg[k];
+          // one block reduction: kinetic energy, finiteness, and the sub-tree U-turn dots
+          const int idx_max = __popc((unsigned)n >> 1);
+          const bool odd = (n & 1) != 0;
+          const int ntrail = __ffs(~(unsigned)n) - 1;
+          const int idx_min = idx_max - ntrail + 1;
+          const int nlev = odd ? (idx_max - idx_min + 1) : 0;
+          double rv[2 + 2 * kBlockCk];
+          kin_parts<KD>(zr, zg, minv, D, rv[0], rv[1]);
+#pragma unroll
+          for (int k = 0; k < KD; ++k) rho_s[k] += zr[k];
+          for (int q = 0; q < nlev; ++q) {
+            const int i = idx_max - q;
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int k = 0; k < KD; ++k) {
+              const double cr = ck_r[i][k];
+              const double sr = rho_s[k] - ck_rho[i][k] + cr;
+              a += sr * (minv[k] * cr);
+              b += sr * (minv[k] * zr[k]);
+            }
+            rv[2 + 2 * q] = a;
+            rv[3 + 2 * q] = b;
+          }
+          block_reduce_n(rv, 2 + 2 * nlev, red);
+          const double K = 0.5 * rv[0];
+          const bool ok = isfinite(zlp) && rv[1] == 0.0 && isfinite(K);
+          zH = ok ? (-zlp + K) : CUDART_INF;
+          const double dH = zH - H0;
+          const double a = exp(fmin(0.0, -dH));
+          sum_a += a;
+          ++n_a;
+          if (fabs(dH) > fabs(dHmax)) dHmax = dH;
+          const double lw_leaf = -dH;
+          const double lw_new = ls_logaddexp(lw_s, lw_leaf);
+          const double p = (lw_leaf == -CUDART_INF) ? 0.0 : exp(lw_leaf - lw_new);
+          const double u = uniform1(rp.seed, gchain, it, SLOT_LEAF, (1u << j) + (uint32_t)n);
+          if (u < p) {
+#pragma unroll
+            for (int k = 0; k < KD; ++k) {
+              thS[k] = zt[k];
+              gS[k] = zg[k];
+            }
+            lpS = zlp;
+            HS = zH;
+          }
+          lw_s = lw_new;
+          if (!(dH < rp.delta_max)) {
+            numerr = true;
+            term_s = true;
+            break;
+          }
+          if (!odd) {
+#pragma unroll
+            for (int k = 0; k < KD; ++k) {
+              ck_r[idx_max][k] = zr[k];
+              ck_rho[idx_max][k] = rho_s[k];
+            }
+          } else {
+            for (int q = 0; q < nlev; ++q)
+              if ((rv[2 + 2 * q] <= 0.0) || (rv[3 + 2 * q] <= 0.0)) term_s = true;
+            if (term_s) break;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < KD; ++k) {
+          edge[v][k] = zt[k];
+          edge[v][KD + k] = zr[k];
+          edge[v][2 * KD + k] = zg[k];
+        }
+        elp[v] = zlp;
+        if (!term_s) {
+          const double u = uniform1(rp.seed, gchain, it, SLOT_MH, (uint32_t)j);
+          ++j;
+          const double dl = lw_s - lw;
+          if (u < (dl < 0.0 ? exp(dl) : 1.0)) {
+#pragma unroll
+            for (int k = 0; k < KD; ++k) {
+              thC[k] = thS[k];
+              gC[k] = gS[k];
+            }
+            lpC = lpS;
+            HC = HS;
+          }
+        }
+        double d2[2] = {0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < KD; ++k) {
+          rho[k] += rho_s[k];
+          d2[0] += rho[k] * (minv[k] * edge[0][KD + k]);
+          d2[1] += rho[k] * (minv[k] * edge[1][KD + k]);
+        }
+        block_reduce<2>(d2, red);
+        lw = ls_logaddexp(lw, lw_s);
+        term = term_s || (d2[0] <= 0.0) || (d2[1] <= 0.0);
+      }
+      stats[ST_NSTEPS] = (double)n_a;
+      stats[ST_ACC] = sum_a / (double)n_a;
+      stats[ST_LP] = lpC;
+      stats[ST_H] = HC;
+      stats[ST_HERR] = HC - H0;
+      stats[ST_MAXHERR] = dHmax;
+      stats[ST_DEPTH] = (double)j;
+      stats[ST_NUMERR] = numerr ? 1.0 : 0.0;
+      stats[ST_EPS] = eps;
+#pragma unroll
+      for (int k = 0; k < KD; ++k) {
+        th[k] = thC[k];
+        g[k] = gC[k];
+      }
+      lp = lpC;
     }
-    lp = lpC;
     iter += 1;
 
     // ---- AHMC.adapt! ----

@@ -193,8 +193,6 @@ static LockstepExt *ext_of(Engine *e) { return reinterpret_cast<LockstepExt *>(e
 
 // ------------------------------------------------------------------------------------------
 int lockstep_create(Engine *e) {
-  if (e->cfg.algorithm != TNUTS_ALG_NUTS)
-    return set_error(e, TNUTS_E_UNSUPPORTED, "lock-step strategy implements NUTS only (HMC/HMCDA run on the thread-per-chain strategy)");
   if (e->cfg.max_depth > kMaxLevels)
     return set_error(e, TNUTS_E_UNSUPPORTED, "lock-step: max_depth too large");
   LockstepExt *x = new LockstepExt();
@@ -475,6 +473,11 @@ k_ls_fs_decide(ChainState st, LockstepState ls, int *n_left) {
   }
 }
 
+__global__ void k_ls_set_eps(ChainState st, double eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < st.C) st.eps[c] = eps;
+}
+
 __global__ void k_ls_finish_init(ChainState st) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= st.C) return;
@@ -510,7 +513,10 @@ int lockstep_init(Engine *e, const double *theta0_dev) {
     n_bad = ls->h_count[0];
   }
   if (n_bad > 0) return TNUTS_OK;  // tnuts_init reports TNUTS_E_INIT from the status array
-  if (e->cfg.init_eps == 0.0) {
+  if (e->cfg.init_eps == 0.0 && e->cfg.algorithm == TNUTS_ALG_HMC) {
+    k_ls_set_eps<<<(C + 255) / 256, 256, 0, e->stream>>>(st, 0.1);
+    e->launches += 1;
+  } else if (e->cfg.init_eps == 0.0) {
     // find_good_stepsize for every chain
     k_ls_fs_begin<<<tiles(C), kTileThreads, 0, e->stream>>>(st, *ls, e->rp);
     e->launches += 1;
@@ -554,7 +560,7 @@ int lockstep_run(Engine *e) {
   cudaEvent_t ev[2];
   TN_CUDA(e, cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
   TN_CUDA(e, cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
-  const long long max_pumps = rp.n_transitions * ((1LL << rp.max_depth) + 2) + 64;
+  const long long max_pumps = rp.n_transitions * ((1LL << rp.max_depth) + 2 + (rp.algorithm != TNUTS_ALG_NUTS ? 100000 : 0)) + 64;
   int listed_done = -1, n_max = C;
   rc = TNUTS_OK;
   // Rows sharded over ranks: every pump contains an NCCL all-reduce, so all ranks must issue

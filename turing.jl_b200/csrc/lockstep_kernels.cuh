@@ -244,9 +244,40 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
     }
   }
   tile_reduce<2>(a1, red);
+  const bool hmc = rp.algorithm != TNUTS_ALG_NUTS;
   bool accept = false, divergent = false, term_s = false, sub_done = false;
+  bool trans_end = false;
   double zH = 0.0;
-  if (leaf) {
+  if (leaf && hmc) {
+    // ---- HMC / HMCDA: static trajectory of j (= L) leapfrogs, Metropolis accept at its end ----
+    const double K = 0.5 * a1[0];
+    const bool ok = isfinite(zlp) && a1[1] == 0.0 && isfinite(K);
+    zH = ok ? (-zlp + K) : CUDART_INF;
+    n += 1;
+    n_a += 1;
+    if (n >= j || !ok) {
+      const double dH = zH - H0;
+      const double alpha = exp(fmin(0.0, -dH));
+      const double u = uniform1(rp.seed, gchain, it, SLOT_MH, 0u);
+      accept = u < alpha;
+      sum_a = alpha * (double)n_a;  // acceptance_rate column = alpha
+      dHmax = dH;
+      numerr = ok ? 0 : 1;
+      if (accept) {
+#pragma unroll 4
+        for (int d = t.dl; d < D; d += kTileD) {
+          const size_t o = (size_t)d * C + t.c;
+          thC_[o] = zt_[o];
+          gC_[o] = zg_[o];
+        }
+        lpC = zlp;
+        HC = zH;
+      }
+      j = accept ? 1 : 0;  // the tree_depth column carries is_accept for HMC
+      trans_end = true;
+    }
+  }
+  if (leaf && !hmc) {
     const double K = 0.5 * a1[0];
     const bool ok = isfinite(zlp) && a1[1] == 0.0 && isfinite(K);
     zH = ok ? (-zlp + K) : CUDART_INF;
@@ -276,7 +307,7 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
   const bool odd = (n & 1) != 0;
   const int ntrail = __ffs(~(unsigned)n) - 1;
   const int idx_min = idx_max - ntrail + 1;
-  const int nlev = (leaf && odd && !divergent) ? (idx_max - idx_min + 1) : 0;
+  const int nlev = (leaf && !hmc && odd && !divergent) ? (idx_max - idx_min + 1) : 0;
   if (threadIdx.x == 0) s_maxlev = 0;
   __syncthreads();
   if (t.dl == 0 && nlev > 0) atomicMax(&s_maxlev, nlev);
@@ -285,7 +316,7 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
   double dots[2 * kMaxLevels];
 #pragma unroll
   for (int q = 0; q < 2 * kMaxLevels; ++q) dots[q] = 0.0;
-  if (leaf) {
+  if (leaf && !hmc) {
 #pragma unroll 4
     for (int d = t.dl; d < D; d += kTileD) {
       const size_t o = (size_t)d * C + t.c;
@@ -318,13 +349,12 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
     tile_reduce<2>(pr, red);
     if (q < nlev && ((pr[0] <= 0.0) || (pr[1] <= 0.0))) term_s = true;
   }
-  if (leaf) {
+  if (leaf && !hmc) {
     sub_done = term_s || (n + 1 == (1 << j));
     if (!sub_done) n += 1;
   }
 
   // ================= [B] end of a doubling =================
-  bool trans_end = false;
   if (__syncthreads_or(leaf && sub_done)) {
     const bool me = leaf && sub_done;
     bool take = false;
@@ -557,7 +587,16 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
       elp0 = elp1 = lp0;
       j = 0;
       numerr = 0;
-      v = (uniform1(rp.seed, gchain, it, SLOT_DIRECTION, 0u) < 0.5) ? 0 : 1;
+      if (hmc) {
+        v = 1;
+        j = rp.n_leapfrog;
+        if (rp.algorithm == TNUTS_ALG_HMCDA) {
+          j = (int)floor(rp.lambda / eps);
+          if (j < 1) j = 1;
+        }
+      } else {
+        v = (uniform1(rp.seed, gchain, it, SLOT_DIRECTION, 0u) < 0.5) ? 0 : 1;
+      }
       zlp = lp0;
       lw_s = -CUDART_INF;
       n = 0;
