@@ -44,6 +44,42 @@ def test_eight_schools_agrees_with_oracle_posterior(built):
     assert ch.ess_bulk().min() > 0.2 * 1024 * 1000
 
 
+@pytest.mark.parametrize("which", ["logistic", "hier", "linreg"])
+def test_big_families_agree_with_oracle_posterior(built, which):
+    """posterior means within 4 MCSE and variances within 15 % of the oracle's NUTS, R-hat < 1.01,
+    for the families that run on the pump / CTA-per-chain strategies"""
+    if which == "logistic":
+        model = T.models.synthetic_logistic(400, 6, seed=8)
+    elif which == "hier":
+        model = T.models.synthetic_hier(12, 30, seed=9)   # informative groups: no funnel
+    else:
+        model = T.models.config1_linear_regression()
+    spl = T.NUTS(0.8)
+    ch = T.sample(model, spl, T.MCMCThreads(), 600, 512, seed=13, verbose=False, diagnostics=True)
+    ref = O.sample_chains(oracle_of(model), oracle_config(spl, 300, 2013), 64, 899, first_keep=300)
+    sr = dg.summarize(ref["params"])
+    gp = ch.get_params()
+    P = model.D
+    mean = gp.mean(axis=(0, 2))
+    var = gp.transpose(1, 0, 2).reshape(P, -1).var(axis=1, ddof=1)
+    assert ch.rhat().max() < 1.01 and sr["rhat"].max() < 1.02
+    assert np.abs((mean - sr["mean"]) / sr["mcse"]).max() < 4.5
+    assert np.abs(var / sr["var"] - 1).max() < 0.2
+    assert ch.size() == (600, P + 12, 512)
+    np.testing.assert_allclose(ch["logjoint"], ch["logprior"] + ch["loglikelihood"], rtol=1e-10)
+
+
+def test_single_chain_and_odd_counts(built):
+    """ragged sizes: 1 chain, chain counts that are not multiples of the CTA / tile sizes"""
+    for model in (T.gdemo_default(), T.models.synthetic_logistic(77, 3, seed=1), T.models.synthetic_hier(3, 5)):
+        for n in (1, 13):
+            ch = T.sample(model, T.NUTS(20, 0.8), T.MCMCThreads(), 30, n, seed=2, verbose=False)
+            assert ch.size() == (30, model.D + 12, n)
+            assert np.all(np.isfinite(ch.value))
+    ch = T.sample(T.gdemo_default(), T.NUTS(20, 0.8), 25, seed=2, verbose=False)
+    assert ch.size() == (25, 14, 1)
+
+
 def test_device_diagnostics_match_numpy(built):
     ch = T.sample(T.EightSchools(), T.NUTS(0.8), T.MCMCThreads(), 400, 48, seed=4, verbose=False,
                   diagnostics=True)

@@ -57,12 +57,10 @@ int thread_run(Engine *e) {
     const int *pm_ = e->perm_valid ? e->perm : nullptr;                                      \
     if (e->flat && e->cfg.algorithm == TNUTS_ALG_NUTS)                                       \
       k_chain_run_flat<M, 2><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_); \
-    else if (e->occupancy == 3)                                                              \
-      k_chain_run<M, 3><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_);  \
-    else if (e->occupancy == 4)                                                              \
-      k_chain_run<M, 4><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_);  \
+    else if (e->cfg.algorithm != TNUTS_ALG_NUTS)                                             \
+      k_chain_run<M, 2, false><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_); \
     else                                                                                     \
-      k_chain_run<M, 2><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_);  \
+      k_chain_run<M, 2, true><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_); \
   } while (0)
   TN_DISPATCH_SMALL(e, CALL);
 #undef CALL

@@ -310,7 +310,7 @@ __device__ __forceinline__ void hmc_transition_d(const SmallData &md, const RunP
 // ------------------------------------------------------------------------------------------
 // run kernel: n_transitions for every chain
 // ------------------------------------------------------------------------------------------
-template <class M, int MINB>
+template <class M, int MINB, bool IS_NUTS>
 __global__ void __launch_bounds__(kChainBlock, MINB) k_chain_run(SmallData md, ChainState st,
                                                                 DrawBuffers out, RunParams rp,
                                                                 const int *__restrict__ perm) {
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(kChainBlock, MINB) k_chain_run(SmallData md, C
   for (long long t = 1; t <= rp.n_transitions; ++t) {
     const uint32_t it = (uint32_t)(iter + 1);
     double stats[TNUTS_NSTAT];
-    if (rp.algorithm == TNUTS_ALG_NUTS)
+    if (IS_NUTS)  // compile-time: the NUTS kernel carries no HMC code and vice versa
       nuts_transition_d<M>(md, rp, gchain, it, th, g, lp, minv, eps, ngrad, stats);
     else
       hmc_transition_d<M>(md, rp, gchain, it, th, g, lp, minv, eps, ngrad, stats);

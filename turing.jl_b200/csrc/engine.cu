@@ -490,7 +490,6 @@ int tnuts_set_option(tnuts_engine *h, const char *name, double value) {
   if (!e || !name) return set_error(e, TNUTS_E_ARG, "tnuts_set_option: null argument");
   const std::string n(name);
   if (n == "keep_theta") e->keep_theta = value != 0.0;
-  else if (n == "occupancy") e->occupancy = (int)value;
   else if (n == "sort_chains") e->sort_chains = value != 0.0;
   else if (n == "flat") e->flat = value != 0.0;
   else if (n == "flat_batch") e->rp.flat_batch = (int)value;

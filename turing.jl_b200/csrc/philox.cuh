@@ -7,8 +7,10 @@
 
 namespace tnuts {
 
-__device__ __forceinline__ uint4 philox4x32_10(unsigned long long seed, uint32_t c0, uint32_t c1,
-                                               uint32_t c2, uint32_t c3) {
+// NOT inlined on purpose: the thread-per-chain kernel draws from ~25 call sites; inlining the
+// 10 rounds everywhere made its SASS 133 KB (instruction-fetch stalls in the ncu profile)
+static __device__ __noinline__ uint4 philox4x32_10(unsigned long long seed, uint32_t c0, uint32_t c1,
+                                                   uint32_t c2, uint32_t c3) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
@@ -45,7 +47,7 @@ __device__ __forceinline__ double uniform1(unsigned long long seed, uint32_t cha
 }
 
 // Box-Muller: two normals per Philox block
-__device__ __forceinline__ void normal2(unsigned long long seed, uint32_t chain, uint32_t iter,
+static __device__ __noinline__ void normal2(unsigned long long seed, uint32_t chain, uint32_t iter,
                                         uint32_t slot, uint32_t sub, double &z0, double &z1) {
   double u0, u1;
   uniform2(seed, chain, iter, slot, sub, u0, u1);
