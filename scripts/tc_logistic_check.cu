@@ -151,17 +151,20 @@ static int run_case(long long N, int D, int C, int ncheck, bool timing, bool use
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; ++i) CK(tc::launch(data, N, D, dth, C, nullptr, nullptr, C, C, dpart, cap, 0, nullptr));
-    CK(cudaEventRecord(e0));
-    const int reps = 20;
-    for (int i = 0; i < reps; ++i) CK(tc::launch(data, N, D, dth, C, nullptr, nullptr, C, C, dpart, cap, 0, nullptr));
-    CK(cudaEventRecord(e1));
-    CK(cudaDeviceSynchronize());
-    float ms;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    ms /= reps;
-    printf("TIMING N=%lld D=%d C=%d: %.3f ms per gradient of all chains = %.1f TFLOP/s-equivalent (4ND per chain)\n", N, D,
-           C, ms, 4.0 * N * D * C / (ms * 1e-3) / 1e12);
+    const int nx = getenv("TC_XMODES") ? 4 : 1;
+    for (int xm = 0; xm < nx; ++xm) {
+      for (int i = 0; i < 3; ++i) CK(tc::launch(data, N, D, dth, C, nullptr, nullptr, C, C, dpart, cap, 0, nullptr, xm));
+      CK(cudaEventRecord(e0));
+      const int reps = 20;
+      for (int i = 0; i < reps; ++i) CK(tc::launch(data, N, D, dth, C, nullptr, nullptr, C, C, dpart, cap, 0, nullptr, xm));
+      CK(cudaEventRecord(e1));
+      CK(cudaDeviceSynchronize());
+      float ms;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      ms /= reps;
+      printf("TIMING xmode=%d N=%lld D=%d C=%d: %.3f ms per gradient of all chains = %.1f TFLOP/s-equivalent (4ND per chain)\n",
+             xm, N, D, C, ms, 4.0 * N * D * C / (ms * 1e-3) / 1e12);
+    }
   }
   tc::release(&data);
   cudaFree(dX);
@@ -176,6 +179,7 @@ static int run_case(long long N, int D, int C, int ncheck, bool timing, bool use
 int main(int argc, char **argv) {
   int bad = 0;
   const bool big = argc > 1 && atoi(argv[1]) > 0;
+  if (argc > 1 && atoi(argv[1]) == 2) return run_case(100000, 100, 4096, 1, true, false);
   bad += run_case(70, 100, 128, 4, false, false);
   bad += run_case(5000 + 17, 100, 200, 4, false, true);
   bad += run_case(3001, 128, 256, 3, false, false);

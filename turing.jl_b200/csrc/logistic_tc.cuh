@@ -40,7 +40,6 @@ namespace tnuts {
 namespace tc {
 
 constexpr int kChainsPerCta = 128;
-constexpr int kThreads = 192;
 constexpr int kStages = 4;
 constexpr int kTmemCols = 512;
 
@@ -198,14 +197,31 @@ __global__ void k_tc_convert_y(const double *__restrict__ y, long long nrows, lo
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-constexpr int kT = 64;  // rows per tile
+constexpr int kT = 64;          // rows per tile
+constexpr int kEpiWarps = 16;   // 4 lane quarters x 4 column groups of 16 rows
+constexpr int kThreads = 32 * (2 + kEpiWarps);
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 
 template <int KP>
 __global__ void __launch_bounds__(kThreads, 1)
 k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict__ yf, long long nrows, int D,
               const double *__restrict__ th, int C, const int *__restrict__ list, const int *__restrict__ count,
               int n_all, int rows_per_chunk, double *__restrict__ part /* [chunks][D+1][cap] */, int cap,
-              float *__restrict__ dbg) {
+              float *__restrict__ dbg, int xmode) {
   constexpr int T = kT;
   static_assert(KP == 64 || KP == 128, "feature padding is 64 or 128");
   constexpr int NKB = KP / 64;                      // 128-byte boxes along the feature axis
@@ -216,10 +232,12 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
   constexpr uint32_t COL_TH = 0, COL_G = 3 * TH_PLANE, COL_BUF = COL_G + KP;
   constexpr uint32_t BUF_COLS = 3 * T / 2;          // eta (T cols), then R planes (3 x T/2 cols)
   static_assert(COL_BUF + 2 * BUF_COLS <= kTmemCols, "TMEM budget");
+  constexpr int NEPI = 32 * kEpiWarps;
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kStages + 6];
   __shared__ uint32_t tmem_slot;
+  __shared__ double lp_part[kEpiWarps / 4][kChainsPerCta];
 
   const int n = count ? *count : n_all;
   const int k0 = blockIdx.x * kChainsPerCta;
@@ -230,7 +248,8 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
   const long long rend = (rbeg + rows_per_chunk < nrows) ? rbeg + rows_per_chunk : nrows;
   const int ntile = (int)((rend - rbeg + T - 1) / T);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
   const uint32_t stage0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar0 = smem_u32(bars);
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
@@ -240,18 +259,18 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
   const uint32_t bar_theta = bar0 + 8u * (2 * kStages + 4);
   const uint32_t bar_g = bar0 + 8u * (2 * kStages + 5);
 
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&mapX);
+  if (warp == 0 && elect_one()) tma_prefetch_desc(&mapX);
   if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int s = 0; s < kStages; ++s) {
         mbar_init(bar_full(s), 1);
         mbar_init(bar_empty(s), 1);
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(bar_eta(b), 1);
-        mbar_init(bar_r(b), 128);
+        mbar_init(bar_r(b), NEPI);
       }
-      mbar_init(bar_theta, 128);
+      mbar_init(bar_theta, NEPI);
       mbar_init(bar_g, 1);
       fence_barrier_init();
     }
@@ -267,12 +286,12 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
   const int n2 = (D + 15) & ~15;          // GEMM2 N
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      for (int t = 0; t < ntile; ++t) {
-        const int s = t % kStages;
-        const uint32_t ph = (uint32_t)(t / kStages) & 1u;
-        mbar_wait(bar_empty(s), ph ^ 1u);
+    // ===== TMA producer (warp-uniform control flow, one elected lane issues) =====
+    for (int t = 0; t < ntile; ++t) {
+      const int s = t % kStages;
+      const uint32_t ph = (uint32_t)(t / kStages) & 1u;
+      mbar_wait(bar_empty(s), ph ^ 1u);
+      if (elect_one()) {
         mbar_expect_tx(bar_full(s), STAGE_BYTES);
         const uint32_t dst = stage0 + (uint32_t)s * STAGE_BYTES;
         const int row0 = (int)(rbeg + (long long)t * T);
@@ -282,75 +301,85 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
           for (int kb = 0; kb < NKB; ++kb)
             tma_load_3d(dst + pl * PLANE_BYTES + kb * BOX_BYTES, &mapX, bar_full(s), kb * 64, row0, pl);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc1 = instr_desc(T, 0);
-      const uint32_t idesc2 = instr_desc(n2, 1);
-      // the six plane products, smallest first: (A plane, B plane)
-      constexpr int PA[6] = {2, 1, 0, 1, 0, 0};
-      constexpr int PB[6] = {0, 1, 2, 0, 1, 0};
-      auto gemm1 = [&](int t) {
-        const int s = t % kStages;
-        mbar_wait(bar_full(s), (uint32_t)(t / kStages) & 1u);
-        tc_fence_after();
-        const uint32_t d_col = tmem + COL_BUF + (uint32_t)(t & 1) * BUF_COLS;
-        const uint32_t xs = stage0 + (uint32_t)s * STAGE_BYTES;
-        uint32_t acc = 0;
+    // ===== MMA issuer (warp-uniform control flow, one elected lane issues) =====
+    const uint32_t idesc1 = instr_desc(T, 0);
+    const uint32_t idesc2 = instr_desc(n2, 1);
+    // descriptor words: hi = SBO 1024 | version 1 | SWIZZLE_128B; lo = address | LBO
+    constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+    constexpr uint32_t LBO_K = (16u >> 4) << 16, LBO_MN = (BOX_BYTES >> 4) << 16;
+    // the six plane products, smallest first: (A plane, B plane)
+    constexpr int PA[6] = {2, 1, 0, 1, 0, 0};
+    constexpr int PB[6] = {0, 1, 2, 0, 1, 0};
+    const int q0 = (xmode & 2) ? 5 : 0;
+    auto gemm1 = [&](int t) {
+      const int s = t % kStages;
+      mbar_wait(bar_full(s), (uint32_t)(t / kStages) & 1u);
+      tc_fence_after();
+      const uint32_t d_col = tmem + COL_BUF + (uint32_t)(t & 1) * BUF_COLS;
+      const uint32_t xs = (stage0 + (uint32_t)s * STAGE_BYTES) >> 4;
+      if (elect_one()) {
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
+          if (q < q0) continue;
           const uint32_t a_col = tmem + COL_TH + PA[q] * TH_PLANE;
-          const uint32_t b = xs + PB[q] * PLANE_BYTES;
-          for (int ks = 0; ks < ks1; ++ks) {
-            const uint64_t bd = smem_desc(b + (uint32_t)(ks >> 2) * BOX_BYTES + (uint32_t)(ks & 3) * 32u, 16, 1024);
-            mma_bf16_ts(d_col, a_col + (uint32_t)ks * 8u, bd, idesc1, acc);
-            acc = 1;
+          const uint32_t b_lo = (xs + PB[q] * (PLANE_BYTES >> 4)) | LBO_K;
+#pragma unroll
+          for (int ks = 0; ks < KP / 16; ++ks) {
+            if (ks < ks1) {
+              const uint32_t lo = b_lo + (uint32_t)(ks >> 2) * (BOX_BYTES >> 4) + (uint32_t)(ks & 3) * 2u;
+              mma_bf16_ts(d_col, a_col + (uint32_t)ks * 8u, ((uint64_t)DESC_HI << 32) | lo, idesc1,
+                          (q > q0 || ks > 0) ? 1u : 0u);
+            }
           }
         }
         tc_commit(bar_eta(t & 1));
-      };
-      uint32_t accg = 0;
-      auto gemm2 = [&](int t) {
-        const int s = t % kStages;
-        mbar_wait(bar_r(t & 1), (uint32_t)(t >> 1) & 1u);
-        tc_fence_after();
-        const uint32_t r_col = tmem + COL_BUF + (uint32_t)(t & 1) * BUF_COLS;
-        const uint32_t xs = stage0 + (uint32_t)s * STAGE_BYTES;
+      }
+      __syncwarp();
+    };
+    auto gemm2 = [&](int t) {
+      const int s = t % kStages;
+      mbar_wait(bar_r(t & 1), (uint32_t)(t >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t r_col = tmem + COL_BUF + (uint32_t)(t & 1) * BUF_COLS;
+      const uint32_t xs = (stage0 + (uint32_t)s * STAGE_BYTES) >> 4;
+      if (elect_one()) {
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
+          if (q < q0) continue;
           const uint32_t a_col = r_col + PA[q] * (T / 2);
-          const uint32_t b = xs + PB[q] * PLANE_BYTES;
+          const uint32_t b_lo = (xs + PB[q] * (PLANE_BYTES >> 4)) | LBO_MN;
 #pragma unroll
-          for (int rs = 0; rs < T / 16; ++rs) {
-            const uint64_t bd = smem_desc(b + (uint32_t)rs * 2048u, BOX_BYTES, 1024);
-            mma_bf16_ts(tmem + COL_G, a_col + (uint32_t)rs * 8u, bd, idesc2, accg);
-            accg = 1;
-          }
+          for (int rs = 0; rs < T / 16; ++rs)
+            mma_bf16_ts(tmem + COL_G, a_col + (uint32_t)rs * 8u, ((uint64_t)DESC_HI << 32) | (b_lo + (uint32_t)rs * 128u),
+                        idesc2, (t > 0 || q > q0 || rs > 0) ? 1u : 0u);
         }
         tc_commit(bar_empty(s));
-      };
-      mbar_wait(bar_theta, 0);
-      tc_fence_after();
-      gemm1(0);
-      for (int t = 0; t < ntile; ++t) {
-        if (t + 1 < ntile) gemm1(t + 1);
-        gemm2(t);
       }
-      tc_commit(bar_g);
+      __syncwarp();
+    };
+    mbar_wait(bar_theta, 0);
+    tc_fence_after();
+    gemm1(0);
+    for (int t = 0; t < ntile; ++t) {
+      if (t + 1 < ntile) gemm1(t + 1);
+      gemm2(t);
     }
+    if (elect_one()) tc_commit(bar_g);
     __syncwarp();
   } else {
-    // ===== epilogue warps: this thread is chain slot k =====
-    const int wq = warp & 3;
+    // ===== epilogue warps: lane quarter wq (hardware: warp % 4), column group cg =====
+    const int wq = warp & 3, cg = (warp - 2) >> 2;
     const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
     const int kl = wq * 32 + lane;
     const int k = k0 + kl;
     const bool live = k < n;
     const int c = live ? (list ? list[k] : k) : 0;
-    // Theta -> TMEM, three packed bf16 planes, zero padded to the k-steps the MMAs read
-    for (int d0 = 0; d0 < 16 * ks1; d0 += 32) {
+    // Theta -> TMEM, three packed bf16 planes; this warp: features [32 cg, 32 cg + 32)
+    if (32 * cg < 16 * ks1) {
+      const int d0 = 32 * cg;
       uint32_t vh[16], vm[16], vl[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -365,8 +394,8 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
       tmem_st16(lane_addr + COL_TH + 0 * TH_PLANE + d0 / 2, vh);
       tmem_st16(lane_addr + COL_TH + 1 * TH_PLANE + d0 / 2, vm);
       tmem_st16(lane_addr + COL_TH + 2 * TH_PLANE + d0 / 2, vl);
+      tc_wait_st();
     }
-    tc_wait_st();
     tc_fence_before();
     mbar_arrive(bar_theta);
 
@@ -374,72 +403,94 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
     constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
     for (int t = 0; t < ntile; ++t) {
       const int b = t & 1;
+      const long long row0 = rbeg + (long long)t * T + 16 * cg;   // this warp's 16 rows
+      // y of this warp's rows (independent of the MMA: issue the loads before waiting)
+      float ys[16];
+      {
+        const float4 *yp = reinterpret_cast<const float4 *>(yf + row0);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 y4 = __ldg(yp + j4);
+          ys[4 * j4 + 0] = y4.x;
+          ys[4 * j4 + 1] = y4.y;
+          ys[4 * j4 + 2] = y4.z;
+          ys[4 * j4 + 3] = y4.w;
+        }
+      }
       mbar_wait(bar_eta(b), (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
       const uint32_t buf = lane_addr + COL_BUF + (uint32_t)b * BUF_COLS;
-      const long long row0 = rbeg + (long long)t * T;
-      uint32_t v[T];
-#pragma unroll
-      for (int q = 0; q < T / 16; ++q) tmem_ld16(buf + q * 16, v + q * 16);
+      uint32_t v[16];
+      tmem_ld16(buf + 16 * cg, v);
       tc_wait_ld();
       const bool dump = dbg && blockIdx.x == 0 && blockIdx.y == 0 && t == 0;
       if (dump) {
 #pragma unroll
-        for (int j = 0; j < T; ++j) dbg[kl * T + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 16; ++j) dbg[kl * T + 16 * cg + j] = __uint_as_float(v[j]);
       }
-      uint32_t ph[T / 2], pm[T / 2], pl[T / 2];
-      const float4 *yp = reinterpret_cast<const float4 *>(yf + row0);
+      float rr[16], tsum = 0.f;
+      const int nvalid = (nrows - row0 >= 16) ? 16 : (int)(nrows - row0);  // <= 0: tile rows past the data
 #pragma unroll
-      for (int j4 = 0; j4 < T / 4; ++j4) {
-        const float4 y4 = __ldg(yp + j4);
-        const float ys[4] = {y4.x, y4.y, y4.z, y4.w};
-        float rr[4];
-        float acc4 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int j = j4 * 4 + i;
-          const float eta = __uint_as_float(v[j]);
-          const float e = ex2_approx(-fabsf(eta) * kLog2e);      // exp(-|eta|) in (0, 1]
-          const float s = rcp_approx(1.f + e);
-          const float sig = eta >= 0.f ? s : e * s;
-          rr[i] = ys[i] - sig;
-          const float l1 = fmaxf(eta, 0.f) + kLn2 * lg2_approx(1.f + e);
-          const float term = ys[i] * eta - l1;
-          acc4 += (row0 + j < nrows) ? term : 0.f;
+      for (int j = 0; j < 16; ++j) {
+        const float eta = __uint_as_float(v[j]);
+        if (xmode & 1) {
+          rr[j] = eta;
+          continue;
         }
-        lp += (double)acc4;
-        if (dump) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dbg[128 * T + kl * T + j4 * 4 + i] = rr[i];
+        const float e = ex2_approx(-fabsf(eta) * kLog2e);      // exp(-|eta|) in (0, 1]
+        const float s = rcp_approx(1.f + e);
+        const float sig = eta >= 0.f ? s : e * s;
+        rr[j] = ys[j] - sig;
+        const float l1 = fmaxf(eta, 0.f) + kLn2 * lg2_approx(1.f + e);
+        const float term = ys[j] * eta - l1;
+        tsum += (j < nvalid) ? term : 0.f;
+        if ((j & 3) == 3) {
+          lp += (double)tsum;
+          tsum = 0.f;
         }
-        split3(rr[0], rr[1], ph[2 * j4], pm[2 * j4], pl[2 * j4]);
-        split3(rr[2], rr[3], ph[2 * j4 + 1], pm[2 * j4 + 1], pl[2 * j4 + 1]);
       }
+      if (dump) {
 #pragma unroll
-      for (int q = 0; q < T / 32; ++q) {
-        tmem_st16(buf + 0 * (T / 2) + q * 16, ph + q * 16);
-        tmem_st16(buf + 1 * (T / 2) + q * 16, pm + q * 16);
-        tmem_st16(buf + 2 * (T / 2) + q * 16, pl + q * 16);
+        for (int j = 0; j < 16; ++j) dbg[128 * T + kl * T + 16 * cg + j] = rr[j];
       }
+      // all four column groups must have read eta before anybody overwrites it with R planes
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + wq), "r"(32 * (kEpiWarps / 4)) : "memory");
+      uint32_t ph[8], pm[8], pl[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split3(rr[2 * j], rr[2 * j + 1], ph[j], pm[j], pl[j]);
+      tmem_st8(buf + 0 * (T / 2) + 8 * cg, ph);
+      tmem_st8(buf + 1 * (T / 2) + 8 * cg, pm);
+      tmem_st8(buf + 2 * (T / 2) + 8 * cg, pl);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(bar_r(b));
     }
-    // G -> partial sums (fp64), chain slot fastest
+    // G -> partial sums (fp64), chain slot fastest; this warp: features [32 cg, 32 cg + 32)
+    lp_part[cg][kl] = lp;
     mbar_wait(bar_g, 0);
     tc_fence_after();
     double *pc = part + (size_t)chunk * (D + 1) * cap;
-    for (int d0 = 0; d0 < n2; d0 += 16) {
-      uint32_t g[16];
-      tmem_ld16(lane_addr + COL_G + d0, g);
-      tc_wait_ld();
-      if (live) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (d0 + j < D) pc[(size_t)(d0 + j) * cap + k] = (double)__uint_as_float(g[j]);
+    for (int h = 0; h < 2; ++h) {
+      const int d0 = 32 * cg + 16 * h;
+      if (d0 < n2) {
+        uint32_t g[16];
+        tmem_ld16(lane_addr + COL_G + d0, g);
+        tc_wait_ld();
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (d0 + j < D) pc[(size_t)(d0 + j) * cap + k] = (double)__uint_as_float(g[j]);
+        }
       }
     }
-    if (live) pc[(size_t)D * cap + k] = lp;
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + wq), "r"(32 * (kEpiWarps / 4)) : "memory");
+    if (cg == 0 && live) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < kEpiWarps / 4; ++q) s += lp_part[q][kl];
+      pc[(size_t)D * cap + k] = s;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -526,7 +577,7 @@ inline void release(Data *d) {
 // partial sums part[chunk][D+1][cap] for the n_max (upper bound) chains of the work list
 inline cudaError_t launch(const Data &d, long long nrows, int D, const double *th, int C, const int *list,
                           const int *count, int n_all, int n_max, double *part, int cap, cudaStream_t stream,
-                          float *dbg = nullptr) {
+                          float *dbg = nullptr, int xmode = 0) {
   const Plan &p = d.pl;
   const dim3 grid((n_max + kChainsPerCta - 1) / kChainsPerCta, p.chunks);
 #define TN_TC_LAUNCH(KP_)                                                                                 \
@@ -535,7 +586,7 @@ inline cudaError_t launch(const Data &d, long long nrows, int D, const double *t
     cudaError_t s_ = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem); \
     if (s_ != cudaSuccess) return s_;                                                                     \
     kfn<<<grid, kThreads, p.smem, stream>>>(d.map, d.yf, nrows, D, th, C, list, count, n_all, p.rpc,      \
-                                            part, cap, dbg);                                              \
+                                            part, cap, dbg, xmode);                                       \
   } while (0)
   if (p.kp == 128) TN_TC_LAUNCH(128);
   else TN_TC_LAUNCH(64);
