@@ -157,7 +157,15 @@ int tnuts_fetch(tnuts_engine *e, double *params, double *logp, double *stats, do
 int tnuts_num_columns(const tnuts_engine *e);
 int tnuts_fetch_draws(tnuts_engine *e, double *draws);
 
-/* engine options: "keep_theta" (0/1, default 0) keeps linked-space draws for tnuts_fetch */
+/* engine options:
+ *   "keep_theta"  (0/1, default 0) keeps linked-space draws for tnuts_fetch
+ *   "sort_chains" (0/1, default 1) thread-per-chain strategy: re-sort chains by step size after warm-up
+ *   "logistic_tc" (0/1, default 0) TNUTS_LOGISTIC with D <= 128: evaluate the likelihood and its
+ *                 gradient (the X*B contraction across chains, src/mcmc/hmc.jl:181) on the tcgen05
+ *                 tensor cores with bf16x3 operand planes -- fp32-grade dot products, fp64
+ *                 accumulation of the log-likelihood -- instead of the fp64 DMMA kernel.
+ *                 Stated bounds (tests/test_gpu_tc.py): |d lp| <= 3e-7 |lp|,
+ *                 |d grad| <= 1e-4 |grad|.  Set before tnuts_init. */
 int tnuts_set_option(tnuts_engine *e, const char *name, double value);
 
 /* current linked-space position of every chain, [n_chains][D] row-major */

@@ -1,5 +1,6 @@
 """Full-job measurement of the big BASELINE.json configs (too long for the default bench.py run):
   python scripts/run_config.py logistic   # configs[2]: N=100k, D=100, 4096 chains, NUTS(0.8), 1000 draws
+  python scripts/run_config.py logistic_tc  # the same job with the tcgen05 (bf16x3) likelihood kernel
   python scripts/run_config.py hier       # configs[3]: 1000 groups x 100 obs, D=2005, 1024 chains
 Prints one JSON line (same keys as bench.py where they apply)."""
 import json, os, sys, time
@@ -11,7 +12,8 @@ def main():
     which = sys.argv[1]
     scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
     N = 1000
-    if which == "logistic":
+    tc = which == "logistic_tc"
+    if which in ("logistic", "logistic_tc"):
         model, C, name = T.models.config3_logistic(), int(4096 * scale), "BASELINE.json configs[2]: logistic regression N=100000 D=100 fp64"
         flops_per_grad = 4.0 * model.N * model.D
     else:
@@ -21,6 +23,8 @@ def main():
     nad = 500
     t0 = time.perf_counter()
     eng = T.Engine(model, spl, C, nad, seed=11)
+    if tc:
+        eng.set_option("logistic_tc", 1)
     t_create = time.perf_counter() - t0
     t0 = time.perf_counter(); eng.init(); t_init = time.perf_counter() - t0
     g_init = eng.grad_evals
@@ -46,10 +50,24 @@ def main():
         "gradient_kernel_ms_all_chains": grad_ms, "gpu_launches": int(eng.launches),
     }
     if flops_per_grad:
-        line["roofline"] = {"bound": "tensor", "unit": "TFLOP/s", "achieved": flops_per_grad * C / (grad_ms * 1e-3) / 1e12,
-                            "peak": 37.19, "peak_source": "measured here: mma.sync f64 (scripts/fp64_peak.cu); tcgen05 has no f64 kind",
-                            "kernel": "k_logistic_mma"}
-        line["roofline"]["frac"] = line["roofline"]["achieved"] / 37.19
+        if tc:
+            # executed tensor work: 12 bf16 plane products per (row, padded feature, chain):
+            # 6 for eta (K = 16*ceil(D/16)) and 6 for X^T R (N = 16*ceil(D/16)), 2 flop each
+            dpad = 16 * ((model.D + 15) // 16)
+            peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))) \
+                if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else {}
+            peak = peaks.get("bf16_tflops", 1614.0)
+            ach = 24.0 * model.N * dpad * C / (grad_ms * 1e-3) / 1e12
+            line["roofline"] = {"bound": "tensor", "unit": "TFLOP/s", "achieved": ach, "peak": peak,
+                                "peak_source": "MEASURED_PEAKS.json bf16 burst (kernel timed alone)" if peaks else "fallback",
+                                "kernel": "k_logistic_tc", "frac": ach / peak,
+                                "fp64_equivalent_tflops": flops_per_grad * C / (grad_ms * 1e-3) / 1e12,
+                                "note": "achieved = executed bf16 tensor flops (bf16x3: 12 plane products); fp64_equivalent = 4ND per chain"}
+        else:
+            line["roofline"] = {"bound": "tensor", "unit": "TFLOP/s", "achieved": flops_per_grad * C / (grad_ms * 1e-3) / 1e12,
+                                "peak": 37.19, "peak_source": "measured here: mma.sync f64 (scripts/fp64_peak.cu); tcgen05 has no f64 kind",
+                                "kernel": "k_logistic_mma"}
+            line["roofline"]["frac"] = line["roofline"]["achieved"] / 37.19
         line["sustained_tflops_whole_job"] = grads * flops_per_grad / (t_init + t_run) / 1e12
     else:
         line["roofline"] = {"bound": "hbm", "unit": "GB/s", "achieved": 6 * model.D * 8 * grads / t_run / 1e9, "peak": 6545.9}

@@ -1,0 +1,112 @@
+"""GPU: the tcgen05 (bf16x3) logistic-regression likelihood, engine option "logistic_tc"
+(turing.jl_b200/csrc/logistic_tc.cuh), through the C ABI.
+
+This mode trades the 1e-12 fp64 parity of the default DMMA path for tensor-core throughput; the
+north star allows "a stated bound in fp32".  The bounds stated (include/tnuts.h) and tested here:
+  log-likelihood ........ |d lp| <= 3e-7 * |lp|           (fp64 accumulation of fp32 terms; the tensor
+                                                          core's fp32 accumulation rounds |eta| down by
+                                                          ~1e-7 relative, a same-sign bias equivalent to
+                                                          rescaling X by 1 - 1e-7)
+  energy differences .... |d (lp_a - lp_b)| <= 1e-3 over a posterior-width cloud at N = 20000 (measured
+                          3e-4; it is the same 1e-7 shrink of eta, i.e. c * theta . grad_lik, a smooth
+                          function of theta and not noise)
+  gradient .............. |d g|_2 <= 1e-4 * |g_lik|_2     (measured ~1e-6 .. 2e-5: fp32 accumulation
+                                                          of the row sums in tensor memory)
+  sampling .............. posterior means within 4 MCSE of the fp64 path, R-hat < 1.01; the same
+                          seed gives bit-identical chains (the kernel is deterministic)
+"""
+import numpy as np
+import pytest
+
+import turing_jl_b200 as T
+
+from helpers import oracle_of
+
+pytestmark = pytest.mark.gpu
+
+TC = {"logistic_tc": 1}
+
+
+@pytest.mark.parametrize("N,D,n", [(70, 100, 5), (5017, 100, 200), (3001, 128, 130), (2000, 64, 257),
+                                   (999, 20, 64), (300, 5, 33), (1, 3, 2), (64, 1, 1)])
+def test_tc_lpgrad_against_oracle(built, N, D, n):
+    model = T.models.synthetic_logistic(N, D, seed=N + D)
+    ldf = T.LogDensityFunction(model, options=TC)
+    rng = np.random.default_rng(N)
+    th = rng.standard_normal((n, D)) * 0.5
+    lp, g = ldf.logdensity_and_gradient(th)
+    olp, og = oracle_of(model).lpgrad(th)
+    # the prior part is evaluated in fp64 by both; bounds are relative to the likelihood part
+    prior_g = -th / model.hyper[0] ** 2
+    glik = og - prior_g
+    np.testing.assert_allclose(lp, olp, rtol=3e-7, atol=1e-6)
+    err = np.linalg.norm(g - og, axis=1)
+    assert np.all(err <= 1e-4 * np.linalg.norm(glik, axis=1) + 1e-6), err.max()
+    # value-only entry and single-point form agree with the batched one
+    np.testing.assert_array_equal(ldf.logdensity(th), lp)
+    l1, g1 = ldf.logdensity_and_gradient(th[0])
+    np.testing.assert_allclose(l1, lp[0], rtol=3e-7)
+
+
+def test_tc_energy_differences_are_tight(built):
+    """what the sampler consumes are lp DIFFERENCES along a trajectory"""
+    N, D = 20000, 100
+    model = T.models.synthetic_logistic(N, D, seed=3)
+    ldf = T.LogDensityFunction(model, options=TC)
+    ref = T.LogDensityFunction(model)
+    rng = np.random.default_rng(0)
+    centre = rng.standard_normal(D) * 0.2
+    th = centre + rng.standard_normal((256, D)) * 0.02      # a posterior-width cloud
+    lp = ldf.logdensity(th)
+    rlp = ref.logdensity(th)
+    d = (lp - lp[0]) - (rlp - rlp[0])
+    assert np.max(np.abs(d)) < 1e-3, np.max(np.abs(d))
+
+
+def test_tc_rejects_wide_models(built):
+    model = T.models.synthetic_logistic(257, 130, seed=5)
+    ldf = T.LogDensityFunction(model, options=TC)
+    with pytest.raises(T._lib.TnutsError):
+        ldf.logdensity(np.zeros((2, 130)))
+
+
+def test_tc_sampling_is_deterministic_and_matches_fp64_posterior(built):
+    model = T.models.synthetic_logistic(4000, 24, seed=8)
+    kw = dict(seed=11, verbose=False, diagnostics=True)
+    a = T.sample(model, T.NUTS(0.8), T.MCMCThreads(), 300, 256, engine_options=TC, **kw)
+    b = T.sample(model, T.NUTS(0.8), T.MCMCThreads(), 300, 256, engine_options=TC, **kw)
+    np.testing.assert_array_equal(a.value, b.value)
+    ref = T.sample(model, T.NUTS(0.8), T.MCMCThreads(), 300, 256, **kw)
+    assert np.max(a.info["rhat"]) < 1.01 and np.max(ref.info["rhat"]) < 1.01
+    P = model.D
+    ma, mr = a.value[:, :P].mean(axis=(0, 2)), ref.value[:, :P].mean(axis=(0, 2))
+    sd = ref.value[:, :P].std(axis=(0, 2))
+    mcse = sd / np.sqrt(np.minimum(a.info["ess_bulk"], ref.info["ess_bulk"]))
+    assert np.all(np.abs(ma - mr) < 4 * np.sqrt(2) * mcse), np.max(np.abs(ma - mr) / mcse)
+    va, vr = a.value[:, :P].var(axis=(0, 2)), ref.value[:, :P].var(axis=(0, 2))
+    np.testing.assert_allclose(va, vr, rtol=0.05)
+    # same sampler behaviour: step sizes and tree depths of the two arithmetic modes agree closely
+    np.testing.assert_allclose(np.mean(a.info["step_size"]), np.mean(ref.info["step_size"]), rtol=0.02)
+
+
+def test_tc_pump_work_list(built):
+    """chains finish at different pumps: the tcgen05 kernel reads the compacted work list"""
+    model = T.models.synthetic_logistic(700, 10, seed=2)
+    eng = T.Engine(model, T.NUTS(20, 0.8), 200, 20, seed=3)
+    eng.set_option("logistic_tc", 1)
+    eng.set_option("keep_theta", 1)
+    eng.init()
+    eng.run(40, 1, 1)
+    out = eng.fetch(theta=True)
+    ref = T.Engine(model, T.NUTS(20, 0.8), 200, 20, seed=3)
+    ref.set_option("keep_theta", 1)
+    ref.init()
+    ref.run(40, 1, 1)
+    rout = ref.fetch(theta=True)
+    # identical seeds and nearly identical arithmetic: the first transitions build the same trees
+    st, rst = out["stats"], rout["stats"]
+    same = np.mean(st[:3, 0] == rst[:3, 0])
+    assert same > 0.95, same
+    np.testing.assert_allclose(out["theta"][:2], rout["theta"][:2], atol=1e-3)
+    eng.close()
+    ref.close()

@@ -493,6 +493,7 @@ int tnuts_set_option(tnuts_engine *h, const char *name, double value) {
   else if (n == "sort_chains") e->sort_chains = value != 0.0;
   else if (n == "flat") e->flat = value != 0.0;
   else if (n == "flat_batch") e->rp.flat_batch = (int)value;
+  else if (n == "logistic_tc") e->logistic_tc = value != 0.0;
 
   else return set_error(e, TNUTS_E_ARG, "tnuts_set_option: unknown option " + n);
   return TNUTS_OK;

@@ -54,6 +54,9 @@ struct Engine {
   long long host_iter = 0;  // transitions done since init (identical for every chain)
   bool flat = false;  // flat-scheduled thread-per-chain kernel (chain_flat.cuh)
   int occupancy = 2;  // CTAs of 128 threads per SM the thread-per-chain kernel is compiled for
+  // logistic regression: likelihood gradient on the tcgen05 tensor cores (bf16x3 planes, fp32-grade
+  // dot products, logistic_tc.cuh) instead of the fp64 DMMA kernel; opt-in, D <= 128
+  bool logistic_tc = false;
 
   LockstepState *ls = nullptr;
   DiagWork *diag = nullptr;

@@ -6,11 +6,13 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
 #include "engine.cuh"
 #include "lockstep_kernels.cuh"
+#include "logistic_tc.cuh"
 #include "lpgrad_kernels.cuh"
 
 #ifdef TNUTS_WITH_NCCL
@@ -99,6 +101,8 @@ static int logistic_plan(const ModelDev &m, int cap, LogiPlan *p) {
   return 0;
 }
 
+static tc::Data *tc_data_of(Engine *e);
+
 static int grad_launch(Engine *e, const double *th, int C, double *lp, double *g, const int *list,
                        const int *count, int n_all, int n_max, GradWork *gw) {
   const ModelDev &m = e->model;
@@ -120,7 +124,21 @@ static int grad_launch(Engine *e, const double *th, int C, double *lp, double *g
       LogiPlan lp_;
       if (logistic_plan(m, gw->cap, &lp_)) return set_error(e, TNUTS_E_UNSUPPORTED, "logistic regression: D > 256 not supported");
       const int stride = gw->stride;
-      const int D = m.D, chunks = lp_.chunks;
+      const int D = m.D;
+      int chunks = lp_.chunks;
+      if (e->logistic_tc) {
+        // tcgen05 path: same partial-sum layout, its own (fixed) row cut
+        tc::Data *td = tc_data_of(e);
+        if (!td->ready) {
+          const char *msg = tc::prepare(m.X, m.y, m.N, D, e->stream, td);
+          if (msg) return set_error(e, TNUTS_E_UNSUPPORTED, msg);
+          e->launches += 2;
+        }
+        chunks = td->pl.chunks;
+        if ((size_t)chunks * stride * ((size_t)D + 1) > gw->part_elems)
+          return set_error(e, TNUTS_E_UNSUPPORTED, "logistic_tc: partial buffer too small");
+        TN_CUDA(e, tc::launch(*td, m.N, D, th, C, list, count, n_all, n_max, gw->part, stride, e->stream));
+      } else {
       const dim3 grid((n_max + lp_.tch - 1) / lp_.tch, (chunks + lp_.ng - 1) / lp_.ng);
 #define TN_LOGI(NWN, NWM, MT, TR, NG)                                                                 \
   do {                                                                                                \
@@ -146,6 +164,7 @@ static int grad_launch(Engine *e, const double *th, int C, double *lp, double *g
       else if (lp_.mt == 13) TN_LOGI(8, 1, 13, 64, 1);
       else TN_LOGI(8, 1, 16, 64, 1);
 #undef TN_LOGI
+      }
       const dim3 rg((n_max + 127) / 128, D + 1);
       k_logistic_reduce<<<rg, 128, 0, e->stream>>>(gw->part, chunks, D, stride, count, n_all, gw->lik, gw->cap);
       if (e->world > 1 && e->cfg.row_shards > 1) {
@@ -171,7 +190,10 @@ static int gradwork_alloc(Engine *e, GradWork *gw, int cap, std::vector<void *> 
   gw->chunks = lp_.chunks;
   gw->rows_per_chunk = lp_.rpc;
   gw->stride = ((cap + lp_.tch - 1) / lp_.tch) * lp_.tch;
-  gw->part_elems = (size_t)lp_.chunks * gw->stride * ((size_t)e->model.D + 1);
+  int max_chunks = lp_.chunks;
+  tc::Plan tp;
+  if (tc::plan(e->model.N, e->model.D, &tp) && tp.chunks > max_chunks) max_chunks = tp.chunks;
+  gw->part_elems = (size_t)max_chunks * gw->stride * ((size_t)e->model.D + 1);
   const size_t D1 = (size_t)e->model.D + 1;
   void *p = nullptr;
   TN_CUDA(e, cudaMalloc(&p, 8 * gw->part_elems));
@@ -187,9 +209,11 @@ static int gradwork_alloc(Engine *e, GradWork *gw, int cap, std::vector<void *> 
 struct LockstepExt {
   LockstepState ls;  // first member: Engine::ls points here
   GradWork gw;
+  tc::Data tcd;      // logistic regression on tcgen05 (option "logistic_tc"), built on first use
   std::vector<void *> allocs;
 };
 static LockstepExt *ext_of(Engine *e) { return reinterpret_cast<LockstepExt *>(e->ls); }
+static tc::Data *tc_data_of(Engine *e) { return &ext_of(e)->tcd; }
 
 // ------------------------------------------------------------------------------------------
 int lockstep_create(Engine *e) {
@@ -266,6 +290,7 @@ void lockstep_destroy(Engine *e) {
   if (!e->ls) return;
   LockstepExt *x = ext_of(e);
   for (void *p : x->allocs) cudaFree(p);
+  tc::release(&x->tcd);
   if (x->ls.h_count) cudaFreeHost(x->ls.h_count);
   delete x;
   e->ls = nullptr;
@@ -569,7 +594,11 @@ int lockstep_run(Engine *e) {
   // fixed pump numbers instead of polling the (timing-dependent) mirror.
   const bool lockstep_ranks = e->world > 1 && e->cfg.row_shards > 1;
   int done = 0;
+  static const bool trace = getenv("TNUTS_PUMP_TRACE") != nullptr;
+  long long pumps_done = 0;
   for (long long pump = 0; pump < max_pumps; ++pump) {
+    pumps_done = pump;
+    if (trace && pump % 4096 == 0) fprintf(stderr, "[tnuts pump] %lld done=%d listed=%d\n", pump, (int)*h_done, n_max);
     if (!lockstep_ranks) {
       done = *h_done;
     } else if (pump % 16 == 0 && pump > 0) {
@@ -597,6 +626,7 @@ int lockstep_run(Engine *e) {
   }
   cudaEventDestroy(ev[0]);
   cudaEventDestroy(ev[1]);
+  if (trace) fprintf(stderr, "[tnuts pump] finished after %lld pumps\n", pumps_done);
   if (rc) return rc;
   TN_CUDA(e, cudaGetLastError());
   return TNUTS_OK;

@@ -72,8 +72,12 @@ def _resolve_initial_params(model, initial_params, n_chains):
 def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_params=None,
            initial_state=None, nadapts=None, discard_adapt=True, discard_initial=-1, thinning=1,
            save_state=False, progress=False, verbose=True, check_model=True, devices=None,
-           diagnostics=False, strategy=0, keep_engine=False, chain_offset=0, chunk_draws=None):
-    """sample(model, spl, N) | sample(model, spl, ensemble, N, n_chains)."""
+           diagnostics=False, strategy=0, keep_engine=False, chain_offset=0, chunk_draws=None,
+           engine_options=None):
+    """sample(model, spl, N) | sample(model, spl, ensemble, N, n_chains).
+
+    engine_options: {name: value} passed to tnuts_set_option before init, e.g.
+    {"logistic_tc": 1} (tcgen05 likelihood for logistic regression, include/tnuts.h)."""
     if len(args) == 1:
         N, n_chains, single = int(args[0]), 1, True
         if initial_params is not None and not isinstance(initial_params, (list, tuple)):
@@ -123,6 +127,8 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
     for i, dev in enumerate(devices):
         engines.append(Engine(model, spl, bounds[i + 1] - bounds[i], _nadapts, seed64, device=dev,
                               chain_offset=chain_offset + bounds[i], strategy=strategy))
+        for k, v in (engine_options or {}).items():
+            engines[-1].set_option(k, v)
     tm["create"] = time.perf_counter() - t_start
     results = [None] * ndev
     errors = [None] * ndev
@@ -245,10 +251,12 @@ class LogDensityFunction:
     `DynamicPPL.LogDensityFunction(model, getlogjoint_internal, LinkAll())`
     (src/mcmc/hmc.jl:170-182)."""
 
-    def __init__(self, model, device=0, strategy=0):
+    def __init__(self, model, device=0, strategy=0, options=None):
         from .samplers import NUTS
         self.model = model
         self._e = Engine(model, NUTS(), 1, 0, 0, device=device, strategy=strategy)
+        for k, v in (options or {}).items():
+            self._e.set_option(k, v)
 
     def dimension(self):
         return self._e.D
