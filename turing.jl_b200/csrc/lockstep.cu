@@ -134,7 +134,8 @@ static int grad_launch(Engine *e, const double *th, int C, double *lp, double *g
           if (msg) return set_error(e, TNUTS_E_UNSUPPORTED, msg);
           e->launches += 2;
         }
-        chunks = td->pl.chunks;
+        int rpc_;
+        tc::cut_for(m.N, (n_max + tc::kChainsPerCta - 1) / tc::kChainsPerCta, &chunks, &rpc_);
         if ((size_t)chunks * stride * ((size_t)D + 1) > gw->part_elems)
           return set_error(e, TNUTS_E_UNSUPPORTED, "logistic_tc: partial buffer too small");
         TN_CUDA(e, tc::launch(*td, m.N, D, th, C, list, count, n_all, n_max, gw->part, stride, e->stream));
@@ -165,15 +166,20 @@ static int grad_launch(Engine *e, const double *th, int C, double *lp, double *g
       else TN_LOGI(8, 1, 16, 64, 1);
 #undef TN_LOGI
       }
-      const dim3 rg((n_max + 127) / 128, D + 1);
-      k_logistic_reduce<<<rg, 128, 0, e->stream>>>(gw->part, chunks, D, stride, count, n_all, gw->lik, gw->cap);
       if (e->world > 1 && e->cfg.row_shards > 1) {
+        const dim3 rg((n_max + 127) / 128, D + 1);
+        k_logistic_reduce<<<rg, 128, 0, e->stream>>>(gw->part, chunks, D, stride, count, n_all, gw->lik, gw->cap);
         int rc = comm_allreduce_sum(e, gw->lik, (size_t)(D + 1) * gw->cap);
         if (rc) return rc;
+        k_logistic_finish<<<(n_max + 127) / 128, 128, 0, e->stream>>>(m, gw->lik, gw->cap, th, C, list,
+                                                                     count, n_all, 1.0, lp, g);
+        e->launches += 3;
+      } else {
+        const dim3 rg((n_max + 31) / 32, (D + 1 + 7) / 8);
+        k_logistic_reduce_finish<<<rg, 256, 0, e->stream>>>(m, gw->part, chunks, stride, th, C, list, count, n_all,
+                                                            lp, g);
+        e->launches += 2;
       }
-      k_logistic_finish<<<(n_max + 127) / 128, 128, 0, e->stream>>>(m, gw->lik, gw->cap, th, C, list,
-                                                                   count, n_all, 1.0, lp, g);
-      e->launches += 3;
     } break;
     default:
       return set_error(e, TNUTS_E_UNSUPPORTED, "lock-step: unknown family");
@@ -192,7 +198,11 @@ static int gradwork_alloc(Engine *e, GradWork *gw, int cap, std::vector<void *> 
   gw->stride = ((cap + lp_.tch - 1) / lp_.tch) * lp_.tch;
   int max_chunks = lp_.chunks;
   tc::Plan tp;
-  if (tc::plan(e->model.N, e->model.D, &tp) && tp.chunks > max_chunks) max_chunks = tp.chunks;
+  if (tc::plan(e->model.N, e->model.D, &tp)) {
+    int c1, r1;
+    tc::cut_for(e->model.N, 1, &c1, &r1);  // the finest cut
+    if (c1 > max_chunks) max_chunks = c1;
+  }
   gw->part_elems = (size_t)max_chunks * gw->stride * ((size_t)e->model.D + 1);
   const size_t D1 = (size_t)e->model.D + 1;
   void *p = nullptr;
@@ -585,6 +595,8 @@ int lockstep_run(Engine *e) {
   cudaEvent_t ev[2];
   TN_CUDA(e, cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
   TN_CUDA(e, cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  cudaEvent_t ev_cnt;
+  TN_CUDA(e, cudaEventCreateWithFlags(&ev_cnt, cudaEventDisableTiming));
   const long long max_pumps = rp.n_transitions * ((1LL << rp.max_depth) + 2 + (rp.algorithm != TNUTS_ALG_NUTS ? 100000 : 0)) + 64;
   int listed_done = -1, n_max = C;
   rc = TNUTS_OK;
@@ -592,7 +604,10 @@ int lockstep_run(Engine *e) {
   // exactly the same launch sequence.  The chains are bit-identical on every rank, hence so is
   // the finished-chain counter after a given pump: read it with a stream synchronisation at
   // fixed pump numbers instead of polling the (timing-dependent) mirror.
-  const bool lockstep_ranks = e->world > 1 && e->cfg.row_shards > 1;
+  // The tcgen05 logistic kernel cuts the rows by the number of listed chains, so that number has
+  // to be a deterministic function of the pump index as well.
+  const bool lockstep_ranks = (e->world > 1 && e->cfg.row_shards > 1) ||
+                              (e->logistic_tc && e->model.family == TNUTS_LOGISTIC);
   int done = 0;
   static const bool trace = getenv("TNUTS_PUMP_TRACE") != nullptr;
   long long pumps_done = 0;
@@ -602,7 +617,19 @@ int lockstep_run(Engine *e) {
     if (!lockstep_ranks) {
       done = *h_done;
     } else if (pump % 16 == 0 && pump > 0) {
-      if ((rc = read_count(e, ls->count + 1, ls->h_count + 1))) break;
+      // snapshot of the counter as of this pump, consumed 8 pumps later: deterministic, and the
+      // stream never drains
+      if (cudaMemcpyAsync(ls->h_count + 1, ls->count + 1, sizeof(int), cudaMemcpyDeviceToHost, e->stream) !=
+              cudaSuccess ||
+          cudaEventRecord(ev_cnt, e->stream) != cudaSuccess) {
+        rc = set_error(e, TNUTS_E_CUDA, "pump: counter snapshot failed");
+        break;
+      }
+    } else if (pump % 16 == 8 && pump > 16) {
+      if (cudaEventSynchronize(ev_cnt) != cudaSuccess) {
+        rc = set_error(e, TNUTS_E_CUDA, "pump: counter snapshot failed");
+        break;
+      }
       done = ls->h_count[1];
     }
     if (done >= C) break;
@@ -626,6 +653,7 @@ int lockstep_run(Engine *e) {
   }
   cudaEventDestroy(ev[0]);
   cudaEventDestroy(ev[1]);
+  cudaEventDestroy(ev_cnt);
   if (trace) fprintf(stderr, "[tnuts pump] finished after %lld pumps\n", pumps_done);
   if (rc) return rc;
   TN_CUDA(e, cudaGetLastError());

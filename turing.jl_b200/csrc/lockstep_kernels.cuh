@@ -209,6 +209,8 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
                               *__restrict__ const grad_ = st.grad;
   const bool in = t.c < C && st.status[t.c] == 0;
   int phase = in ? s.phase[t.c] : 2;
+  // a CTA whose 8 chains have all finished has nothing to do (the tail of a run is mostly such CTAs)
+  if (__syncthreads_and(phase == 2)) return;
   const uint32_t gchain = (uint32_t)(rp.chain_offset + t.c);
   // chain scalars (registers, redundantly in the chain's 32 threads)
   double eps = 0, H0 = 0, lw = 0, lw_s = 0, sum_a = 0, dHmax = 0, lpC = 0, HC = 0, lpS = 0, HS = 0,

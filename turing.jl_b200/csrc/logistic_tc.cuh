@@ -198,6 +198,7 @@ __global__ void k_tc_convert_y(const double *__restrict__ y, long long nrows, lo
 // the kernel
 // ------------------------------------------------------------------------------------------
 constexpr int kT = 64;          // rows per tile
+constexpr int kG2Planes = 2;    // bf16 planes of R and X used by GEMM2 (2: three products, 3: six)
 constexpr int kEpiWarps = 16;   // 4 lane quarters x 4 column groups of 16 rows
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 
@@ -230,7 +231,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
   constexpr uint32_t STAGE_BYTES = 3 * PLANE_BYTES;
   constexpr uint32_t TH_PLANE = KP / 2;             // TMEM columns of one Theta plane
   constexpr uint32_t COL_TH = 0, COL_G = 3 * TH_PLANE, COL_BUF = COL_G + KP;
-  constexpr uint32_t BUF_COLS = 3 * T / 2;          // eta (T cols), then R planes (3 x T/2 cols)
+  constexpr uint32_t BUF_COLS = (kG2Planes * T / 2 > T) ? kG2Planes * T / 2 : T;  // eta (T cols), then R planes
   static_assert(COL_BUF + 2 * BUF_COLS <= kTmemCols, "TMEM budget");
   constexpr int NEPI = 32 * kEpiWarps;
 
@@ -346,15 +347,22 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
       const uint32_t r_col = tmem + COL_BUF + (uint32_t)(t & 1) * BUF_COLS;
       const uint32_t xs = (stage0 + (uint32_t)s * STAGE_BYTES) >> 4;
       if (elect_one()) {
+        // the gradient only steers the leapfrog map: with kG2Planes == 2 it keeps the products
+        // down to 2^-16 (R_m*X_h, R_h*X_m, R_h*X_h), comparable to its fp32 accumulation error
+        constexpr int NQ2 = kG2Planes == 3 ? 6 : 3;
+        constexpr int PA2[6] = {2, 1, 0, 1, 0, 0}, PB2[6] = {0, 1, 2, 0, 1, 0};
+        constexpr int PA3[3] = {1, 0, 0}, PB3[3] = {0, 1, 0};
+        const int q20 = (xmode & 2) ? NQ2 - 1 : 0;
 #pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          if (q < q0) continue;
-          const uint32_t a_col = r_col + PA[q] * (T / 2);
-          const uint32_t b_lo = (xs + PB[q] * (PLANE_BYTES >> 4)) | LBO_MN;
+        for (int q = 0; q < NQ2; ++q) {
+          if (q < q20) continue;
+          const int pa = kG2Planes == 3 ? PA2[q] : PA3[q], pb = kG2Planes == 3 ? PB2[q] : PB3[q];
+          const uint32_t a_col = r_col + pa * (T / 2);
+          const uint32_t b_lo = (xs + pb * (PLANE_BYTES >> 4)) | LBO_MN;
 #pragma unroll
           for (int rs = 0; rs < T / 16; ++rs)
             mma_bf16_ts(tmem + COL_G, a_col + (uint32_t)rs * 8u, ((uint64_t)DESC_HI << 32) | (b_lo + (uint32_t)rs * 128u),
-                        idesc2, (t > 0 || q > q0 || rs > 0) ? 1u : 0u);
+                        idesc2, (t > 0 || q > q20 || rs > 0) ? 1u : 0u);
         }
         tc_commit(bar_empty(s));
       }
@@ -457,10 +465,17 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
       asm volatile("bar.sync %0, %1;" ::"r"(1 + wq), "r"(32 * (kEpiWarps / 4)) : "memory");
       uint32_t ph[8], pm[8], pl[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) split3(rr[2 * j], rr[2 * j + 1], ph[j], pm[j], pl[j]);
+      for (int j = 0; j < 8; ++j) {
+        if (kG2Planes == 3) {
+          split3(rr[2 * j], rr[2 * j + 1], ph[j], pm[j], pl[j]);
+        } else {
+          ph[j] = pack_bf16(rr[2 * j], rr[2 * j + 1]);
+          pm[j] = pack_bf16(rr[2 * j] - bf16_lo(ph[j]), rr[2 * j + 1] - bf16_hi(ph[j]));
+        }
+      }
       tmem_st8(buf + 0 * (T / 2) + 8 * cg, ph);
       tmem_st8(buf + 1 * (T / 2) + 8 * cg, pm);
-      tmem_st8(buf + 2 * (T / 2) + 8 * cg, pl);
+      if (kG2Planes == 3) tmem_st8(buf + 2 * (T / 2) + 8 * cg, pl);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(bar_r(b));
@@ -523,6 +538,20 @@ inline bool plan(long long nrows, int D, Plan *p) {
   return true;
 }
 
+// Row cut for a launch over n_tiles chain tiles: with few chains left the rows are cut finer so
+// that the grid still fills the 148 SMs.  A function of (N, n_tiles) only.  The summation order of
+// a chain's gradient therefore depends on how many chains run beside it: in this mode a run is
+// reproducible for a fixed (seed, chain count, sharding), not across different chain counts
+// (the fp64 path keeps that stronger property).
+inline void cut_for(long long nrows, int n_tiles, int *chunks, int *rpc) {
+  const long long tiles = (nrows + kT - 1) / kT;
+  long long want = n_tiles >= 4 ? 37 : n_tiles >= 2 ? 74 : 148;
+  if (want > tiles) want = tiles;
+  const long long tpc = (tiles + want - 1) / want;
+  *rpc = (int)(tpc * kT);
+  *chunks = (int)((nrows + *rpc - 1) / *rpc);
+}
+
 struct Data {
   __nv_bfloat16 *xb = nullptr;
   float *yf = nullptr;
@@ -577,15 +606,19 @@ inline void release(Data *d) {
 // partial sums part[chunk][D+1][cap] for the n_max (upper bound) chains of the work list
 inline cudaError_t launch(const Data &d, long long nrows, int D, const double *th, int C, const int *list,
                           const int *count, int n_all, int n_max, double *part, int cap, cudaStream_t stream,
-                          float *dbg = nullptr, int xmode = 0) {
+                          float *dbg = nullptr, int xmode = 0, int *chunks_out = nullptr) {
   const Plan &p = d.pl;
-  const dim3 grid((n_max + kChainsPerCta - 1) / kChainsPerCta, p.chunks);
+  const int n_tiles = (n_max + kChainsPerCta - 1) / kChainsPerCta;
+  int chunks, rpc;
+  cut_for(nrows, n_tiles, &chunks, &rpc);
+  if (chunks_out) *chunks_out = chunks;
+  const dim3 grid(n_tiles, chunks);
 #define TN_TC_LAUNCH(KP_)                                                                                 \
   do {                                                                                                    \
     auto kfn = k_logistic_tc<KP_>;                                                                        \
     cudaError_t s_ = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem); \
     if (s_ != cudaSuccess) return s_;                                                                     \
-    kfn<<<grid, kThreads, p.smem, stream>>>(d.map, d.yf, nrows, D, th, C, list, count, n_all, p.rpc,      \
+    kfn<<<grid, kThreads, p.smem, stream>>>(d.map, d.yf, nrows, D, th, C, list, count, n_all, rpc,        \
                                             part, cap, dbg, xmode);                                       \
   } while (0)
   if (p.kp == 128) TN_TC_LAUNCH(128);

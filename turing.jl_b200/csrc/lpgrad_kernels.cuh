@@ -382,6 +382,47 @@ __global__ void k_logistic_finish(ModelDev m, const double *lik, int cap, const 
   lp_out[c] = lik[(size_t)D * cap + k] + prior_scale * (-0.5 * D * kLog2Pi - D * log(sd) - 0.5 * q * is2);
 }
 
+// k_logistic_reduce + k_logistic_finish in one launch (single-GPU rows): block = 32 work-list
+// slots x 8 rows of the (D+1)-row partial block, one row per thread.  The sum over the row chunks
+// runs in the same fixed order (chunk 0, 1, ...), so the result is bit-identical to the
+// two-kernel path; the thread that owns the lp row also evaluates the prior.
+__global__ void __launch_bounds__(256)
+k_logistic_reduce_finish(ModelDev m, const double *__restrict__ part, int chunks, int stride,
+                         const double *__restrict__ th, int C, const int *__restrict__ list,
+                         const int *__restrict__ count, int n_all, double *__restrict__ lp_out,
+                         double *__restrict__ g) {
+  const int n = count ? *count : n_all;
+  const int k = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int d = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int D = m.D;
+  if (k >= n || d > D) return;
+  const int c = list ? list[k] : k;
+  const size_t cs = (size_t)(D + 1) * stride;
+  const double *p = part + (size_t)d * stride + k;
+  double s = 0.0;
+  int ch = 0;
+  for (; ch + 4 <= chunks; ch += 4) {  // four loads in flight, summed in chunk order
+    const double a0 = p[(size_t)ch * cs], a1 = p[(size_t)(ch + 1) * cs], a2 = p[(size_t)(ch + 2) * cs],
+                 a3 = p[(size_t)(ch + 3) * cs];
+    s += a0;
+    s += a1;
+    s += a2;
+    s += a3;
+  }
+  for (; ch < chunks; ++ch) s += p[(size_t)ch * cs];
+  const double sd = m.hyper[0], is2 = 1.0 / (sd * sd);
+  if (d < D) {
+    g[(size_t)d * C + c] = s - th[(size_t)d * C + c] * is2;
+  } else {
+    double q = 0.0;
+    for (int j = 0; j < D; ++j) {
+      const double t = th[(size_t)j * C + c];
+      q += t * t;
+    }
+    lp_out[c] = s + (-0.5 * D * kLog2Pi - D * log(sd) - 0.5 * q * is2);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // hierarchical linear regression from centred per-group sufficient statistics:
 //   n_g, xbar_g, ybar_g, Sxx_g = sum (x - xbar)^2, Sxy_g, Syy_g
