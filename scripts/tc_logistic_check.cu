@@ -62,7 +62,10 @@ static int run_case(long long N, int D, int C, int ncheck, bool timing, bool use
   const tc::Plan &p = data.pl;
   printf("plan: KP=%d T=%d chunks=%d rows/chunk=%d smem=%zu\n", p.kp, p.t, p.chunks, p.rpc, p.smem);
   const int cap = ((C + 127) / 128) * 128;
-  const size_t part_elems = (size_t)p.chunks * (D + 1) * cap;
+  int chunks = 0, rpc = 0;
+  tc::cut_for(N, cap / 128, &chunks, &rpc);   // the cut the launch below will use
+  printf("cut for %d chain tiles: chunks=%d rows/chunk=%d\n", cap / 128, chunks, rpc);
+  const size_t part_elems = (size_t)chunks * (D + 1) * cap;
   CK(cudaMalloc(&dpart, 8 * part_elems));
   CK(cudaMemset(dpart, 0xff, 8 * part_elems));
   float *ddbg;
@@ -126,7 +129,7 @@ static int run_case(long long N, int D, int C, int ncheck, bool timing, bool use
     }
     double lp_gpu = 0;
     std::vector<double> g_gpu(D, 0.0);
-    for (int ch = 0; ch < p.chunks; ++ch) {
+    for (int ch = 0; ch < chunks; ++ch) {
       lp_gpu += part[((size_t)ch * (D + 1) + D) * cap + k];
       for (int d = 0; d < D; ++d) g_gpu[d] += part[((size_t)ch * (D + 1) + d) * cap + k];
     }
@@ -151,7 +154,7 @@ static int run_case(long long N, int D, int C, int ncheck, bool timing, bool use
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    const int nx = getenv("TC_XMODES") ? 4 : 1;
+    const int nx = getenv("TC_XMODES") ? 8 : 1;
     for (int xm = 0; xm < nx; ++xm) {
       for (int i = 0; i < 3; ++i) CK(tc::launch(data, N, D, dth, C, nullptr, nullptr, C, C, dpart, cap, 0, nullptr, xm));
       CK(cudaEventRecord(e0));

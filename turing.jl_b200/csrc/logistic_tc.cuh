@@ -232,11 +232,14 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
   constexpr uint32_t TH_PLANE = KP / 2;             // TMEM columns of one Theta plane
   constexpr uint32_t COL_TH = 0, COL_G = 3 * TH_PLANE, COL_BUF = COL_G + KP;
   constexpr uint32_t BUF_COLS = (kG2Planes * T / 2 > T) ? kG2Planes * T / 2 : T;  // eta (T cols), then R planes
-  static_assert(COL_BUF + 2 * BUF_COLS <= kTmemCols, "TMEM budget");
+  // three eta/R buffers: GEMM1 runs two tiles ahead, so neither GEMM1(t+2) nor the epilogue of
+  // tile t+1 ever waits for the epilogue of tile t
+  constexpr int NBUF = kG2Planes == 2 ? 3 : 2;
+  static_assert(COL_BUF + NBUF * BUF_COLS <= kTmemCols, "TMEM budget");
   constexpr int NEPI = 32 * kEpiWarps;
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * kStages + 6];
+  __shared__ __align__(8) uint64_t bars[2 * kStages + 2 * 3 + 2];
   __shared__ uint32_t tmem_slot;
   __shared__ double lp_part[kEpiWarps / 4][kChainsPerCta];
 
@@ -256,9 +259,9 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_empty = [&](int s) { return bar0 + 8u * (kStages + s); };
   auto bar_eta = [&](int b) { return bar0 + 8u * (2 * kStages + b); };
-  auto bar_r = [&](int b) { return bar0 + 8u * (2 * kStages + 2 + b); };
-  const uint32_t bar_theta = bar0 + 8u * (2 * kStages + 4);
-  const uint32_t bar_g = bar0 + 8u * (2 * kStages + 5);
+  auto bar_r = [&](int b) { return bar0 + 8u * (2 * kStages + 3 + b); };
+  const uint32_t bar_theta = bar0 + 8u * (2 * kStages + 6);
+  const uint32_t bar_g = bar0 + 8u * (2 * kStages + 7);
 
   if (warp == 0 && elect_one()) tma_prefetch_desc(&mapX);
   if (warp == 1) {
@@ -267,9 +270,9 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
         mbar_init(bar_full(s), 1);
         mbar_init(bar_empty(s), 1);
       }
-      for (int b = 0; b < 2; ++b) {
+      for (int b = 0; b < NBUF; ++b) {
         mbar_init(bar_eta(b), 1);
-        mbar_init(bar_r(b), NEPI);
+        mbar_init(bar_r(b), NEPI / 2);
       }
       mbar_init(bar_theta, NEPI);
       mbar_init(bar_g, 1);
@@ -293,14 +296,15 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
       const uint32_t ph = (uint32_t)(t / kStages) & 1u;
       mbar_wait(bar_empty(s), ph ^ 1u);
       if (elect_one()) {
-        mbar_expect_tx(bar_full(s), STAGE_BYTES);
+        const int npl = (xmode & 4) ? 1 : 3;   // experiment: one plane only (timing of the X stream)
+        mbar_expect_tx(bar_full(s), npl * PLANE_BYTES);
         const uint32_t dst = stage0 + (uint32_t)s * STAGE_BYTES;
         const int row0 = (int)(rbeg + (long long)t * T);
 #pragma unroll
         for (int pl = 0; pl < 3; ++pl)
 #pragma unroll
           for (int kb = 0; kb < NKB; ++kb)
-            tma_load_3d(dst + pl * PLANE_BYTES + kb * BOX_BYTES, &mapX, bar_full(s), kb * 64, row0, pl);
+            if (pl < npl) tma_load_3d(dst + pl * PLANE_BYTES + kb * BOX_BYTES, &mapX, bar_full(s), kb * 64, row0, pl);
       }
       __syncwarp();
     }
@@ -319,7 +323,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
       const int s = t % kStages;
       mbar_wait(bar_full(s), (uint32_t)(t / kStages) & 1u);
       tc_fence_after();
-      const uint32_t d_col = tmem + COL_BUF + (uint32_t)(t & 1) * BUF_COLS;
+      const uint32_t d_col = tmem + COL_BUF + (uint32_t)(t % NBUF) * BUF_COLS;
       const uint32_t xs = (stage0 + (uint32_t)s * STAGE_BYTES) >> 4;
       if (elect_one()) {
 #pragma unroll
@@ -336,15 +340,15 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
             }
           }
         }
-        tc_commit(bar_eta(t & 1));
+        tc_commit(bar_eta(t % NBUF));
       }
       __syncwarp();
     };
     auto gemm2 = [&](int t) {
       const int s = t % kStages;
-      mbar_wait(bar_r(t & 1), (uint32_t)(t >> 1) & 1u);
+      mbar_wait(bar_r(t % NBUF), (uint32_t)(t / NBUF) & 1u);
       tc_fence_after();
-      const uint32_t r_col = tmem + COL_BUF + (uint32_t)(t & 1) * BUF_COLS;
+      const uint32_t r_col = tmem + COL_BUF + (uint32_t)(t % NBUF) * BUF_COLS;
       const uint32_t xs = (stage0 + (uint32_t)s * STAGE_BYTES) >> 4;
       if (elect_one()) {
         // the gradient only steers the leapfrog map: with kG2Planes == 2 it keeps the products
@@ -370,9 +374,9 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
     };
     mbar_wait(bar_theta, 0);
     tc_fence_after();
-    gemm1(0);
+    for (int t = 0; t < NBUF - 1 && t < ntile; ++t) gemm1(t);
     for (int t = 0; t < ntile; ++t) {
-      if (t + 1 < ntile) gemm1(t + 1);
+      if (t + NBUF - 1 < ntile) gemm1(t + NBUF - 1);
       gemm2(t);
     }
     if (elect_one()) tc_commit(bar_g);
@@ -407,78 +411,83 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
     tc_fence_before();
     mbar_arrive(bar_theta);
 
+    // Two groups of 8 warps alternate tiles (group = tile parity), each warp takes
+    // 32 of the tile's 64 rows for its 32 chains.  The groups run half a period apart, so while one
+    // sits in TMEM load/store or barrier latency the other one has arithmetic to issue.
+    const int grp = cg & 1, half = cg >> 1;
     double lp = 0.0;
     constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
-    for (int t = 0; t < ntile; ++t) {
-      const int b = t & 1;
-      const long long row0 = rbeg + (long long)t * T + 16 * cg;   // this warp's 16 rows
-      // y of this warp's rows (independent of the MMA: issue the loads before waiting)
-      float ys[16];
-      {
-        const float4 *yp = reinterpret_cast<const float4 *>(yf + row0);
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 y4 = __ldg(yp + j4);
-          ys[4 * j4 + 0] = y4.x;
-          ys[4 * j4 + 1] = y4.y;
-          ys[4 * j4 + 2] = y4.z;
-          ys[4 * j4 + 3] = y4.w;
-        }
-      }
-      mbar_wait(bar_eta(b), (uint32_t)(t >> 1) & 1u);
+    for (int t = grp; t < ntile; t += 2) {
+      const long long row0 = rbeg + (long long)t * T + 32 * half;   // this warp's 32 rows
+      const float4 *yp = reinterpret_cast<const float4 *>(yf + row0);
+      const int bi = t % NBUF;
+      const uint32_t buf = lane_addr + COL_BUF + (uint32_t)bi * BUF_COLS;
+      mbar_wait(bar_eta(bi), (uint32_t)(t / NBUF) & 1u);
       tc_fence_after();
-      const uint32_t buf = lane_addr + COL_BUF + (uint32_t)b * BUF_COLS;
-      uint32_t v[16];
-      tmem_ld16(buf + 16 * cg, v);
+      uint32_t v[32];
+      tmem_ld16(buf + 32 * half, v);
+      tmem_ld16(buf + 32 * half + 16, v + 16);
       tc_wait_ld();
       const bool dump = dbg && blockIdx.x == 0 && blockIdx.y == 0 && t == 0;
       if (dump) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dbg[kl * T + 16 * cg + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) dbg[kl * T + 32 * half + j] = __uint_as_float(v[j]);
       }
-      float rr[16], tsum = 0.f;
-      const int nvalid = (nrows - row0 >= 16) ? 16 : (int)(nrows - row0);  // <= 0: tile rows past the data
+      const int nvalid = (nrows - row0 >= 32) ? 32 : (int)(nrows - row0);  // <= 0: rows past the data
+      uint32_t ph[16], pm[16], pl[16];
+      float tile_sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float eta = __uint_as_float(v[j]);
-        if (xmode & 1) {
-          rr[j] = eta;
-          continue;
-        }
-        const float e = ex2_approx(-fabsf(eta) * kLog2e);      // exp(-|eta|) in (0, 1]
-        const float s = rcp_approx(1.f + e);
-        const float sig = eta >= 0.f ? s : e * s;
-        rr[j] = ys[j] - sig;
-        const float l1 = fmaxf(eta, 0.f) + kLn2 * lg2_approx(1.f + e);
-        const float term = ys[j] * eta - l1;
-        tsum += (j < nvalid) ? term : 0.f;
-        if ((j & 3) == 3) {
-          lp += (double)tsum;
-          tsum = 0.f;
-        }
-      }
-      if (dump) {
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 y4 = __ldg(yp + j4);
+        const float ys[4] = {y4.x, y4.y, y4.z, y4.w};
+        float rr[4], tsum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dbg[128 * T + kl * T + 16 * cg + j] = rr[j];
-      }
-      // all four column groups must have read eta before anybody overwrites it with R planes
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + wq), "r"(32 * (kEpiWarps / 4)) : "memory");
-      uint32_t ph[8], pm[8], pl[8];
+        for (int i = 0; i < 4; ++i) {
+          const int jj = 4 * j4 + i;
+          const float eta = __uint_as_float(v[jj]);
+          if (xmode & 1) {
+            rr[i] = eta;
+            continue;
+          }
+          const float e = ex2_approx(-fabsf(eta) * kLog2e);      // exp(-|eta|) in (0, 1]
+          // 1 / (1 + e) on the FMA pipe (the XU pipe -- ex2, lg2 -- is the busiest unit of the
+          // epilogue): minimax linear start on [1, 2] (error 1/17), three Newton steps
+          const float x1 = 1.f + e;
+          float sg = fmaf(-8.f / 17.f, x1, 24.f / 17.f);
+          sg = sg * fmaf(-x1, sg, 2.f);
+          sg = sg * fmaf(-x1, sg, 2.f);
+          sg = sg * fmaf(-x1, sg, 2.f);
+          const float sig = eta >= 0.f ? sg : e * sg;
+          rr[i] = ys[i] - sig;
+          const float l1 = fmaxf(eta, 0.f) + kLn2 * lg2_approx(x1);
+          const float term = ys[i] * eta - l1;
+          tsum += (jj < nvalid) ? term : 0.f;
+        }
+        tile_sum += tsum;   // 32 terms of size O(1): fp32 is exact enough, fp64 from here on
+        if (dump) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (kG2Planes == 3) {
-          split3(rr[2 * j], rr[2 * j + 1], ph[j], pm[j], pl[j]);
-        } else {
-          ph[j] = pack_bf16(rr[2 * j], rr[2 * j + 1]);
-          pm[j] = pack_bf16(rr[2 * j] - bf16_lo(ph[j]), rr[2 * j + 1] - bf16_hi(ph[j]));
+          for (int i = 0; i < 4; ++i) dbg[128 * T + kl * T + 32 * half + 4 * j4 + i] = rr[i];
+        }
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int o = 2 * j4 + h2;
+          if (kG2Planes == 3) {
+            split3(rr[2 * h2], rr[2 * h2 + 1], ph[o], pm[o], pl[o]);
+          } else {
+            ph[o] = pack_bf16(rr[2 * h2], rr[2 * h2 + 1]);
+            pm[o] = pack_bf16(rr[2 * h2] - bf16_lo(ph[o]), rr[2 * h2 + 1] - bf16_hi(ph[o]));
+          }
         }
       }
-      tmem_st8(buf + 0 * (T / 2) + 8 * cg, ph);
-      tmem_st8(buf + 1 * (T / 2) + 8 * cg, pm);
-      if (kG2Planes == 3) tmem_st8(buf + 2 * (T / 2) + 8 * cg, pl);
+      lp += (double)tile_sum;
+      // both warps of this (lane quarter, group) must have read eta before either overwrites it
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + wq + 4 * grp), "r"(64) : "memory");
+      tmem_st16(buf + 0 * (T / 2) + 16 * half, ph);
+      tmem_st16(buf + 1 * (T / 2) + 16 * half, pm);
+      if (kG2Planes == 3) tmem_st16(buf + 2 * (T / 2) + 16 * half, pl);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(bar_r(b));
+      mbar_arrive(bar_r(bi));
     }
     // G -> partial sums (fp64), chain slot fastest; this warp: features [32 cg, 32 cg + 32)
     lp_part[cg][kl] = lp;
@@ -499,7 +508,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
         }
       }
     }
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + wq), "r"(32 * (kEpiWarps / 4)) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(9 + wq), "r"(32 * (kEpiWarps / 4)) : "memory");
     if (cg == 0 && live) {
       double s = 0.0;
 #pragma unroll
