@@ -58,6 +58,9 @@ def main():
     n_tr = 14
     eng = D.make_row_sharded_engine(model, spl, C, 10, 7, rank, world, local, dist)
     eng.set_option("keep_theta", 1)
+    tc = "--tc" in sys.argv      # tcgen05 likelihood on every rank's row slice
+    if tc:
+        eng.set_option("logistic_tc", 1)
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
@@ -80,13 +83,16 @@ def main():
         if not big:
             single = T.Engine(model, spl, C, 10, 7, device=local, strategy=2)
             single.set_option("keep_theta", 1)
+            if tc:
+                single.set_option("logistic_tc", 1)
             single.init()
             single.run(n_tr, 1, 1)
             o1 = single.fetch(theta=True)
             d = np.abs(o1["theta"][:6] - out["theta"][:6]).max()
             same = (o1["stats"][:, [0, 6], :] == out["stats"][:, [0, 6], :]).mean()
             print("  vs single GPU: max |dtheta| first 6 transitions %.2e, identical tree stats %.3f" % (d, same))
-            ok = ok and d < 1e-8 and same > 0.95
+            # tcgen05 mode: the ranks' fp32 partial sums group differently from the single-GPU cut
+            ok = ok and (d < 1e-2 and same > 0.8 if tc else d < 1e-8 and same > 0.95)
             single.close()
     eng.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
