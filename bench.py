@@ -12,6 +12,10 @@ constrained parameters, log-probs and sampler statistics recorded.
               and the device->host copy of the full (iterations x names x chains) chain array
   min bulk-ESS/s is reported next to both (ess_bulk_min_per_sec).
 
+`--workload logistic [--tc]` runs BASELINE.json configs[2] (logistic regression N=100000, D=100,
+4096 chains) instead of the default configs[1]; one step of it takes about a minute (--tc: the
+tcgen05 bf16x3 likelihood kernel) or eight (fp64 DMMA), so give it `--steps 1 --warmup 1`.
+
 `--impl reference` times the CPU restatement (oracle/, one chain per thread, all host cores):
 the reference itself is Julia and cannot run in this image.
 """
@@ -98,6 +102,8 @@ def build_workload(name, n_chains):
         return T.EightSchools(), T.NUTS(0.8), 1000, n_chains or 65536
     if name == "linreg":
         return T.models.config1_linear_regression(), T.NUTS(), 1000, n_chains or 4
+    if name == "logistic":
+        return T.models.config3_logistic(), T.NUTS(0.8), 1000, n_chains or 4096
     raise SystemExit("unknown workload " + name)
 
 
@@ -107,8 +113,26 @@ def oracle_model(model):
                          sigma=model.sigma, group=model.group, hyper=model.hyper)
 
 
+def cpu_baseline_logistic(model, budget_s=15.0):
+    """config 3 on the host cores: the full job would take hours, so the bounded sample is a few
+    NUTS transitions per core from the posterior mode (scripts/run_config.py has the details)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("run_config", os.path.join(ROOT, "scripts", "run_config.py"))
+    rc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rc)
+    eps_unit = 0.384 * 2.0 / np.sqrt(model.N)   # adapted step size x posterior sd (unit metric)
+    t = time.perf_counter()
+    out = rc.cpu_baseline_logistic(model, eps_unit, 0.0, budget_s)
+    out["seconds"] = time.perf_counter() - t
+    out.pop("ess_bulk_min_per_sec_extrapolated", None)
+    out["ess_bulk_min_per_sec"] = None
+    return out
+
+
 def cpu_baseline(model, spl, N, budget_s=15.0):
     """oracle (CPU restatement), one chain per thread on all host cores, bounded sample"""
+    if model.family == 3 and model.N * model.D > 1_000_000:
+        return cpu_baseline_logistic(model, budget_s)
     import oracle as O
     from oracle import diagnostics as dg
     cores = os.cpu_count() or 1
@@ -151,6 +175,9 @@ def run_reference(args):
             vals.append(last)
     v = float(np.mean([x["value"] for x in vals]))
     ms = float(np.mean([x["seconds"] for x in vals])) * 1e3
+    for x in vals:
+        if x.get("ess_bulk_min_per_sec") is None:
+            x["ess_bulk_min_per_sec"] = float("nan")
     line = {
         "impl": "reference", "metric": "grad_evals_per_sec", "value": v, "unit": "grad_evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -174,6 +201,12 @@ def workload_config(name, C, N):
                 "chains_per_gpu": C, "draws": N, "D": 10,
                 "l2": "not flushed: each step writes %.1f GB of draws, >> 126 MB L2"
                       % (C * N * 22 * 8 / 1e9)}
+    if name == "logistic":
+        return {"workload": "BASELINE.json configs[2]: Bayesian logistic regression N=100000 D=100, "
+                            "NUTS(0.8), %d chains per GPU, %d draws + %d warm-up" % (C, N, min(1000, N // 2)),
+                "chains_per_gpu": C, "draws": N, "D": 100,
+                "l2": "not flushed: every gradient streams the 60 MB of X planes per chain tile and "
+                      "each step writes %.1f GB of draws" % (C * N * 112 * 8 / 1e9)}
     return {"workload": name, "chains_per_gpu": C, "draws": N}
 
 
@@ -187,6 +220,8 @@ def main():
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: workload's)")
     ap.add_argument("--ref-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tc", action="store_true",
+                    help="logistic workload: tcgen05 bf16x3 likelihood kernel (engine option logistic_tc)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -229,7 +264,10 @@ def main():
     seed = 20261019
 
     # ---------------- arm 1: device-resident (value) ----------------
+    opts = {"logistic_tc": 1} if args.tc else {}
     eng = T.Engine(model, spl, C, nad, seed, device=local, chain_offset=rank * C)
+    for k_, v_ in opts.items():
+        eng.set_option(k_, v_)
     if dist is not None:
         # chains shard over the ranks; the communicator is only used by the pooled diagnostics
         T.distributed.attach_comm(eng, dist, device="cuda:%d" % local)
@@ -239,8 +277,10 @@ def main():
         eng.run(n_tr, nad, 1)
         return eng.L.tnuts_init_device_seconds(eng.h), eng.L.tnuts_device_seconds(eng.h)
 
-    for _ in range(max(args.warmup, 3)):
+    n_warm = max(args.warmup, 3) if args.workload != "logistic" else max(args.warmup, 1)
+    for _ in range(n_warm):
         step()
+    grad_ms = eng.bench_gradient(5) * 1e3 if args.workload == "logistic" else None
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -274,7 +314,7 @@ def main():
     def e2e_step(k):
         # the user-facing call: host model in, host chain array (iterations x names x chains) out
         ch = T.sample(model, spl, T.MCMCThreads(), N, C, seed=seed + k, devices=[local],
-                      chain_offset=rank * C, verbose=False)
+                      chain_offset=rank * C, verbose=False, engine_options=opts)
         res = (ch.info["grad_evals"], ch.info["gpu_launches"], ch.value.nbytes,
                float(ch.value[-1, 0, 0]))
         if os.environ.get("TNUTS_BENCH_VERBOSE"):
@@ -282,7 +322,7 @@ def main():
         del ch  # the chain's pinned buffer returns to the pool for the next step
         return res
 
-    for k in range(max(args.warmup, 3)):
+    for k in range(n_warm):
         e2e_step(k)
     barrier()
     t0 = time.perf_counter()
@@ -303,7 +343,7 @@ def main():
         achieved = alg * (grads / args.steps) / (dev_run / args.steps) / 1e9
         line = {
             "metric": "grad_evals_per_sec", "value": value, "unit": "grad_evals/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": dev_total / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.workload, C, N),
@@ -325,6 +365,30 @@ def main():
                                  "the state in registers, so it is fp64-issue bound, see DESIGN.md"},
             "clocks": clk,
         }
+        if args.workload == "logistic":
+            Dm, Nr = model.D, model.N
+            if args.tc:
+                _, _, _ = measured_peaks()
+                pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1614.0) \
+                    if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
+                dpad = 16 * ((Dm + 15) // 16)
+                ach = 18.0 * Nr * dpad * C / (grad_ms * 1e-3) / 1e12
+                line["dtype"] = "bf16x3 planes, fp32 accumulate, fp64 log-likelihood"
+                line["roofline"] = {
+                    "bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
+                    "traffic": None, "kernel": "k_logistic_tc<128> (+ reduce/finish)",
+                    "peak_source": "MEASURED_PEAKS.json bf16 burst" if which == "measured" else "fallback",
+                    "algorithmic_flops_per_grad_eval": 18.0 * Nr * dpad,
+                    "fp64_equivalent_tflops": 4.0 * Nr * Dm * C / (grad_ms * 1e-3) / 1e12,
+                    "note": "achieved = executed bf16 tensor flops (6 plane products for eta, 3 for X^T R) "
+                            "per launch / CUDA-event time of gradient launches for all chains"}
+            else:
+                ach = 4.0 * Nr * Dm * C / (grad_ms * 1e-3) / 1e12
+                line["roofline"] = {
+                    "bound": "tensor", "achieved": ach, "peak": 37.19, "unit": "TFLOP/s", "frac": ach / 37.19,
+                    "traffic": None, "kernel": "k_logistic_mma (+ reduce/finish)",
+                    "peak_source": "measured here: mma.sync f64, scripts/fp64_peak.cu (tcgen05 has no f64 kind)",
+                    "algorithmic_flops_per_grad_eval": 4.0 * Nr * Dm}
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_baseline(model, spl, N)
             line["cpu_baseline"] = cb

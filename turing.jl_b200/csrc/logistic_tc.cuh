@@ -35,6 +35,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace tnuts {
 namespace tc {
@@ -555,6 +556,7 @@ inline bool plan(long long nrows, int D, Plan *p) {
 inline void cut_for(long long nrows, int n_tiles, int *chunks, int *rpc) {
   const long long tiles = (nrows + kT - 1) / kT;
   long long want = n_tiles >= 4 ? 37 : n_tiles >= 2 ? 74 : 148;
+  if (const char *ov = getenv("TNUTS_TC_CHUNKS")) want = atoi(ov);   // experiments only
   if (want > tiles) want = tiles;
   const long long tpc = (tiles + want - 1) / want;
   *rpc = (int)(tpc * kT);
