@@ -72,6 +72,13 @@ extern "C" {
 #define TNUTS_ALG_NUTS 0
 #define TNUTS_ALG_HMC 1
 #define TNUTS_ALG_HMCDA 2
+/* stochastic-gradient samplers on the batched gradient kernel (src/mcmc/sghmc.jl:79-105, 223-249):
+ * no accept step, no adaptation, one gradient evaluation per transition.  They reuse the config
+ * fields: SGHMC  init_eps = learning_rate, lambda = momentum_decay;
+ *         SGLD   init_eps = a, delta = b, lambda = gamma of PolynomialStepsize a / (t + b)^gamma.
+ * Stats columns: n_steps = 1, log_density, step_size (= SGLD_stepsize); the others are NaN. */
+#define TNUTS_ALG_SGHMC 3
+#define TNUTS_ALG_SGLD 4
 
 typedef struct tnuts_engine tnuts_engine;
 

@@ -913,7 +913,10 @@ int orc_chain_init(const orc_model *m, const orc_config *cfg, uint32_t chain,
     }
   }
   if (!ok) return -1;
-  if (cfg->init_eps == 0.0 && cfg->algorithm != 1)
+  if (cfg->algorithm >= 3) { /* SGHMC / SGLD: velocity zero, no step-size search */
+    for (int d = 0; d < D; ++d) c->wf_mean[d] = 0.0;
+    c->eps = cfg->init_eps;
+  } else if (cfg->init_eps == 0.0 && cfg->algorithm != 1)
     c->eps = orc_find_good_stepsize(m, cfg, chain, c->theta, c->minv, &c->n_grad_evals);
   else
     c->eps = cfg->init_eps;
@@ -923,8 +926,55 @@ int orc_chain_init(const orc_model *m, const orc_config *cfg, uint32_t chain,
   return 0;
 }
 
+/* SGHMC (algorithm 3) and SGLD (algorithm 4), src/mcmc/sghmc.jl:79-105 and :223-249.
+ * Both take the gradient at the current position (cached from the previous step / the init
+ * step), move, and re-evaluate; no accept step, no adaptation.
+ *   SGHMC: theta += v;  v = (1 - alpha) v + eta grad + sqrt(2 eta alpha) z   (eq. 15 of Chen et al.)
+ *          eta = cfg->init_eps (learning_rate), alpha = cfg->lambda (momentum_decay);
+ *          the velocity lives in c->wf_mean (unused otherwise: no mass-matrix adaptation)
+ *   SGLD:  eps_t = a / (t + b)^gamma, t = 1, 2, ...  (PolynomialStepsize, sghmc.jl:124-161)
+ *          theta += eps_t / 2 grad + sqrt(eps_t) z
+ *          a = cfg->init_eps, b = cfg->delta, gamma = cfg->lambda
+ * z: the MOMENTUM slot of the addressing specification, iteration = transition number. */
+static void sg_transition(const orc_model *m, const orc_config *cfg, uint32_t chain, orc_chain *c,
+                          double *stats) {
+  const int D = m->D;
+  const uint32_t it = (uint32_t)(c->iter + 1);
+  double eps;
+  if (cfg->algorithm == 3) {
+    const double eta = cfg->init_eps, alpha = cfg->lambda, sd = sqrt(2.0 * eta * alpha);
+    double *v = c->wf_mean;
+    for (int d = 0; d < D; ++d) {
+      double z[2];
+      orc_normal2(cfg->seed, chain, it, ORC_SLOT_MOMENTUM, (uint32_t)(d >> 1), z);
+      c->theta[d] += v[d];
+      v[d] = (1.0 - alpha) * v[d] + eta * c->grad[d] + sd * z[d & 1];
+    }
+    eps = eta;
+  } else {
+    eps = cfg->init_eps / pow((double)(c->iter + 1) + cfg->delta, cfg->lambda);
+    const double sd = sqrt(eps);
+    for (int d = 0; d < D; ++d) {
+      double z[2];
+      orc_normal2(cfg->seed, chain, it, ORC_SLOT_MOMENTUM, (uint32_t)(d >> 1), z);
+      c->theta[d] += 0.5 * eps * c->grad[d] + sd * z[d & 1];
+    }
+  }
+  c->lp = orc_logdensity_and_gradient(m, c->theta, c->grad);
+  ++c->n_grad_evals;
+  for (int q = 0; q < ORC_NSTAT; ++q) stats[q] = NAN;
+  stats[ST_NSTEPS] = 1.0;
+  stats[ST_LP] = c->lp;
+  stats[ST_EPS] = eps; /* SGLD_stepsize (sghmc.jl:238) */
+}
+
 void orc_chain_step(const orc_model *m, const orc_config *cfg, uint32_t chain, orc_chain *c,
                     double *stats) {
+  if (cfg->algorithm >= 3) {
+    sg_transition(m, cfg, chain, c, stats);
+    c->iter += 1;
+    return;
+  }
   if (cfg->algorithm == 0) nuts_transition(m, cfg, chain, c, stats);
   else hmc_transition(m, cfg, chain, c, stats);
   c->iter += 1;

@@ -156,3 +156,46 @@ def test_divergence_warning(built):
     n = int(np.nansum(ch["numerical_error"]))
     assert n > 0
     assert any("There were %d divergent transitions" % n in str(x.message) for x in w)
+
+
+@pytest.mark.parametrize("name", ["gdemo", "eight_schools", "logistic_small", "hier_small"])
+def test_sghmc_and_sgld_match_oracle(built, name):
+    """SGHMC / SGLD (src/mcmc/sghmc.jl:79-105, 223-249) on the batched gradient kernels: same
+    Philox addresses as the oracle, so the chains agree draw for draw"""
+    from helpers import oracle_config, oracle_of, small_models
+    import oracle as O
+    model = small_models()[name]
+    # the hierarchical model started from U(-2, 2) has gradients of 1e4: keep SGHMC stable there
+    lr = 1e-7 if name == "hier_small" else 1e-4
+    for spl in (T.SGHMC(learning_rate=lr, momentum_decay=0.3),
+                T.SGLD(stepsize=T.PolynomialStepsize(2 * lr, 3.0, 0.6))):
+        C, n_tr = 70, 25
+        eng = T.Engine(model, spl, C, 0, seed=21)
+        eng.set_option("keep_theta", 1)
+        eng.init()
+        eng.run(n_tr, 1, 1)
+        out = eng.fetch(theta=True)
+        ref = O.sample_chains(oracle_of(model), oracle_config(spl, 0, 21), C, n_tr)
+        np.testing.assert_allclose(out["theta"].transpose(2, 0, 1), ref["theta"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(out["params"].transpose(2, 0, 1), ref["params"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(out["logp"].transpose(2, 0, 1), ref["logp"], rtol=1e-9, atol=1e-8)
+        st, rst = out["stats"].transpose(2, 0, 1), ref["stats"]
+        np.testing.assert_allclose(st[:, :, [0, 2, 8]], rst[:, :, [0, 2, 8]], rtol=1e-9, atol=1e-8)
+        assert np.all(np.isnan(st[:, :, [1, 3, 4, 5, 6, 7]]))
+        assert eng.grad_evals == ref["n_grad"]
+        eng.close()
+
+
+def test_sgld_through_sample_reference_style(built):
+    """test/mcmc/sghmc.jl:40-53 through the public call: first sample = initial parameters,
+    SGLD_stepsize column, step-size weighted means (median over chains: no accept step, an early
+    overshoot of a single chain is never forgotten)"""
+    chain = T.sample(T.gdemo_default(), T.SGLD(stepsize=T.PolynomialStepsize(0.5)), T.MCMCThreads(),
+                     10000, 64, seed=1, verbose=False)
+    ss = chain["SGLD_stepsize"]
+    assert chain.value.shape[0] == 10000 and np.all(np.isnan(ss[0]))       # the init step's sample
+    np.testing.assert_allclose(ss[1:4, 0], 0.5 / np.arange(1, 4) ** 0.55, rtol=1e-13)
+    w = ss[1:] / ss[1:].sum(axis=0)
+    assert abs(np.median((chain["s"][1:] * w).sum(axis=0)) - 49 / 24) < 0.2
+    assert abs(np.median((chain["m"][1:] * w).sum(axis=0)) - 7 / 6) < 0.2
+    np.testing.assert_allclose(chain["logjoint"], chain["logprior"] + chain["loglikelihood"], rtol=1e-12)

@@ -172,3 +172,29 @@ def test_diagnostics_against_known(built):
     # shifted chains are detected
     x[:, 0] += 1.0
     assert dg.rhat(x) > 1.05
+
+
+def test_sghmc_and_sgld_oracle_semantics():
+    """src/mcmc/sghmc.jl:79-105, 223-249 restated.  The reference pins them on gdemo
+    (test/mcmc/sghmc.jl:23-53: means 49/24 and 7/6, atol 0.1 for SGHMC(0.02, 0.5) on 10 000 samples,
+    atol 0.2 for the step-size weighted SGLD(PolynomialStepsize(0.5)) means on 20 000) for ONE seed.
+    Neither sampler has an accept step: an SGLD chain whose first (largest, most heavily weighted)
+    steps overshoot carries that forever, so the check here is the median over 16 chains; SGHMC has a
+    discretisation bias of about +0.15 on s, hence atol 0.25 on the pooled mean."""
+    m = O.OracleModel(0, D=2, N=2, y=[1.5, 2.0], hyper=(2.0, 3.0))
+    cfg = O.make_config(algorithm=4, init_eps=0.5, delta=0.0, lambda_=0.55, seed=3)
+    r = O.sample_chains(m, cfg, 16, 10000, first_keep=1)
+    eps = r["stats"][0, :, 8]
+    np.testing.assert_allclose(eps[:4], 0.5 / np.arange(1, 5) ** 0.55, rtol=1e-14)   # SGLD_stepsize
+    w = eps / eps.sum()
+    s_w = np.median((r["params"][:, :, 0] * w).sum(axis=1))    # weighted by the step sizes
+    m_w = np.median((r["params"][:, :, 1] * w).sum(axis=1))
+    assert abs(s_w - 49 / 24) < 0.2 and abs(m_w - 7 / 6) < 0.2, (s_w, m_w)
+    assert r["n_grad"] == 16 * (10000 + 1)
+    assert np.all(r["stats"][:, :, 0] == 1.0) and np.all(np.isnan(r["stats"][:, :, 1]))
+    cfg = O.make_config(algorithm=3, init_eps=0.02, lambda_=0.5, seed=4)
+    r = O.sample_chains(m, cfg, 16, 10000, first_keep=1)
+    assert abs(r["params"][:, :, 0].mean() - 49 / 24) < 0.25
+    assert abs(r["params"][:, :, 1].mean() - 7 / 6) < 0.1
+    # the user-space log-prob identity holds for these samplers too (test_chain_logp_metadata)
+    np.testing.assert_allclose(r["logp"][:, :, 2], r["logp"][:, :, 0] + r["logp"][:, :, 1], rtol=1e-13)

@@ -11,10 +11,10 @@ from .engine import Engine  # noqa: F401
 from .inference import LogDensityFunction, loadstate, post_sample_hook, sample  # noqa: F401
 from .models import (EightSchools, GDemo, HierLinearRegression, LinearRegression,  # noqa: F401
                      LogisticRegression, StdNormal, gdemo_default)
-from .samplers import (HMC, HMCDA, NUTS, InitFromParams, InitFromUniform, MCMCDistributed,  # noqa: F401
-                       MCMCSerial, MCMCThreads)
+from .samplers import (HMC, HMCDA, NUTS, SGHMC, SGLD, InitFromParams, InitFromUniform,  # noqa: F401
+                       MCMCDistributed, MCMCSerial, MCMCThreads, PolynomialStepsize)
 
-__all__ = ["sample", "NUTS", "HMC", "HMCDA", "MCMCThreads", "MCMCSerial", "MCMCDistributed",
+__all__ = ["sample", "NUTS", "HMC", "HMCDA", "SGHMC", "SGLD", "PolynomialStepsize", "MCMCThreads", "MCMCSerial", "MCMCDistributed",
            "Chains", "chainscat", "loadstate", "LogDensityFunction", "Engine", "InitFromParams",
            "InitFromUniform", "GDemo", "gdemo_default", "LinearRegression", "EightSchools",
            "LogisticRegression", "HierLinearRegression", "StdNormal", "models"]

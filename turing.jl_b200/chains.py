@@ -32,7 +32,7 @@ class Chains:
     def __getitem__(self, name):
         """chain[name] -> [iters, chains]"""
         if isinstance(name, str):
-            if name == "nom_step_size":
+            if name in ("nom_step_size", "SGLD_stepsize"):   # src/mcmc/sghmc.jl:238
                 return self["step_size"]
             if name == "is_accept":
                 # NUTS always accepts; HMC/HMCDA carry their accept flag in the tree_depth column

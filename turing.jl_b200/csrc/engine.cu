@@ -311,7 +311,11 @@ static int set_model_impl(tnuts_engine *h, const tnuts_model *m, bool device_ptr
   const bool block_ok = block_strategy_supported(e);
   if (e->cfg.strategy == STRAT_BLOCK && !block_ok)
     return set_error(e, TNUTS_E_UNSUPPORTED, "one-CTA-per-chain strategy not available for this model");
-  if (e->cfg.strategy == STRAT_THREAD || (e->cfg.strategy == STRAT_AUTO && thread_ok)) e->strategy = STRAT_THREAD;
+  const bool sg = e->cfg.algorithm == TNUTS_ALG_SGHMC || e->cfg.algorithm == TNUTS_ALG_SGLD;
+  if (sg && (e->cfg.strategy == STRAT_THREAD || e->cfg.strategy == STRAT_BLOCK))
+    return set_error(e, TNUTS_E_UNSUPPORTED, "SGHMC / SGLD run on the batched (lock-step) strategy only");
+  if (sg) e->strategy = STRAT_LOCKSTEP;
+  else if (e->cfg.strategy == STRAT_THREAD || (e->cfg.strategy == STRAT_AUTO && thread_ok)) e->strategy = STRAT_THREAD;
   else if (e->cfg.strategy == STRAT_BLOCK || (e->cfg.strategy == STRAT_AUTO && block_ok)) e->strategy = STRAT_BLOCK;
   else e->strategy = STRAT_LOCKSTEP;
 

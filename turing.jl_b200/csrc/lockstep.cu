@@ -548,7 +548,11 @@ int lockstep_init(Engine *e, const double *theta0_dev) {
     n_bad = ls->h_count[0];
   }
   if (n_bad > 0) return TNUTS_OK;  // tnuts_init reports TNUTS_E_INIT from the status array
-  if (e->cfg.init_eps == 0.0 && e->cfg.algorithm == TNUTS_ALG_HMC) {
+  if (e->cfg.algorithm == TNUTS_ALG_SGHMC || e->cfg.algorithm == TNUTS_ALG_SGLD) {
+    // no step-size search; the velocity (st.wf_mean) was zeroed by k_ls_init_state
+    k_ls_set_eps<<<(C + 255) / 256, 256, 0, e->stream>>>(st, e->cfg.init_eps);
+    e->launches += 1;
+  } else if (e->cfg.init_eps == 0.0 && e->cfg.algorithm == TNUTS_ALG_HMC) {
     k_ls_set_eps<<<(C + 255) / 256, 256, 0, e->stream>>>(st, 0.1);
     e->launches += 1;
   } else if (e->cfg.init_eps == 0.0) {
@@ -579,7 +583,36 @@ int lockstep_init(Engine *e, const double *theta0_dev) {
 // finished-chain counter into mapped pinned memory, the host polls that word and only bounds
 // how far it runs ahead of the GPU (an event every 64 pumps).
 // ------------------------------------------------------------------------------------------
+// SGHMC / SGLD: every chain takes exactly one gradient per transition, so the "pump" is a plain
+// loop: move (and record the previous kept draw), gradient at the new position, repeat.
+static int lockstep_run_sg(Engine *e) {
+  ChainState &st = e->st;
+  const RunParams &rp = e->rp;
+  const int C = st.C;
+  const int T = tiles(C);
+  const double a = e->cfg.init_eps, b = e->cfg.delta, c = e->cfg.lambda;
+  auto slot = [&](long long tt) -> long long {
+    if (tt >= 1 && rp.first_keep >= 1 && tt >= rp.first_keep && (tt - rp.first_keep) % rp.thin == 0)
+      return (tt - rp.first_keep) / rp.thin;
+    return -1;
+  };
+  int rc;
+  for (long long tt = 1; tt <= rp.n_transitions; ++tt) {
+    k_sg_step<<<T, kTileThreads, 0, e->stream>>>(st, rp, e->model, e->out, slot(tt - 1), 1, a, b, c);
+    e->launches += 1;
+    if ((rc = grad_launch(e, st.theta, C, st.lp, st.grad, nullptr, nullptr, C, C, gw_of(e)))) return rc;
+  }
+  const long long last = slot(rp.n_transitions);
+  if (last >= 0) {
+    k_sg_step<<<T, kTileThreads, 0, e->stream>>>(st, rp, e->model, e->out, last, 0, a, b, c);
+    e->launches += 1;
+  }
+  TN_CUDA(e, cudaGetLastError());
+  return TNUTS_OK;
+}
+
 int lockstep_run(Engine *e) {
+  if (e->cfg.algorithm == TNUTS_ALG_SGHMC || e->cfg.algorithm == TNUTS_ALG_SGLD) return lockstep_run_sg(e);
   LockstepState *ls = e->ls;
   ChainState &st = e->st;
   const RunParams &rp = e->rp;

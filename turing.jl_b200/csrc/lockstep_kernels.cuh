@@ -170,6 +170,79 @@ __device__ __forceinline__ void ls_user_logp(const ModelDev &m, const double *th
 }
 
 // ------------------------------------------------------------------------------------------
+// k_sg_step -- SGHMC / SGLD (src/mcmc/sghmc.jl:79-105, 223-249) on the batched gradient kernels:
+// all chains are in lock step, one launch per transition.  The launch first records the current
+// position as kept draw k_slot (its lp / gradient were just written by the family's gradient
+// kernel), then moves every chain:
+//   SGHMC  theta += v;  v = (1 - alpha) v + eta grad + sqrt(2 eta alpha) z     v in st.wf_mean
+//   SGLD   eps = a / (t + b)^gamma;  theta += eps / 2 grad + sqrt(eps) z       t = iteration, from 1
+// z from the MOMENTUM slot of the RNG addressing specification (the oracle does the same).
+// ------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(kTileThreads)
+k_sg_step(ChainState st, RunParams rp, ModelDev m, DrawBuffers out, long long k_slot, int do_update,
+          double sg_a, double sg_b, double sg_c) {
+  __shared__ double red[2 * 64];
+  const Tile t;
+  const int C = st.C, D = st.D;
+  const bool in = t.c < C && st.status[t.c] == 0;
+  if (k_slot >= 0) {  // launch-uniform
+    double prior, lik;
+    ls_user_logp(m, st.theta, C, t, in, in ? st.lp[t.c] : 0.0, red, prior, lik);
+    if (in) {
+      double *row = out.draws + (size_t)k_slot * out.ncol * C + t.c;
+      for (int d = t.dl; d < D; d += kTileD) {
+        const double th = st.theta[(size_t)d * C + t.c];
+        row[(size_t)d * C] = ls_is_positive(m, d) ? exp(th) : th;
+        if (out.theta) out.theta[((size_t)k_slot * D + d) * C + t.c] = th;
+      }
+      if (t.dl == 0) {
+        row[(size_t)(D + 0) * C] = prior;
+        row[(size_t)(D + 1) * C] = lik;
+        row[(size_t)(D + 2) * C] = prior + lik;
+#pragma unroll
+        for (int q = 0; q < TNUTS_NSTAT; ++q) row[(size_t)(D + 3 + q) * C] = CUDART_NAN;
+        row[(size_t)(D + 3 + ST_NSTEPS) * C] = 1.0;
+        row[(size_t)(D + 3 + ST_LP) * C] = st.lp[t.c];
+        row[(size_t)(D + 3 + ST_EPS) * C] = st.eps[t.c];
+      }
+    }
+  }
+  __syncthreads();  // the d-lane-0 thread reads the whole theta column for the user-space log-probs
+  if (!do_update || !in) return;
+  const long long iter = st.iter[t.c];
+  const uint32_t it = (uint32_t)(iter + 1);
+  const uint32_t gchain = (uint32_t)(rp.chain_offset + t.c);
+  double eps;
+  if (rp.algorithm == TNUTS_ALG_SGHMC) {
+    const double eta = sg_a, alpha = sg_c, sd = sqrt(2.0 * eta * alpha);
+    eps = eta;
+    for (int d = t.dl; d < D; d += kTileD) {
+      const size_t o = (size_t)d * C + t.c;
+      double z0, z1;
+      normal2(rp.seed, gchain, it, SLOT_MOMENTUM, (uint32_t)(d >> 1), z0, z1);
+      const double v = st.wf_mean[o];
+      st.theta[o] += v;
+      st.wf_mean[o] = (1.0 - alpha) * v + eta * st.grad[o] + sd * ((d & 1) ? z1 : z0);
+    }
+  } else {
+    eps = sg_a / pow((double)(iter + 1) + sg_b, sg_c);
+    const double sd = sqrt(eps);
+    for (int d = t.dl; d < D; d += kTileD) {
+      const size_t o = (size_t)d * C + t.c;
+      double z0, z1;
+      normal2(rp.seed, gchain, it, SLOT_MOMENTUM, (uint32_t)(d >> 1), z0, z1);
+      st.theta[o] += 0.5 * eps * st.grad[o] + sd * ((d & 1) ? z1 : z0);
+    }
+  }
+  __syncthreads();  // every d-lane has read iter before it moves on
+  if (t.dl == 0) {
+    st.iter[t.c] = iter + 1;
+    st.n_grad[t.c] += 1;
+    st.eps[t.c] = eps;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // k_ls_pump -- the whole per-chain NUTS state machine as ONE kernel that the host "pumps":
 // every launch advances EVERY unfinished chain by exactly one leapfrog (the gradient at the
 // drifted position was written to zg / zlp by the family's kernel just before).  Chains are

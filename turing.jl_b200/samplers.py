@@ -1,5 +1,6 @@
 """Sampler structs and ensemble markers with the reference's names, defaults and argument
-meaning (src/mcmc/hmc.jl:59-80 HMC, :285-327 HMCDA, :352-402 NUTS; src/Turing.jl:105-107)."""
+meaning (src/mcmc/hmc.jl:59-80 HMC, :285-327 HMCDA, :352-402 NUTS; src/mcmc/sghmc.jl SGHMC, SGLD,
+PolynomialStepsize; src/Turing.jl:105-107)."""
 
 
 class Hamiltonian:
@@ -59,6 +60,47 @@ class HMCDA(Hamiltonian):
         self.n_adapts, self.delta, self.lam = int(n_adapts), float(delta), float(lam)
         self.eps = float(init_eps)
         self.max_depth, self.Delta_max = 10, 1000.0
+
+
+class SGHMC(Hamiltonian):
+    """SGHMC(; learning_rate, momentum_decay) (src/mcmc/sghmc.jl:15-47): theta += v;
+    v = (1 - alpha) v + eta grad + sqrt(2 eta alpha) randn -- eq. (15) of Chen et al. (2014)."""
+    algorithm = 3
+    adaptive = False
+
+    def __init__(self, *, learning_rate, momentum_decay):
+        self.learning_rate, self.momentum_decay = float(learning_rate), float(momentum_decay)
+        # engine config fields (include/tnuts.h): init_eps = learning_rate, lambda = momentum_decay
+        self.eps, self.lam, self.delta = self.learning_rate, self.momentum_decay, 0.0
+        self.n_adapts, self.max_depth, self.Delta_max = 0, 10, 1000.0
+
+
+class PolynomialStepsize:
+    """PolynomialStepsize(a[, b=0, gamma=0.55]): step size a (b + t)^-gamma at iteration t
+    (src/mcmc/sghmc.jl:124-161)."""
+
+    def __init__(self, a, b=0.0, gamma=0.55):
+        if not (0.5 < gamma <= 1):
+            raise ValueError("the decay rate `γ` has to be in (0.5, 1]")
+        self.a, self.b, self.gamma = float(a), float(b), float(gamma)
+
+    def __call__(self, t):
+        return self.a / (t + self.b) ** self.gamma
+
+
+class SGLD(Hamiltonian):
+    """SGLD(; stepsize = PolynomialStepsize(0.01)) (src/mcmc/sghmc.jl:163-186):
+    theta += eps_t / 2 grad + sqrt(eps_t) randn; the chain carries the `SGLD_stepsize` column."""
+    algorithm = 4
+    adaptive = False
+
+    def __init__(self, *, stepsize=None):
+        self.stepsize = stepsize if stepsize is not None else PolynomialStepsize(0.01)
+        if not isinstance(self.stepsize, PolynomialStepsize):
+            raise TypeError("the engine evaluates the step size on the device: it must be a PolynomialStepsize")
+        # engine config fields (include/tnuts.h): init_eps = a, delta = b, lambda = gamma
+        self.eps, self.delta, self.lam = self.stepsize.a, self.stepsize.b, self.stepsize.gamma
+        self.n_adapts, self.max_depth, self.Delta_max = 0, 10, 1000.0
 
 
 class MCMCThreads:
