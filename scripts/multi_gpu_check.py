@@ -45,12 +45,62 @@ def diag_mode(rank, world, local):
     sys.exit(0 if flag.item() == 1 else 1)
 
 
+def mesh_mode(rank, world, local):
+    """chains x rows mesh (SURVEY 8e "Hybrid"): world = chain_groups x 2 row shards.  Ranks of one
+    chain group must hold identical draws; the union over the groups must equal (to the rounding of
+    the regrouped row sums) a single-GPU engine running all chains on all rows."""
+    rs = 2
+    N, Dm, C = 4001, 24, 96
+    model = T.models.synthetic_logistic(N, Dm, seed=3)
+    spl = T.NUTS(10, 0.8)
+    n_tr = 14
+    eng = D.make_mesh_engine(model, spl, C, 10, 7, rank, world, local, dist, rs)
+    cg, rr, ng = eng.mesh
+    eng.set_option("keep_theta", 1)
+    eng.init()
+    eng.run(n_tr, 1, 1)
+    out = eng.fetch(theta=True)
+    th = torch.from_numpy(out["theta"].copy()).cuda()          # [K, D, C_group]
+    b = D.chain_bounds(C, ng)
+    # gather every rank's draws on every rank (groups may differ in size by one chain: pad)
+    cmax = max(b[g + 1] - b[g] for g in range(ng))
+    pad = torch.zeros(th.shape[0], th.shape[1], cmax, dtype=th.dtype, device="cuda")
+    pad[:, :, :th.shape[2]] = th
+    allth = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(allth, pad)
+    ok = True
+    for g in range(ng):
+        ok = ok and bool(torch.equal(allth[g * rs], allth[g * rs + 1]))
+    if rank == 0:
+        print("mesh %d chain groups x %d row shards: identical within every group: %s" % (ng, rs, ok))
+        single = T.Engine(model, spl, C, 10, 7, device=local, strategy=2)
+        single.set_option("keep_theta", 1)
+        single.init()
+        single.run(n_tr, 1, 1)
+        o1 = single.fetch(theta=True)
+        union = np.concatenate([allth[g * rs][:, :, :b[g + 1] - b[g]].cpu().numpy() for g in range(ng)], axis=2)
+        d = np.abs(o1["theta"][:6] - union[:6]).max()
+        print("  union of the groups vs single GPU: max |dtheta| first 6 transitions %.2e" % d)
+        ok = ok and d < 1e-8
+        single.close()
+    eng.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0 and flag.item() == 1:
+        print("MESH-OK")
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if "--diag" in sys.argv:
         return diag_mode(rank, world, local)
+    if "--mesh" in sys.argv:
+        return mesh_mode(rank, world, local)
     big = "--big" in sys.argv
     N, Dm, C = (2_000_000, 256, 256) if big else (4001, 24, 64)
     model = T.models.synthetic_logistic(N, Dm, seed=3)

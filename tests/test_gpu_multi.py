@@ -79,3 +79,17 @@ def test_pooled_diagnostics_two_gpus(built):
         capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "DIAG-OK" in out.stdout
+
+
+def test_chain_by_row_mesh_four_gpus(built):
+    """SURVEY 8e "Hybrid": 2 chain groups x 2 row shards, NCCL all-reduce inside each group only"""
+    import torch
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4",
+         "--master-addr", "127.0.0.1", "--master-port", "29619",
+         os.path.join(ROOT, "scripts", "multi_gpu_check.py"), "--mesh"],
+        capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "MESH-OK" in out.stdout

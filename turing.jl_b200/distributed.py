@@ -7,6 +7,10 @@ Two ways the path shards:
   * rows:   every rank owns all chains and a slice of the data rows; libtnuts sums the
     per-leapfrog [D+1][chains] likelihood/gradient block with ncclAllReduce on its own stream
     (tnuts_comm_init); the host only broadcasts the 128-byte ncclUniqueId.
+  * hybrid: a chains x rows mesh (SURVEY.md 8e "Hybrid"): `world = chain_groups * row_shards`;
+    rank r is row shard r % row_shards of chain group r // row_shards.  Every chain group owns a
+    slice of the chains and a private NCCL communicator over its row shards: the all-reduce stays
+    inside the group, nothing crosses groups on the data path.
 """
 import ctypes as C
 
@@ -35,19 +39,44 @@ def shard_rows(model, world, rank):
                               model.hyper[0])
 
 
-def broadcast_unique_id(dist, rank, device=None):
-    """rank 0 creates the ncclUniqueId through the C ABI; everybody receives the 128 bytes"""
-    import torch
+def _new_unique_id():
     buf = np.zeros(128, dtype=np.uint8)
-    if rank == 0:
-        rc = _lib.load().tnuts_comm_unique_id(buf.ctypes.data_as(C.c_void_p))
-        if rc != 0:
-            raise _lib.TnutsError(rc, "tnuts_comm_unique_id failed")
-    t = torch.from_numpy(buf)
+    rc = _lib.load().tnuts_comm_unique_id(buf.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise _lib.TnutsError(rc, "tnuts_comm_unique_id failed")
+    return buf
+
+
+def broadcast_unique_id(dist, rank, device=None, src=0, group=None, make_id=_new_unique_id):
+    """global rank `src` creates the ncclUniqueId through the C ABI; everybody in `group` (default:
+    the whole process group) receives the 128 bytes"""
+    import torch
+    buf = make_id() if rank == src else np.zeros(128, dtype=np.uint8)
+    t = torch.from_numpy(np.ascontiguousarray(buf, dtype=np.uint8))
     if device is not None:
         t = t.to(device)
-    dist.broadcast(t, src=0)
+    dist.broadcast(t, src=src, group=group)
     return np.ascontiguousarray(t.cpu().numpy())
+
+
+def mesh_coords(rank, world, row_shards):
+    """(chain_group, row_rank, n_chain_groups) of `rank` in a chains x rows mesh"""
+    if row_shards < 1 or world % row_shards != 0:
+        raise ValueError("world size %d is not a multiple of row_shards %d" % (world, row_shards))
+    return rank // row_shards, rank % row_shards, world // row_shards
+
+
+def mesh_row_group(dist, rank, world, row_shards):
+    """the torch process group of this rank's row shards (every rank creates every group, as
+    torch.distributed requires) and the global rank of its leader"""
+    cg, _, ngroups = mesh_coords(rank, world, row_shards)
+    mine = None
+    for g in range(ngroups):
+        ranks = list(range(g * row_shards, (g + 1) * row_shards))
+        grp = dist.new_group(ranks)
+        if g == cg:
+            mine = grp
+    return mine, cg * row_shards
 
 
 def attach_comm(engine, dist, device=None):
@@ -72,6 +101,27 @@ def make_row_sharded_engine(model, spl, n_chains, n_adapts, seed, rank, world, d
     e._local_model = local
     if world > 1:
         attach_comm(e, dist, device="cuda:%d" % device if device is not None else None)
+    return e
+
+
+def make_mesh_engine(model, spl, n_chains_total, n_adapts, seed, rank, world, device, dist, row_shards,
+                     make_id=_new_unique_id):
+    """chains x rows mesh: chain group g = rank // row_shards owns chains [b[g], b[g+1]) and all the
+    rows, cut over its `row_shards` ranks; the per-leapfrog all-reduce runs on a communicator
+    private to the group"""
+    cg, rr, ngroups = mesh_coords(rank, world, row_shards)
+    b = chain_bounds(n_chains_total, ngroups)
+    local = shard_rows(model, row_shards, rr) if row_shards > 1 else model
+    e = Engine(local, spl, b[cg + 1] - b[cg], n_adapts, seed, device=device, chain_offset=b[cg],
+               row_shards=row_shards, row_rank=rr, strategy=2)
+    e._local_model = local
+    e.mesh = (cg, rr, ngroups)
+    if row_shards > 1:
+        grp, leader = mesh_row_group(dist, rank, world, row_shards)
+        uid = broadcast_unique_id(dist, rank, "cuda:%d" % device if device is not None else None,
+                                  src=leader, group=grp, make_id=make_id)
+        e.comm_init(uid.ctypes.data_as(C.c_void_p), row_shards, rr)
+        e._uid = uid
     return e
 
 
