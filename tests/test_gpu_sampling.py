@@ -199,3 +199,21 @@ def test_sgld_through_sample_reference_style(built):
     assert abs(np.median((chain["s"][1:] * w).sum(axis=0)) - 49 / 24) < 0.2
     assert abs(np.median((chain["m"][1:] * w).sum(axis=0)) - 7 / 6) < 0.2
     np.testing.assert_allclose(chain["logjoint"], chain["logprior"] + chain["loglikelihood"], rtol=1e-12)
+
+
+def test_dynamic_scheduling_is_bit_identical(built):
+    """thread-per-chain strategy with more chain groups than resident CTAs: the task-queue kernel
+    (k_chain_run_dyn: sub-ranges of the transitions, state handed over through global memory, any
+    SM) must reproduce the static grid bit for bit, warm-up adaptation included"""
+    outs = []
+    for dyn in (1, 0):
+        eng = T.Engine(T.EightSchools(), T.NUTS(40, 0.8), 40000, 40, seed=17, strategy=1)
+        eng.set_option("dyn_sched", dyn)
+        eng.init()
+        eng.run(40 + 59, 40, 1)          # 99 transitions: warm-up windows and 60 kept draws
+        outs.append((eng.fetch_draws(), eng.stepsize(), eng.inv_metric(), eng.grad_evals))
+        eng.close()
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    np.testing.assert_array_equal(outs[0][2], outs[1][2])
+    assert outs[0][3] == outs[1][3]

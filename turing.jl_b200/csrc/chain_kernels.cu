@@ -1,6 +1,8 @@
 // chain_kernels.cu -- launchers of the one-thread-per-chain strategy (chain_kernels.cuh).
 #include <cub/cub.cuh>
 
+#include <algorithm>
+
 #include "chain_flat.cuh"
 #include "chain_kernels.cuh"
 #include "engine.cuh"
@@ -51,6 +53,9 @@ int thread_init(Engine *e, const double *theta0_dev) {
 }
 
 int thread_run(Engine *e) {
+  int n_sm = 0;
+  TN_CUDA(e, cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, e->device));
+  const bool dyn_ok = e->dyn_sched;
 #define CALL(M)                                                                              \
   do {                                                                                       \
     const int g_ = grid_for(e->st.C, kChainBlock);                                           \
@@ -59,7 +64,25 @@ int thread_run(Engine *e) {
       k_chain_run_flat<M, 2><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_); \
     else if (e->cfg.algorithm != TNUTS_ALG_NUTS)                                             \
       k_chain_run<M, 2, false><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_); \
-    else                                                                                     \
+    else if (dyn_ok) {                                                                       \
+      int per_sm_ = 0;                                                                       \
+      TN_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_, k_chain_run_dyn<M, 2, true>, \
+                                                               kChainBlock, 0));             \
+      const int slots_ = per_sm_ * n_sm;                                                     \
+      if (slots_ > 0 && g_ > slots_ && e->rp.n_transitions >= 32) {                          \
+        /* about ten tasks per slot, sub-ranges of at least 16 transitions */                \
+        long long n_sub_ = (10LL * slots_ + g_ - 1) / g_;                                    \
+        n_sub_ = std::max(1LL, std::min(n_sub_, e->rp.n_transitions / 16));                  \
+        const long long len_ = (e->rp.n_transitions + n_sub_ - 1) / n_sub_;                  \
+        n_sub_ = (e->rp.n_transitions + len_ - 1) / len_;                                    \
+        if (!e->dyn_work) TN_CUDA(e, cudaMalloc((void **)&e->dyn_work, sizeof(int) * (size_t)(g_ + 1))); \
+        TN_CUDA(e, cudaMemsetAsync(e->dyn_work, 0, sizeof(int) * (size_t)(g_ + 1), e->stream)); \
+        k_chain_run_dyn<M, 2, true><<<slots_, kChainBlock, 0, e->stream>>>(                  \
+            e->small, e->st, e->out, e->rp, pm_, g_, (int)n_sub_, len_, e->dyn_work, e->dyn_work + 1); \
+      } else {                                                                               \
+        k_chain_run<M, 2, true><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_); \
+      }                                                                                      \
+    } else                                                                                   \
       k_chain_run<M, 2, true><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_); \
   } while (0)
   TN_DISPATCH_SMALL(e, CALL);

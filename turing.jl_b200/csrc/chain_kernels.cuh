@@ -310,12 +310,15 @@ __device__ __forceinline__ void hmc_transition_d(const SmallData &md, const RunP
 // ------------------------------------------------------------------------------------------
 // run kernel: n_transitions for every chain
 // ------------------------------------------------------------------------------------------
-template <class M, int MINB, bool IS_NUTS>
-__global__ void __launch_bounds__(kChainBlock, MINB) k_chain_run(SmallData md, ChainState st,
-                                                                DrawBuffers out, RunParams rp,
-                                                                const int *__restrict__ perm) {
+// transitions (t_begin, t_end] of this launch for the chain in `slot`; state is loaded from and
+// stored back to the ChainState arrays, so a launch can be cut into ranges that run on different
+// SMs (k_chain_run_dyn).  State loads bypass L1 (ld.cg): another SM may have written them.
+template <class M, bool IS_NUTS>
+__device__ __forceinline__ void chain_run_range(const SmallData &md, const ChainState &st,
+                                                const DrawBuffers &out, const RunParams &rp,
+                                                const int *__restrict__ perm, int slot,
+                                                long long t_begin, long long t_end) {
   constexpr int D = M::D;
-  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   const int C = st.C;
   if (slot >= C) return;
   // lane -> chain map: after warm-up the chains are sorted by step size so that the 32 chains
@@ -328,17 +331,17 @@ __global__ void __launch_bounds__(kChainBlock, MINB) k_chain_run(SmallData md, C
   double th[D], g[D], minv[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    th[d] = st.theta[(size_t)d * C + c];
-    g[d] = st.grad[(size_t)d * C + c];
-    minv[d] = st.minv[(size_t)d * C + c];
+    th[d] = __ldcg(st.theta + (size_t)d * C + c);
+    g[d] = __ldcg(st.grad + (size_t)d * C + c);
+    minv[d] = __ldcg(st.minv + (size_t)d * C + c);
   }
-  double lp = st.lp[c], eps = st.eps[c];
-  long long iter = st.iter[c], ngrad = st.n_grad[c];
-  double da_mu = st.da_mu[c], da_xbar = st.da_xbar[c], da_hbar = st.da_hbar[c],
-         da_eps = st.da_eps[c];
-  long long da_m = st.da_m[c], wf_n = st.wf_n[c];
+  double lp = __ldcg(st.lp + c), eps = __ldcg(st.eps + c);
+  long long iter = __ldcg(st.iter + c), ngrad = __ldcg(st.n_grad + c);
+  double da_mu = __ldcg(st.da_mu + c), da_xbar = __ldcg(st.da_xbar + c), da_hbar = __ldcg(st.da_hbar + c),
+         da_eps = __ldcg(st.da_eps + c);
+  long long da_m = __ldcg(st.da_m + c), wf_n = __ldcg(st.wf_n + c);
 
-  for (long long t = 1; t <= rp.n_transitions; ++t) {
+  for (long long t = t_begin + 1; t <= t_end; ++t) {
     const uint32_t it = (uint32_t)(iter + 1);
     double stats[TNUTS_NSTAT];
     if (IS_NUTS)  // compile-time: the NUTS kernel carries no HMC code and vice versa
@@ -373,7 +376,7 @@ __global__ void __launch_bounds__(kChainBlock, MINB) k_chain_run(SmallData md, C
 #pragma unroll
         for (int d = 0; d < D; ++d) {
           const size_t o = (size_t)d * C + c;
-          double mean = st.wf_mean[o], m2 = st.wf_m2[o];
+          double mean = __ldcg(st.wf_mean + o), m2 = __ldcg(st.wf_m2 + o);
           const double delta = th[d] - mean;
           mean += delta / n;
           m2 += delta * (th[d] - mean);
@@ -433,6 +436,49 @@ __global__ void __launch_bounds__(kChainBlock, MINB) k_chain_run(SmallData md, C
   st.da_eps[c] = da_eps;
   st.da_m[c] = da_m;
   st.wf_n[c] = wf_n;
+}
+
+template <class M, int MINB, bool IS_NUTS>
+__global__ void __launch_bounds__(kChainBlock, MINB) k_chain_run(SmallData md, ChainState st,
+                                                                DrawBuffers out, RunParams rp,
+                                                                const int *__restrict__ perm) {
+  chain_run_range<M, IS_NUTS>(md, st, out, rp, perm, blockIdx.x * blockDim.x + threadIdx.x, 0,
+                              rp.n_transitions);
+}
+
+// The same run with dynamic scheduling: 65 536 chains are 512 groups of 128 chains, but only
+// 2 x 148 CTAs are resident, so a static grid runs 1.73 waves (the second one 73 % full) and a
+// group with long trees finishes last.  Here one resident CTA per slot pulls tasks
+// (sub-range s of the launch's transitions, chain group g) from a counter in order of s; task
+// (s, g) waits for (s - 1, g), which an earlier-claiming -- hence running -- CTA owns, so there is
+// no deadlock.  A chain's state travels through the ChainState arrays; its result does not depend
+// on where or when a task runs.
+template <class M, int MINB, bool IS_NUTS>
+__global__ void __launch_bounds__(kChainBlock, MINB)
+k_chain_run_dyn(SmallData md, ChainState st, DrawBuffers out, RunParams rp, const int *__restrict__ perm,
+                int n_groups, int n_sub, long long sub_len, int *counter, int *done /* [n_groups] */) {
+  __shared__ int s_task;
+  for (;;) {
+    if (threadIdx.x == 0) s_task = atomicAdd(counter, 1);
+    __syncthreads();
+    const int task = s_task;
+    __syncthreads();
+    if (task >= n_groups * n_sub) return;
+    const int sub = task / n_groups, grp = task - sub * n_groups;
+    if (sub > 0) {
+      if (threadIdx.x == 0) {
+        while (atomicAdd(done + grp, 0) < sub) __nanosleep(200);
+        __threadfence();
+      }
+      __syncthreads();
+    }
+    const long long t0 = (long long)sub * sub_len;
+    const long long t1 = (t0 + sub_len < rp.n_transitions) ? t0 + sub_len : rp.n_transitions;
+    chain_run_range<M, IS_NUTS>(md, st, out, rp, perm, grp * kChainBlock + threadIdx.x, t0, t1);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicExch(done + grp, sub + 1);
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -218,6 +218,7 @@ int tnuts_destroy(tnuts_engine *h) {
   for (double *p : {e->out.draws, e->out.theta})
     if (p) cudaFreeAsync(p, e->stream);
   cudaStreamSynchronize(e->stream);
+  if (e->dyn_work) cudaFree(e->dyn_work);
   if (e->perm) cudaFree(e->perm);
   if (e->perm_keys) cudaFree(e->perm_keys);
   if (e->perm_tmp) cudaFree(e->perm_tmp);
@@ -497,6 +498,7 @@ int tnuts_set_option(tnuts_engine *h, const char *name, double value) {
   else if (n == "sort_chains") e->sort_chains = value != 0.0;
   else if (n == "flat") e->flat = value != 0.0;
   else if (n == "flat_batch") e->rp.flat_batch = (int)value;
+  else if (n == "dyn_sched") e->dyn_sched = value != 0.0;
   else if (n == "logistic_tc") e->logistic_tc = value != 0.0;
 
   else return set_error(e, TNUTS_E_ARG, "tnuts_set_option: unknown option " + n);
