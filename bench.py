@@ -359,7 +359,7 @@ def main():
             "gpu_launches": int(launches + l_e2e),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": None, "peak_source": which,
-                         "kernel": "k_chain_run<EightSchools<8>>",
+                         "kernel": "k_chain_run_dyn<EightSchools<8>> (k_chain_run when the grid fits one wave)",
                          "algorithmic_bytes_per_grad_eval": alg,
                          "note": "SURVEY 8(d) streaming figure 6*D*8 B per leapfrog; the kernel keeps "
                                  "the state in registers, so it is fp64-issue bound, see DESIGN.md"},
