@@ -60,14 +60,19 @@ int thread_run(Engine *e) {
   do {                                                                                       \
     const int g_ = grid_for(e->st.C, kChainBlock);                                           \
     const int *pm_ = e->perm_valid ? e->perm : nullptr;                                      \
+    const size_t sm_ = e->ck_smem ? chain_ck_smem_bytes<M::D>() : 0;                         \
     if (e->flat && e->cfg.algorithm == TNUTS_ALG_NUTS)                                       \
       k_chain_run_flat<M, 2><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_); \
     else if (e->cfg.algorithm != TNUTS_ALG_NUTS)                                             \
-      k_chain_run<M, 2, false><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_); \
+      k_chain_run<M, 2, false><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_, 0); \
     else if (dyn_ok) {                                                                       \
       int per_sm_ = 0;                                                                       \
+      TN_CUDA(e, cudaFuncSetAttribute(k_chain_run_dyn<M, 2, true>,                           \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_ck_smem_bytes<M::D>())); \
+      TN_CUDA(e, cudaFuncSetAttribute(k_chain_run<M, 2, true>,                               \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_ck_smem_bytes<M::D>())); \
       TN_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_, k_chain_run_dyn<M, 2, true>, \
-                                                               kChainBlock, 0));             \
+                                                               kChainBlock, sm_));           \
       const int slots_ = per_sm_ * n_sm;                                                     \
       if (slots_ > 0 && g_ > slots_ && e->rp.n_transitions >= 32) {                          \
         /* about ten tasks per slot, sub-ranges of at least 16 transitions */                \
@@ -77,13 +82,13 @@ int thread_run(Engine *e) {
         n_sub_ = (e->rp.n_transitions + len_ - 1) / len_;                                    \
         if (!e->dyn_work) TN_CUDA(e, cudaMalloc((void **)&e->dyn_work, sizeof(int) * (size_t)(g_ + 1))); \
         TN_CUDA(e, cudaMemsetAsync(e->dyn_work, 0, sizeof(int) * (size_t)(g_ + 1), e->stream)); \
-        k_chain_run_dyn<M, 2, true><<<slots_, kChainBlock, 0, e->stream>>>(                  \
-            e->small, e->st, e->out, e->rp, pm_, g_, (int)n_sub_, len_, e->dyn_work, e->dyn_work + 1); \
+        k_chain_run_dyn<M, 2, true><<<slots_, kChainBlock, sm_, e->stream>>>(                \
+            e->small, e->st, e->out, e->rp, pm_, g_, (int)n_sub_, len_, e->dyn_work, e->dyn_work + 1, (int)(sm_ > 0)); \
       } else {                                                                               \
-        k_chain_run<M, 2, true><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_); \
+        k_chain_run<M, 2, true><<<g_, kChainBlock, sm_, e->stream>>>(e->small, e->st, e->out, e->rp, pm_, (int)(sm_ > 0)); \
       }                                                                                      \
     } else                                                                                   \
-      k_chain_run<M, 2, true><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_); \
+      k_chain_run<M, 2, true><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_, 0); \
   } while (0)
   TN_DISPATCH_SMALL(e, CALL);
 #undef CALL

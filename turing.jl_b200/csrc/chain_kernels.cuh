@@ -34,6 +34,11 @@ namespace tnuts {
 
 constexpr int kChainBlock = 128;
 constexpr int kMaxCk = 12;  // checkpoint levels: max_depth <= kMaxCk + 1 for this strategy
+// the lowest checkpoint levels are the busy ones (level l is written every 2^(l+1) leaves and read
+// about as often): they live in shared memory, [level][r | rho][d][thread], the others in local
+constexpr int kCkSm = 4;
+template <int D>
+constexpr size_t chain_ck_smem_bytes() { return sizeof(double) * kCkSm * 2 * D * 128; }
 
 __device__ __forceinline__ double logaddexp_d(double a, double b) {
   if (a == -CUDART_INF) return b;
@@ -108,7 +113,8 @@ __device__ __forceinline__ void nuts_transition_d(const SmallData &md, const Run
                                                   double (&th)[M::D], double (&g)[M::D],
                                                   double &lp, const double (&minv)[M::D],
                                                   double eps, long long &ngrad,
-                                                  double (&stats)[TNUTS_NSTAT]) {
+                                                  double (&stats)[TNUTS_NSTAT],
+                                                  double *__restrict__ ck_sm /* smem + tid, or null */) {
   constexpr int D = M::D;
   double r[D];
   draw_momentum_d<D>(rp.seed, gchain, it, SLOT_MOMENTUM, minv, r);
@@ -139,6 +145,7 @@ __device__ __forceinline__ void nuts_transition_d(const SmallData &md, const Run
   }
   // per-level checkpoints for the sub-tree U-turn checks
   double ck_r[kMaxCk][D], ck_rho[kMaxCk][D];
+  const int sm_levels = ck_sm ? kCkSm : 0;
 
   int j = 0;
   bool term = false, numerr = false;
@@ -191,19 +198,38 @@ __device__ __forceinline__ void nuts_transition_d(const SmallData &md, const Run
       }
       const int idx_max = __popc((unsigned)n >> 1);
       if ((n & 1) == 0) {
+        if (idx_max < sm_levels) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-          ck_r[idx_max][d] = zr[d];
-          ck_rho[idx_max][d] = rho_s[d];
+          for (int d = 0; d < D; ++d) {
+            ck_sm[((idx_max * 2 + 0) * D + d) * kChainBlock] = zr[d];
+            ck_sm[((idx_max * 2 + 1) * D + d) * kChainBlock] = rho_s[d];
+          }
+        } else {
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            ck_r[idx_max][d] = zr[d];
+            ck_rho[idx_max][d] = rho_s[d];
+          }
         }
       } else {
         const int ntrail = __ffs(~(unsigned)n) - 1;  // trailing ones of n
         const int idx_min = idx_max - ntrail + 1;
         for (int i = idx_max; i >= idx_min; --i) {
-          double sr[D];
+          double sr[D], cr[D];
+          if (i < sm_levels) {
 #pragma unroll
-          for (int d = 0; d < D; ++d) sr[d] = rho_s[d] - ck_rho[i][d] + ck_r[i][d];
-          if (uturn_d<D>(sr, ck_r[i], zr, minv)) {
+            for (int d = 0; d < D; ++d) {
+              cr[d] = ck_sm[((i * 2 + 0) * D + d) * kChainBlock];
+              sr[d] = rho_s[d] - ck_sm[((i * 2 + 1) * D + d) * kChainBlock] + cr[d];
+            }
+          } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+              cr[d] = ck_r[i][d];
+              sr[d] = rho_s[d] - ck_rho[i][d] + cr[d];
+            }
+          }
+          if (uturn_d<D>(sr, cr, zr, minv)) {
             term_s = true;
             break;
           }
@@ -317,7 +343,8 @@ template <class M, bool IS_NUTS>
 __device__ __forceinline__ void chain_run_range(const SmallData &md, const ChainState &st,
                                                 const DrawBuffers &out, const RunParams &rp,
                                                 const int *__restrict__ perm, int slot,
-                                                long long t_begin, long long t_end) {
+                                                long long t_begin, long long t_end,
+                                                double *__restrict__ ck_sm) {
   constexpr int D = M::D;
   const int C = st.C;
   if (slot >= C) return;
@@ -345,7 +372,7 @@ __device__ __forceinline__ void chain_run_range(const SmallData &md, const Chain
     const uint32_t it = (uint32_t)(iter + 1);
     double stats[TNUTS_NSTAT];
     if (IS_NUTS)  // compile-time: the NUTS kernel carries no HMC code and vice versa
-      nuts_transition_d<M>(md, rp, gchain, it, th, g, lp, minv, eps, ngrad, stats);
+      nuts_transition_d<M>(md, rp, gchain, it, th, g, lp, minv, eps, ngrad, stats, ck_sm);
     else
       hmc_transition_d<M>(md, rp, gchain, it, th, g, lp, minv, eps, ngrad, stats);
     iter += 1;
@@ -441,9 +468,11 @@ __device__ __forceinline__ void chain_run_range(const SmallData &md, const Chain
 template <class M, int MINB, bool IS_NUTS>
 __global__ void __launch_bounds__(kChainBlock, MINB) k_chain_run(SmallData md, ChainState st,
                                                                 DrawBuffers out, RunParams rp,
-                                                                const int *__restrict__ perm) {
+                                                                const int *__restrict__ perm,
+                                                                int use_ck_sm) {
+  extern __shared__ double ck_smem[];
   chain_run_range<M, IS_NUTS>(md, st, out, rp, perm, blockIdx.x * blockDim.x + threadIdx.x, 0,
-                              rp.n_transitions);
+                              rp.n_transitions, (IS_NUTS && use_ck_sm) ? ck_smem + threadIdx.x : nullptr);
 }
 
 // The same run with dynamic scheduling: 65 536 chains are 512 groups of 128 chains, but only
@@ -456,8 +485,10 @@ __global__ void __launch_bounds__(kChainBlock, MINB) k_chain_run(SmallData md, C
 template <class M, int MINB, bool IS_NUTS>
 __global__ void __launch_bounds__(kChainBlock, MINB)
 k_chain_run_dyn(SmallData md, ChainState st, DrawBuffers out, RunParams rp, const int *__restrict__ perm,
-                int n_groups, int n_sub, long long sub_len, int *counter, int *done /* [n_groups] */) {
+                int n_groups, int n_sub, long long sub_len, int *counter, int *done /* [n_groups] */,
+                int use_ck_sm) {
   __shared__ int s_task;
+  extern __shared__ double ck_smem[];
   for (;;) {
     if (threadIdx.x == 0) s_task = atomicAdd(counter, 1);
     __syncthreads();
@@ -474,7 +505,8 @@ k_chain_run_dyn(SmallData md, ChainState st, DrawBuffers out, RunParams rp, cons
     }
     const long long t0 = (long long)sub * sub_len;
     const long long t1 = (t0 + sub_len < rp.n_transitions) ? t0 + sub_len : rp.n_transitions;
-    chain_run_range<M, IS_NUTS>(md, st, out, rp, perm, grp * kChainBlock + threadIdx.x, t0, t1);
+    chain_run_range<M, IS_NUTS>(md, st, out, rp, perm, grp * kChainBlock + threadIdx.x, t0, t1,
+                                (IS_NUTS && use_ck_sm) ? ck_smem + threadIdx.x : nullptr);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) atomicExch(done + grp, sub + 1);

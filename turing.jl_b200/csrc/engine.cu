@@ -499,6 +499,7 @@ int tnuts_set_option(tnuts_engine *h, const char *name, double value) {
   else if (n == "flat") e->flat = value != 0.0;
   else if (n == "flat_batch") e->rp.flat_batch = (int)value;
   else if (n == "dyn_sched") e->dyn_sched = value != 0.0;
+  else if (n == "ck_smem") e->ck_smem = value != 0.0;
   else if (n == "logistic_tc") e->logistic_tc = value != 0.0;
 
   else return set_error(e, TNUTS_E_ARG, "tnuts_set_option: unknown option " + n);

@@ -55,6 +55,7 @@ struct Engine {
   bool flat = false;  // flat-scheduled thread-per-chain kernel (chain_flat.cuh)
   bool dyn_sched = true;   // thread-per-chain: task queue over (transition sub-range, chain group)
   int *dyn_work = nullptr; // [1 + groups]: task counter, per-group completed sub-ranges
+  bool ck_smem = true;     // thread-per-chain NUTS: lowest checkpoint levels in shared memory
   int occupancy = 2;  // CTAs of 128 threads per SM the thread-per-chain kernel is compiled for
   // logistic regression: likelihood gradient on the tcgen05 tensor cores (bf16x3 planes, fp32-grade
   // dot products, logistic_tc.cuh) instead of the fp64 DMMA kernel; opt-in, D <= 128
