@@ -25,7 +25,7 @@ int block_run(Engine *e) {
     if (e->out.theta) TN_CUDA(e, cudaMalloc((void **)&tcm, 8 * (size_t)C * keep * D));
   }
   HierStatsDev hs{ls->hs_n, ls->hs_xbar, ls->hs_ybar, ls->hs_sxx, ls->hs_sxy, ls->hs_syy};
-  const size_t smem = sizeof(double) * ((size_t)D + (2 + 2 * kBlockCk) * 8);
+  const size_t smem = sizeof(double) * ((size_t)D + (2 + 2 * kBlockCk) * kBlockWarps);
   const int kd = (D + kBlockThreads - 1) / kBlockThreads;
 #define TN_BLK(M, KD)                                                                              \
   do {                                                                                             \

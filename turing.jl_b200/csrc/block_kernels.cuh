@@ -16,10 +16,14 @@
 
 namespace tnuts {
 
-constexpr int kBlockThreads = 256;
+#ifndef TNUTS_BLOCK_THREADS
+#define TNUTS_BLOCK_THREADS 256
+#endif
+constexpr int kBlockThreads = TNUTS_BLOCK_THREADS;
+constexpr int kBlockWarps = kBlockThreads / 32;
 constexpr int kBlockCk = 12;  // checkpoint levels (max_depth <= 13)
 
-// block-wide sum of NR values; result valid in every thread.  red: [NR][8] doubles
+// block-wide sum of NR values; result valid in every thread.  red: [NR][kBlockWarps] doubles
 template <int NR>
 __device__ __forceinline__ void block_reduce(double (&v)[NR], double *red) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -31,14 +35,14 @@ __device__ __forceinline__ void block_reduce(double (&v)[NR], double *red) {
   __syncthreads();
   if (lane == 0) {
 #pragma unroll
-    for (int r = 0; r < NR; ++r) red[r * 8 + warp] = v[r];
+    for (int r = 0; r < NR; ++r) red[r * kBlockWarps + warp] = v[r];
   }
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[r * 8 + w];
+    for (int w = 0; w < kBlockWarps; ++w) s += red[r * kBlockWarps + w];
     v[r] = s;
   }
 }
@@ -52,12 +56,12 @@ __device__ __forceinline__ void block_reduce_n(double *v, int nv, double *red) {
   }
   __syncthreads();
   if (lane == 0)
-    for (int r = 0; r < nv; ++r) red[r * 8 + warp] = v[r];
+    for (int r = 0; r < nv; ++r) red[r * kBlockWarps + warp] = v[r];
   __syncthreads();
   for (int r = 0; r < nv; ++r) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[r * 8 + w];
+    for (int w = 0; w < kBlockWarps; ++w) s += red[r * kBlockWarps + w];
     v[r] = s;
   }
 }
@@ -237,7 +241,7 @@ k_block_run(ModelDev m, HierStatsDev hs, ChainState st, RunParams rp, double *dr
             long long keep, int ncol, double *theta_cm /* [C][keep][D] or null */) {
   extern __shared__ double smem[];
   double *sth = smem;             // [D]
-  double *red = smem + m.D;       // [(2 + 2*kBlockCk)][8]
+  double *red = smem + m.D;       // [(2 + 2*kBlockCk)][kBlockWarps]
   const int c = blockIdx.x, C = st.C, D = m.D, tid = threadIdx.x;
   if (st.status[c] != 0) return;
   const uint32_t gchain = (uint32_t)(rp.chain_offset + c);
