@@ -183,6 +183,7 @@ int main(int argc, char **argv) {
   int bad = 0;
   const bool big = argc > 1 && atoi(argv[1]) > 0;
   if (argc > 1 && atoi(argv[1]) == 2) return run_case(100000, 100, 4096, 1, true, false);
+  if (argc > 1 && atoi(argv[1]) == 3) return run_case(100000, 100, 128, 1, true, false) + run_case(100000, 100, 512, 1, true, false);
   bad += run_case(70, 100, 128, 4, false, false);
   bad += run_case(5000 + 17, 100, 200, 4, false, true);
   bad += run_case(3001, 128, 256, 3, false, false);
