@@ -398,5 +398,17 @@ def main():
         dist.destroy_process_group()
 
 
+def _only_json_on_stdout():
+    """Libraries below us write to the C-level stdout (NCCL prints its version banner there when
+    NCCL_DEBUG=VERSION is in the environment).  The contract is ONE JSON line on stdout: point fd 1
+    at stderr for the duration of the run and hand the real stdout to `print` only."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real
+
+
 if __name__ == "__main__":
+    _only_json_on_stdout()
     main()
+    sys.stdout.flush()
