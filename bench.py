@@ -96,6 +96,32 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local):
+    """Multi-GPU runs move 11.5 GB of draws per GPU and step to host memory: pin this process (and,
+    by first touch, its pinned host buffers) to the NUMA node its GPU hangs off, otherwise half of
+    the ranks copy across the socket interconnect.  Best effort; returns the node or None."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def build_workload(name, n_chains):
     import turing_jl_b200 as T
     if name == "eight_schools":
@@ -234,6 +260,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: the engine has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -365,6 +392,8 @@ def main():
                                  "the state in registers, so it is fp64-issue bound, see DESIGN.md"},
             "clocks": clk,
         }
+        if world > 1:
+            line["e2e"]["host_numa_binding"] = "rank pinned to its GPU's NUMA node" if numa is not None else "none"
         if args.workload == "logistic":
             Dm, Nr = model.D, model.N
             if args.tc:
