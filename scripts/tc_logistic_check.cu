@@ -1,8 +1,11 @@
 // Stand-alone check + timing of the tcgen05 logistic kernel (turing.jl_b200/csrc/logistic_tc.cuh)
 // against a plain fp64 CPU evaluation.  Development tool; the parity tests proper go through the
 // C ABI (tests/test_gpu_tc.py).
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o scripts/tc_logistic_check scripts/tc_logistic_check.cu
-//   scripts/tc_logistic_check            # correctness cases + config-3 timing
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -DTNUTS_TC_EXPERIMENTS -o scripts/tc_logistic_check scripts/tc_logistic_check.cu
+//   scripts/tc_logistic_check 1          # correctness cases + config-3 timing
+//   TC_XMODES=1 scripts/tc_logistic_check 2   # timing with pieces switched off (xmode bits: 1 no epilogue
+//                                              # arithmetic, 2 one MMA pass, 4 one X plane)
+//   TNUTS_TC_CHUNKS=n scripts/tc_logistic_check 3   # small chain counts with a forced row cut
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>

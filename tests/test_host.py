@@ -117,3 +117,22 @@ def test_chains_container():
     assert np.all(c["is_accept"] == 1.0)
     cc = T.chainscat([c, c])
     assert cc.size() == (5, 14, 6)
+
+
+def test_sghmc_sgld_constructors():
+    """test/mcmc/sghmc.jl:18-21, 35-38; src/mcmc/sghmc.jl:134-141 (decay rate check)"""
+    import turing_jl_b200 as T
+    a = T.SGHMC(learning_rate=0.01, momentum_decay=0.1)
+    assert isinstance(a, T.SGHMC) and a.algorithm == 3 and not a.adaptive
+    assert (a.eps, a.lam) == (0.01, 0.1)
+    g = T.SGLD(stepsize=T.PolynomialStepsize(0.25))
+    assert isinstance(g, T.SGLD) and g.algorithm == 4
+    assert (g.eps, g.delta, g.lam) == (0.25, 0.0, 0.55)
+    assert T.SGLD().stepsize.a == 0.01                      # default PolynomialStepsize(0.01)
+    f = T.PolynomialStepsize(0.5, 2.0, 0.6)
+    assert f(3) == pytest.approx(0.5 / 5.0 ** 0.6)
+    for bad in (0.5, 1.01, 0.0):
+        with pytest.raises(ValueError, match="decay rate"):
+            T.PolynomialStepsize(0.1, 0.0, bad)
+    with pytest.raises(TypeError):
+        T.SGHMC(0.01, 0.1)                                   # keyword-only, like the reference

@@ -225,6 +225,9 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
               int n_all, int rows_per_chunk, double *__restrict__ part /* [chunks][D+1][cap] */, int cap,
               float *__restrict__ dbg, int xmode) {
   constexpr int T = kT;
+#ifndef TNUTS_TC_EXPERIMENTS
+  xmode = 0;  // timing experiments (scripts/tc_logistic_check.cu) only: skip MMA passes / arithmetic / planes
+#endif
   static_assert(KP == 64 || KP == 128, "feature padding is 64 or 128");
   constexpr int NKB = KP / 64;                      // 128-byte boxes along the feature axis
   constexpr uint32_t BOX_BYTES = T * 128;           // [T rows][64 bf16]
@@ -556,7 +559,9 @@ inline bool plan(long long nrows, int D, Plan *p) {
 inline void cut_for(long long nrows, int n_tiles, int *chunks, int *rpc) {
   const long long tiles = (nrows + kT - 1) / kT;
   long long want = n_tiles >= 4 ? 37 : n_tiles >= 2 ? 74 : 148;
-  if (const char *ov = getenv("TNUTS_TC_CHUNKS")) want = atoi(ov);   // experiments only
+#ifdef TNUTS_TC_EXPERIMENTS
+  if (const char *ov = getenv("TNUTS_TC_CHUNKS")) want = atoi(ov);
+#endif
   if (want > tiles) want = tiles;
   const long long tpc = (tiles + want - 1) / want;
   *rpc = (int)(tpc * kT);
@@ -627,8 +632,14 @@ inline cudaError_t launch(const Data &d, long long nrows, int D, const double *t
 #define TN_TC_LAUNCH(KP_)                                                                                 \
   do {                                                                                                    \
     auto kfn = k_logistic_tc<KP_>;                                                                        \
-    cudaError_t s_ = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem); \
-    if (s_ != cudaSuccess) return s_;                                                                     \
+    static int attr_dev_ = -1; /* the attribute is per device: set it once per device, not per launch */ \
+    int dev_ = 0;                                                                                         \
+    cudaGetDevice(&dev_);                                                                                 \
+    if (attr_dev_ != dev_) {                                                                              \
+      cudaError_t s_ = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem); \
+      if (s_ != cudaSuccess) return s_;                                                                   \
+      attr_dev_ = dev_;                                                                                   \
+    }                                                                                                     \
     kfn<<<grid, kThreads, p.smem, stream>>>(d.map, d.yf, nrows, D, th, C, list, count, n_all, rpc,        \
                                             part, cap, dbg, xmode);                                       \
   } while (0)
