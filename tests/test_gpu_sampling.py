@@ -217,3 +217,15 @@ def test_dynamic_scheduling_is_bit_identical(built):
     np.testing.assert_array_equal(outs[0][1], outs[1][1])
     np.testing.assert_array_equal(outs[0][2], outs[1][2])
     assert outs[0][3] == outs[1][3]
+
+
+def test_sghmc_resume_carries_the_velocity(built):
+    """SGHMCState(logdensity, params, velocity) (src/mcmc/sghmc.jl:49-53): the state blob holds the
+    velocity, so a resumed SGHMC run continues the uninterrupted one bit for bit"""
+    m = T.models.synthetic_logistic(300, 5, seed=4)
+    spl = T.SGHMC(learning_rate=1e-4, momentum_decay=0.2)
+    full = T.sample(m, spl, T.MCMCThreads(), 41, 24, seed=5, verbose=False)
+    first = T.sample(m, spl, T.MCMCThreads(), 21, 24, seed=5, save_state=True, verbose=False)
+    rest = T.sample(m, spl, T.MCMCThreads(), 20, 24, initial_state=T.loadstate(first), verbose=False)
+    np.testing.assert_array_equal(first.value[1:], full.value[1:21])   # NaN stats columns compare equal
+    np.testing.assert_array_equal(rest.value, full.value[21:])
