@@ -30,7 +30,7 @@ struct TnutsConfig
     algorithm::Int32; delta::Float64; max_depth::Int32; delta_max::Float64; init_eps::Float64
     n_adapts::Int64; n_leapfrog::Int32; lambda::Float64; seed::UInt64
     n_chains::Int32; chain_offset::Int32; device::Int32; row_shards::Int32; row_rank::Int32
-    strategy::Int32; reserved::NTuple{5,Int32}
+    strategy::Int32; metric::Int32; reserved::NTuple{4,Int32}
 end
 const TNUTS_NSTAT = 9
 const STAT_NAMES = (:n_steps, :acceptance_rate, :log_density, :hamiltonian_energy,
@@ -67,7 +67,8 @@ mutable struct Engine
 end
 function Engine(spl::CUDANUTS, nchains::Int, nadapts::Int, seed::UInt64)
     cfg = Ref(TnutsConfig(0, spl.δ, spl.max_depth, spl.Δ_max, spl.ϵ, nadapts, 0, 0.0, seed,
-                          nchains, 0, spl.device, 1, 0, 0, ntuple(_ -> Int32(0), 5)))
+                          nchains, 0, spl.device, 1, 0, 0, Int32(0) #= TNUTS_METRIC_DIAG: NUTS default =#,
+                          ntuple(_ -> Int32(0), 4)))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(C_NULL, ccall((:tnuts_create, libtnuts), Cint, (Ref{TnutsConfig}, Ref{Ptr{Cvoid}}), cfg, h))
     d = spl.data

@@ -77,6 +77,13 @@ extern "C" {
  * fields: SGHMC  init_eps = learning_rate, lambda = momentum_decay;
  *         SGLD   init_eps = a, delta = b, lambda = gamma of PolynomialStepsize a / (t + b)^gamma.
  * Stats columns: n_steps = 1, log_density, step_size (= SGLD_stepsize); the others are NaN. */
+/* metricT (src/mcmc/hmc.jl:59-80, 285-327, 352-402): NUTS defaults to DiagEuclideanMetric, HMC and
+ * HMCDA to UnitEuclideanMetric.  With the unit metric the StanHMCAdaptor keeps its windows (the
+ * dual-averaging restarts at their ends: the NaiveHMCAdaptor branch of hmc.jl:456 is dead code, it
+ * compares an instance with a type) but the mass matrix stays the identity.  DenseEuclideanMetric
+ * is not implemented. */
+#define TNUTS_METRIC_DIAG 0
+#define TNUTS_METRIC_UNIT 1
 #define TNUTS_ALG_SGHMC 3
 #define TNUTS_ALG_SGLD 4
 
@@ -112,7 +119,8 @@ typedef struct {
   int32_t row_shards;   /* >1: data rows sharded over ranks (needs tnuts_comm_init)  */
   int32_t row_rank;
   int32_t strategy;     /* 0 auto, 1 one-thread-per-chain, 2 lock-step pump, 3 one-CTA-per-chain */
-  int32_t reserved[5];
+  int32_t metric;       /* TNUTS_METRIC_*: metricT of the sampler (src/mcmc/hmc.jl:178-179)  */
+  int32_t reserved[4];
 } tnuts_config;
 
 #define TNUTS_NSTAT 9

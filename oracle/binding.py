@@ -29,7 +29,7 @@ class _Config(C.Structure):
     _fields_ = [("delta", C.c_double), ("max_depth", C.c_int), ("delta_max", C.c_double),
                 ("init_eps", C.c_double), ("n_adapts", C.c_int64), ("sampler_mode", C.c_int),
                 ("seed", C.c_uint64), ("algorithm", C.c_int), ("n_leapfrog", C.c_int),
-                ("lambda_", C.c_double)]
+                ("lambda_", C.c_double), ("metric", C.c_int)]
 
 
 def build(force=False):
@@ -122,11 +122,12 @@ class OracleModel:
 
 
 def make_config(delta=0.65, max_depth=10, delta_max=1000.0, init_eps=0.0, n_adapts=0,
-                sampler_mode=1, seed=0, algorithm=0, n_leapfrog=0, lambda_=0.0):
+                sampler_mode=1, seed=0, algorithm=0, n_leapfrog=0, lambda_=0.0, metric=0):
     c = _Config()
     c.delta, c.max_depth, c.delta_max, c.init_eps = delta, max_depth, delta_max, init_eps
     c.n_adapts, c.sampler_mode, c.seed = n_adapts, sampler_mode, seed
     c.algorithm, c.n_leapfrog, c.lambda_ = algorithm, n_leapfrog, lambda_
+    c.metric = metric
     return c
 
 

@@ -793,7 +793,7 @@ static void adapt(const orc_config *cfg, int D, orc_chain *c, double alpha) {
   const int wend = is_window_end(i, splits, ns);
   if (i >= ws && i <= we) {
     welford_push(c, D, c->theta);
-    if (wend && c->wf_n >= 10) { /* n_min = 10 */
+    if (wend && c->wf_n >= 10 && cfg->metric != 1) { /* n_min = 10; UnitMassMatrix: no update */
       const double n = (double)c->wf_n;
       for (int d = 0; d < D; ++d)
         c->minv[d] = n / ((n + 5.0) * (n - 1.0)) * c->wf_m2[d] + 1e-3 * (5.0 / (n + 5.0));

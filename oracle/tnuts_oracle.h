@@ -91,6 +91,9 @@ typedef struct {
   int algorithm;      /* 0 = NUTS, 1 = HMC (fixed n_leapfrog), 2 = HMCDA (fixed lambda) */
   int n_leapfrog;     /* HMC */
   double lambda;      /* HMCDA */
+  int metric;         /* 0 = DiagEuclideanMetric (NUTS default), 1 = UnitEuclideanMetric (HMC / HMCDA
+                         default, src/mcmc/hmc.jl:76,308,323): windows and dual-averaging restarts
+                         as usual, the mass matrix stays the identity */
 } orc_config;
 
 #define ORC_NSTAT 9

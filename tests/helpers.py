@@ -62,4 +62,4 @@ def oracle_config(spl, n_adapts, seed, mode=1):
     return O.make_config(delta=spl.delta, max_depth=spl.max_depth, delta_max=spl.Delta_max,
                          init_eps=spl.eps, n_adapts=n_adapts, seed=seed, sampler_mode=mode,
                          algorithm=spl.algorithm, n_leapfrog=getattr(spl, "n_leapfrog", 0),
-                         lambda_=getattr(spl, "lam", 0.0))
+                         lambda_=getattr(spl, "lam", 0.0), metric=getattr(spl, "metric", 0))

@@ -209,3 +209,27 @@ def test_init_failure_message(built):
         T.sample(model, T.NUTS(0.8), T.MCMCThreads(), 10, 4, verbose=False)
     assert "failed to find valid initial parameters in 1000 tries" in str(ei.value)
     assert "https://turinglang.org/docs/uri/initial-parameters" in str(ei.value)
+
+
+@pytest.mark.parametrize("name,strategy", [("eight_schools", 1), ("eight_schools", 2), ("logistic_small", 2),
+                                           ("hier_small", 3)])
+def test_unit_metric_matches_oracle(built, name, strategy):
+    """metricT = UnitEuclideanMetric (the HMC / HMCDA default, selectable for NUTS): windows and
+    dual-averaging restarts as with the diagonal metric, identity mass matrix, on every strategy"""
+    model = small_models()[name]
+    for spl in (T.NUTS(120, 0.8, metricT="unit"), T.HMCDA(120, 0.65, 0.1)):
+        assert spl.metric == 1
+        C, n_tr = 64, 130
+        eng = T.Engine(model, spl, C, 120, seed=31, strategy=strategy)
+        eng.set_option("keep_theta", 1)
+        eng.init()
+        eng.run(n_tr, 1, 1)
+        out = eng.fetch(theta=True)
+        assert np.all(eng.inv_metric() == 1.0)
+        ref = O.sample_chains(oracle_of(model), oracle_config(spl, 120, 31), C, n_tr)
+        st = out["stats"].transpose(2, 0, 1)
+        np.testing.assert_array_equal(st[:, :8, 0], ref["stats"][:, :8, 0])          # n_steps
+        np.testing.assert_allclose(out["theta"].transpose(2, 0, 1)[:, :8], ref["theta"][:, :8], atol=1e-7)
+        # the adapted step sizes agree after all windows (loose: the chains decorrelate by rounding)
+        np.testing.assert_allclose(np.median(eng.stepsize()), np.median(ref["eps"]), rtol=0.05)
+        eng.close()

@@ -198,3 +198,17 @@ def test_sghmc_and_sgld_oracle_semantics():
     assert abs(r["params"][:, :, 1].mean() - 7 / 6) < 0.1
     # the user-space log-prob identity holds for these samplers too (test_chain_logp_metadata)
     np.testing.assert_allclose(r["logp"][:, :, 2], r["logp"][:, :, 0] + r["logp"][:, :, 1], rtol=1e-13)
+
+
+def test_unit_metric_keeps_identity_mass_matrix():
+    """HMCDA / HMC default to UnitEuclideanMetric (src/mcmc/hmc.jl:76, 308, 323): the Stan windows and
+    the dual-averaging restarts run as for NUTS, the mass matrix never moves"""
+    m = O.OracleModel(O.EIGHT_SCHOOLS, D=10, N=8, y=[28, 8, -3, 7, -1, 1, 18, 12],
+                      sigma=[15, 10, 16, 11, 9, 11, 10, 18], hyper=(5.0, 5.0))
+    unit = O.sample_chains(m, O.make_config(delta=0.8, n_adapts=150, seed=2, metric=1), 4, 160)
+    diag = O.sample_chains(m, O.make_config(delta=0.8, n_adapts=150, seed=2, metric=0), 4, 160)
+    assert np.all(unit["minv"] == 1.0)
+    assert np.all(diag["minv"] != 1.0)
+    # before the first window ends (iteration 100 of 150: windows 76-100) the two runs are identical
+    np.testing.assert_array_equal(unit["theta"][:, :99], diag["theta"][:, :99])
+    assert not np.array_equal(unit["theta"][:, 120:], diag["theta"][:, 120:])

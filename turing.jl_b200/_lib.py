@@ -31,7 +31,7 @@ class TnutsConfig(C.Structure):
                 ("n_leapfrog", C.c_int32), ("lambda_", C.c_double), ("seed", C.c_uint64),
                 ("n_chains", C.c_int32), ("chain_offset", C.c_int32), ("device", C.c_int32),
                 ("row_shards", C.c_int32), ("row_rank", C.c_int32), ("strategy", C.c_int32),
-                ("reserved", C.c_int32 * 5)]
+                ("metric", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class TnutsError(RuntimeError):

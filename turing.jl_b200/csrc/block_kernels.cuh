@@ -522,7 +522,7 @@ k_block_run(ModelDev m, HierStatsDev hs, ChainState st, RunParams rp, double *dr
             mean += delta / nw;
             m2 += delta * (th[k] - mean);
             if (wend) {
-              if (wf_n >= 10) minv[k] = nw / ((nw + 5.0) * (nw - 1.0)) * m2 + 1e-3 * (5.0 / (nw + 5.0));
+              if (wf_n >= 10 && !rp.unit_metric) minv[k] = nw / ((nw + 5.0) * (nw - 1.0)) * m2 + 1e-3 * (5.0 / (nw + 5.0));
               mean = 0.0;
               m2 = 0.0;
             }

@@ -120,7 +120,7 @@ k_chain_run_flat(SmallData md, ChainState st, DrawBuffers out, RunParams rp,
                 mean += delta / nw;
                 m2 += delta * (th[d] - mean);
                 if (wend) {
-                  if (wf_n >= 10) minv[d] = nw / ((nw + 5.0) * (nw - 1.0)) * m2 + 1e-3 * (5.0 / (nw + 5.0));
+                  if (wf_n >= 10 && !rp.unit_metric) minv[d] = nw / ((nw + 5.0) * (nw - 1.0)) * m2 + 1e-3 * (5.0 / (nw + 5.0));
                   mean = 0.0;
                   m2 = 0.0;
                 }

@@ -408,7 +408,7 @@ __device__ __forceinline__ void chain_run_range(const SmallData &md, const Chain
           mean += delta / n;
           m2 += delta * (th[d] - mean);
           if (wend) {
-            if (wf_n >= 10) minv[d] = n / ((n + 5.0) * (n - 1.0)) * m2 + 1e-3 * (5.0 / (n + 5.0));
+            if (wf_n >= 10 && !rp.unit_metric) minv[d] = n / ((n + 5.0) * (n - 1.0)) * m2 + 1e-3 * (5.0 / (n + 5.0));
             mean = 0.0;
             m2 = 0.0;
           }

@@ -174,6 +174,8 @@ int tnuts_create(const tnuts_config *cfg, tnuts_engine **out) {
     return set_error(nullptr, TNUTS_E_CUDA,
                      std::string("tnuts_create: libtnuts is built for sm_100a only; device is ") +
                          prop.name);
+  if (cfg->metric != TNUTS_METRIC_DIAG && cfg->metric != TNUTS_METRIC_UNIT)
+    return set_error(nullptr, TNUTS_E_UNSUPPORTED, "tnuts_create: metric must be TNUTS_METRIC_DIAG or TNUTS_METRIC_UNIT (DenseEuclideanMetric is not implemented)");
   Engine *e = new Engine();
   e->cfg = *cfg;
   e->device = cfg->device;
@@ -200,6 +202,7 @@ int tnuts_create(const tnuts_config *cfg, tnuts_engine **out) {
   rp.seed = cfg->seed;
   rp.chain_offset = cfg->chain_offset;
   rp.flat_batch = 12;
+  rp.unit_metric = cfg->metric == TNUTS_METRIC_UNIT ? 1 : 0;
   window_schedule(cfg->n_adapts, rp);
   *out = (tnuts_engine *)e;
   return TNUTS_OK;

@@ -523,7 +523,7 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
           mean += delta / nw;
           m2 += delta * (th - mean);
           if (wend) {
-            if (wf_n + 1 >= 10)
+            if (wf_n + 1 >= 10 && !rp.unit_metric)
               minv_[o] = nw / ((nw + 5.0) * (nw - 1.0)) * m2 + 1e-3 * (5.0 / (nw + 5.0));
             mean = 0.0;
             m2 = 0.0;

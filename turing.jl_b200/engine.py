@@ -25,6 +25,7 @@ class Engine:
         cfg.n_adapts = int(n_adapts)
         cfg.n_leapfrog = getattr(spl, "n_leapfrog", 0)
         cfg.lambda_ = getattr(spl, "lam", 0.0)
+        cfg.metric = getattr(spl, "metric", 0)
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.n_chains = int(n_chains)
         cfg.chain_offset = int(chain_offset)

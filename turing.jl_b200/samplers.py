@@ -3,6 +3,19 @@ meaning (src/mcmc/hmc.jl:59-80 HMC, :285-327 HMCDA, :352-402 NUTS; src/mcmc/sghm
 PolynomialStepsize; src/Turing.jl:105-107)."""
 
 
+METRICS = {"diag": 0, "DiagEuclideanMetric": 0, "unit": 1, "UnitEuclideanMetric": 1}
+
+
+def _metric_id(metricT):
+    """metricT of the reference's constructors (AHMC.DiagEuclideanMetric / UnitEuclideanMetric)"""
+    if metricT in ("dense", "DenseEuclideanMetric"):
+        raise NotImplementedError("DenseEuclideanMetric is not implemented by the engine")
+    try:
+        return METRICS[metricT]
+    except KeyError:
+        raise ValueError("unknown metricT %r" % (metricT,)) from None
+
+
 class Hamiltonian:
     """`allow_discrete_variables = false` (src/mcmc/hmc.jl:4); InitFromUniform (:82)."""
     algorithm = -1
@@ -27,9 +40,7 @@ class NUTS(Hamiltonian):
             n_adapts, delta = int(args[0]), float(args[1])
         else:
             raise TypeError("NUTS takes at most (n_adapts, delta)")
-        if metricT != "diag":
-            raise NotImplementedError("only DiagEuclideanMetric (the NUTS default, hmc.jl:383) "
-                                      "is implemented by the engine")
+        self.metric = _metric_id(metricT)
         self.n_adapts, self.delta = n_adapts, float(delta)
         self.max_depth, self.Delta_max, self.eps = int(max_depth), float(Delta_max), float(init_eps)
 
@@ -39,7 +50,8 @@ class HMC(Hamiltonian):
     algorithm = 1
     adaptive = False
 
-    def __init__(self, eps, n_leapfrog):
+    def __init__(self, eps, n_leapfrog, metricT="unit"):
+        self.metric = _metric_id(metricT)     # no adaptation at all: the metric stays as created
         self.eps, self.n_leapfrog = float(eps), int(n_leapfrog)
         self.n_adapts, self.delta = 0, 0.0
         self.max_depth, self.Delta_max = 10, 1000.0
@@ -50,7 +62,8 @@ class HMCDA(Hamiltonian):
     algorithm = 2
     adaptive = True
 
-    def __init__(self, *args, init_eps=0.0):
+    def __init__(self, *args, init_eps=0.0, metricT="unit"):
+        self.metric = _metric_id(metricT)     # default UnitEuclideanMetric (hmc.jl:308, 323)
         if len(args) == 2:
             n_adapts, delta, lam = -1, args[0], args[1]
         elif len(args) == 3:
