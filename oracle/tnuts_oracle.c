@@ -916,11 +916,10 @@ int orc_chain_init(const orc_model *m, const orc_config *cfg, uint32_t chain,
   if (cfg->algorithm >= 3) { /* SGHMC / SGLD: velocity zero, no step-size search */
     for (int d = 0; d < D; ++d) c->wf_mean[d] = 0.0;
     c->eps = cfg->init_eps;
-  } else if (cfg->init_eps == 0.0 && cfg->algorithm != 1)
+  } else if (cfg->init_eps == 0.0) /* iszero(spl.eps): every Hamiltonian sampler, hmc.jl:189-194 */
     c->eps = orc_find_good_stepsize(m, cfg, chain, c->theta, c->minv, &c->n_grad_evals);
   else
     c->eps = cfg->init_eps;
-  if (cfg->init_eps == 0.0 && cfg->algorithm == 1) c->eps = 0.1;
   c->da_eps = c->eps;
   da_reset(c); /* StepSizeAdaptor(delta, eps): mu = log(10 eps) */
   return 0;

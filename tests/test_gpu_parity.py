@@ -233,3 +233,16 @@ def test_unit_metric_matches_oracle(built, name, strategy):
         # the adapted step sizes agree after all windows (loose: the chains decorrelate by rounding)
         np.testing.assert_allclose(np.median(eng.stepsize()), np.median(ref["eps"]), rtol=0.05)
         eng.close()
+
+
+@pytest.mark.parametrize("name,strategy", [("gdemo", 1), ("gdemo", 2), ("hier_small", 3)])
+def test_hmc_with_zero_step_size_searches_one(built, name, strategy):
+    """src/mcmc/hmc.jl:189-194: `iszero(spl.eps)` runs find_good_stepsize for HMC as well"""
+    model = small_models()[name]
+    spl = T.HMC(0.0, 4)
+    eng = T.Engine(model, spl, 48, 0, seed=6, strategy=strategy)
+    eng.init()
+    ref = O.sample_chains(oracle_of(model), oracle_config(spl, 0, 6), 48, 0)
+    np.testing.assert_allclose(eng.stepsize(), ref["eps"], rtol=1e-9)
+    assert len(np.unique(eng.stepsize())) > 1        # searched per chain, not a constant
+    eng.close()

@@ -615,10 +615,9 @@ __global__ void __launch_bounds__(kChainBlock) k_chain_init(SmallData md, ChainS
   st.init_tries[c] = tries;
   st.status[c] = ok ? 0 : 1;
   double eps = init_eps;
-  if (ok && init_eps == 0.0) {
-    if (rp.algorithm == TNUTS_ALG_HMC) eps = 0.1;
-    else eps = find_good_stepsize_d<M>(md, rp, gchain, th, g, lp, minv, ngrad);
-  }
+  // iszero(spl.eps) => AHMC.find_good_stepsize for every Hamiltonian sampler, HMC included
+  // (src/mcmc/hmc.jl:189-194)
+  if (ok && init_eps == 0.0) eps = find_good_stepsize_d<M>(md, rp, gchain, th, g, lp, minv, ngrad);
 #pragma unroll
   for (int d = 0; d < D; ++d) {
     const size_t o = (size_t)d * C + c;

@@ -552,11 +552,8 @@ int lockstep_init(Engine *e, const double *theta0_dev) {
     // no step-size search; the velocity (st.wf_mean) was zeroed by k_ls_init_state
     k_ls_set_eps<<<(C + 255) / 256, 256, 0, e->stream>>>(st, e->cfg.init_eps);
     e->launches += 1;
-  } else if (e->cfg.init_eps == 0.0 && e->cfg.algorithm == TNUTS_ALG_HMC) {
-    k_ls_set_eps<<<(C + 255) / 256, 256, 0, e->stream>>>(st, 0.1);
-    e->launches += 1;
   } else if (e->cfg.init_eps == 0.0) {
-    // find_good_stepsize for every chain
+    // find_good_stepsize for every chain (iszero(spl.eps), HMC included: src/mcmc/hmc.jl:189-194)
     k_ls_fs_begin<<<tiles(C), kTileThreads, 0, e->stream>>>(st, *ls, e->rp);
     e->launches += 1;
     int left = C;
