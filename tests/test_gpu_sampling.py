@@ -229,3 +229,19 @@ def test_sghmc_resume_carries_the_velocity(built):
     rest = T.sample(m, spl, T.MCMCThreads(), 20, 24, initial_state=T.loadstate(first), verbose=False)
     np.testing.assert_array_equal(first.value[1:], full.value[1:21])   # NaN stats columns compare equal
     np.testing.assert_array_equal(rest.value, full.value[21:])
+
+
+def test_warns_after_ten_failed_initial_draws(built):
+    """src/mcmc/abstractmcmc.jl:62-69: a warning at the tenth failed attempt, then the error with the
+    initial-parameters URL once 1000 attempts are spent (test/mcmc/hmc.jl:284-296)"""
+    model = T.GDemo(float("nan"), 2.0)          # lp is NaN everywhere
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        with pytest.raises(RuntimeError, match="initial-parameters"):
+            T.sample(model, T.NUTS(5, 0.8), T.MCMCThreads(), 4, 8, seed=3, verbose=False)
+    assert any("failed to find valid initial parameters in 10 tries" in str(x.message) for x in w)
+    # a healthy model does not warn
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        T.sample(T.gdemo_default(), T.NUTS(5, 0.8), T.MCMCThreads(), 4, 8, seed=3, verbose=False)
+    assert not any("initial parameters" in str(x.message) for x in w)

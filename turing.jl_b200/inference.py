@@ -150,7 +150,14 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
                 e.set_state(initial_state["blobs"][i])
                 n_tr, first_keep = N * thinning, thinning
             else:
-                e.init(None if theta0 is None else theta0[lo:hi])
+                try:
+                    e.init(None if theta0 is None else theta0[lo:hi])
+                finally:
+                    if theta0 is None and e.init_tries_max >= 10:
+                        # src/mcmc/abstractmcmc.jl:62-63 (emitted at the tenth failed attempt)
+                        warnings.warn("failed to find valid initial parameters in 10 tries; consider "
+                                      "providing a different initialisation strategy with the "
+                                      "`initial_params` keyword")
                 if _discard == 0:
                     # first sample = initial parameters, no sampler stats (test/mcmc/hmc.jl:173-197)
                     th = e.theta()
