@@ -1,3 +1,4 @@
+"""times the logistic gradient kernels (fp64 DMMA path) for several shapes; profiles/ cites it"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
