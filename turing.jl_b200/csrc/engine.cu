@@ -3,6 +3,9 @@
 #include "engine.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -24,17 +27,18 @@ int set_error(Engine *e, int code, const std::string &msg) {
 
 template <class T>
 static int dev_alloc(Engine *e, std::vector<void *> &pool, T **p, size_t n) {
+  // From the device's stream-ordered pool, like the draw buffer: the ~25 state arrays of an engine
+  // are recycled by the next engine of the process.  With cudaMalloc / cudaFree, tnuts_destroy
+  // stalled for 40-500 ms in one job out of three (the driver unmapping them one by one).
   void *q = nullptr;
-  TN_CUDA(e, cudaMalloc(&q, (n ? n : 1) * sizeof(T)));
+  TN_CUDA(e, cudaMallocAsync(&q, (n ? n : 1) * sizeof(T), e->stream));
   TN_CUDA(e, cudaMemsetAsync(q, 0, (n ? n : 1) * sizeof(T), e->stream));
   pool.push_back(q);
   *p = (T *)q;
   return TNUTS_OK;
 }
-// (freeing these cudaMalloc'ed arrays with cudaFreeAsync was tried: tnuts_destroy then took up to
-// 2 s instead of the occasional 0.3 s)
-static void free_pool(std::vector<void *> &pool) {
-  for (void *p : pool) cudaFree(p);
+static void free_pool(std::vector<void *> &pool, cudaStream_t stream) {
+  for (void *p : pool) cudaFreeAsync(p, stream);
   pool.clear();
 }
 
@@ -214,12 +218,25 @@ int tnuts_destroy(tnuts_engine *h) {
   if (!h) return TNUTS_OK;
   Engine *e = (Engine *)h;
   cudaSetDevice(e->device);
+  static const bool trace = getenv("TNUTS_DESTROY_TRACE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  const auto t0 = now();
   cudaStreamSynchronize(e->stream);
+  const auto t1 = now();
   lockstep_destroy(e);
   diagnostics_destroy(e);
   comm_destroy(e);
-  free_pool(e->model_allocs);
-  free_pool(e->state_allocs);
+  const auto t2 = now();
+  free_pool(e->model_allocs, e->stream);
+  const auto t3 = now();
+  free_pool(e->state_allocs, e->stream);
+  const auto t4 = now();
+  if (trace)
+    fprintf(stderr, "[tnuts destroy] sync %.1f ms, strategy/diag/comm %.1f ms, model frees %.1f ms, state frees %.1f ms\n",
+            ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4));
   for (double *p : {e->out.draws, e->out.theta})
     if (p) cudaFreeAsync(p, e->stream);
   if (e->dyn_work) cudaFreeAsync(e->dyn_work, e->stream);
@@ -267,7 +284,7 @@ static int set_model_impl(tnuts_engine *h, const tnuts_model *m, bool device_ptr
       return TNUTS_OK;
     }
     void *q = nullptr;
-    TN_CUDA(e, cudaMalloc(&q, bytes));
+    TN_CUDA(e, cudaMallocAsync(&q, bytes, e->stream));
     e->model_allocs.push_back(q);
     TN_CUDA(e, cudaMemcpyAsync(q, src, bytes, cudaMemcpyHostToDevice, e->stream));
     *dst = q;
