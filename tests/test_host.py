@@ -136,3 +136,25 @@ def test_sghmc_sgld_constructors():
             T.PolynomialStepsize(0.1, 0.0, bad)
     with pytest.raises(TypeError):
         T.SGHMC(0.01, 0.1)                                   # keyword-only, like the reference
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the driver's reference arm) runs without a GPU and prints exactly
+    ONE JSON line on stdout with the contract's keys"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--ref-budget", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "grad_evals_per_sec" and d["unit"] == "grad_evals/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert "configs[1]" in d["config"]["workload"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "grad_evals/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}
