@@ -120,7 +120,9 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
     bounds = [n_chains * i // ndev for i in range(ndev + 1)]
 
     if chunk_draws is None:
-        chunk_draws = max(1, -(-N // 10))
+        # the kept draws leave in segments while the next one computes; after warm-up the copy is the
+        # slower of the two (PCIe), so small segments only matter for how early the first copy starts
+        chunk_draws = max(1, -(-N // 40))
     t_start = time.perf_counter()
     tm = {}
     engines = []
