@@ -389,14 +389,55 @@ static void phase_copy(phase *dst, const phase *src, int D) {
   dst->H = src->H;
 }
 
+/* DenseEuclideanMetric(M^-1) ([dep AdvancedHMC], restated from memory like App. A): the metric
+ * stores M^-1 and the upper Cholesky factor U of M^-1 (M^-1 = U'U); momentum r = U \ randn(D)
+ * (so cov(r) = M), kinetic energy r' M^-1 r / 2, dH/dr = M^-1 r, the U-turn products use M^-1 r.
+ * The active chain's dense metric sits in a thread-local context (one chain per thread); when it is
+ * set, the `minv` argument of the functions below is ignored.  Row-major [D][D]. */
+static __thread const double *tl_dense_minv = NULL, *tl_dense_chol = NULL;
+
+static void dense_apply(int D, const double *A, const double *r, double *out) {
+  for (int i = 0; i < D; ++i) {
+    double s = 0;
+    for (int j = 0; j < D; ++j) s += A[(size_t)i * D + j] * r[j];
+    out[i] = s;
+  }
+}
+/* upper Cholesky factor U of the symmetric positive definite A (A = U'U); 0 on success */
+static int dense_chol_upper(int D, const double *A, double *U) {
+  memset(U, 0, sizeof(double) * (size_t)D * D);
+  for (int j = 0; j < D; ++j) {
+    double s = A[(size_t)j * D + j];
+    for (int k = 0; k < j; ++k) s -= U[(size_t)k * D + j] * U[(size_t)k * D + j];
+    if (!(s > 0)) return -1;
+    const double ujj = sqrt(s);
+    U[(size_t)j * D + j] = ujj;
+    for (int i = j + 1; i < D; ++i) {
+      double t = A[(size_t)j * D + i];
+      for (int k = 0; k < j; ++k) t -= U[(size_t)k * D + j] * U[(size_t)k * D + i];
+      U[(size_t)j * D + i] = t / ujj;
+    }
+  }
+  return 0;
+}
+
 /* energy with the non-finite rule of AdvancedHMC's PhasePoint constructor: any non-finite
  * lp, gradient or kinetic energy makes H = +Inf (App. A.1) */
 static double energy(int D, double lp, const double *grad, const double *r, const double *minv) {
   double k = 0;
   int ok = isfinite(lp);
-  for (int d = 0; d < D; ++d) {
-    k += minv[d] * r[d] * r[d];
-    ok = ok && isfinite(grad[d]);
+  if (tl_dense_minv) {
+    for (int i = 0; i < D; ++i) {
+      double s = 0;
+      for (int j = 0; j < D; ++j) s += tl_dense_minv[(size_t)i * D + j] * r[j];
+      k += r[i] * s;
+      ok = ok && isfinite(grad[i]);
+    }
+  } else {
+    for (int d = 0; d < D; ++d) {
+      k += minv[d] * r[d] * r[d];
+      ok = ok && isfinite(grad[d]);
+    }
   }
   k *= 0.5;
   if (!ok || !isfinite(k)) return INFINITY;
@@ -409,7 +450,14 @@ static void leapfrog(const orc_model *m, phase *z, const double *minv, double ep
   const int D = m->D;
   const double half = 0.5 * eps;
   for (int d = 0; d < D; ++d) z->r[d] = z->r[d] + half * z->grad[d];
-  for (int d = 0; d < D; ++d) z->theta[d] = z->theta[d] + eps * (minv[d] * z->r[d]);
+  if (tl_dense_minv) {
+    double *v = (double *)malloc(sizeof(double) * (size_t)D);
+    dense_apply(D, tl_dense_minv, z->r, v);
+    for (int d = 0; d < D; ++d) z->theta[d] = z->theta[d] + eps * v[d];
+    free(v);
+  } else {
+    for (int d = 0; d < D; ++d) z->theta[d] = z->theta[d] + eps * (minv[d] * z->r[d]);
+  }
   z->lp = orc_logdensity_and_gradient(m, z->theta, z->grad);
   if (n_grad) ++*n_grad;
   for (int d = 0; d < D; ++d) z->r[d] = z->r[d] + half * z->grad[d];
@@ -445,6 +493,20 @@ static double logaddexp(double a, double b) {
 static void draw_momentum(const orc_config *cfg, uint32_t chain, uint32_t iter, uint32_t slot,
                           int D, const double *minv, double *r) {
   /* r = randn(D) ./ sqrt.(M^-1)  (App. A.1) */
+  if (tl_dense_chol) { /* dense: solve U r = z by back substitution */
+    for (int p = 0; 2 * p < D; ++p) {
+      double z[2];
+      orc_normal2(cfg->seed, chain, iter, slot, (uint32_t)p, z);
+      r[2 * p] = z[0];
+      if (2 * p + 1 < D) r[2 * p + 1] = z[1];
+    }
+    for (int d = D - 1; d >= 0; --d) {
+      double t = r[d];
+      for (int e = d + 1; e < D; ++e) t -= tl_dense_chol[(size_t)d * D + e] * r[e];
+      r[d] = t / tl_dense_chol[(size_t)d * D + d];
+    }
+    return;
+  }
   for (int p = 0; 2 * p < D; ++p) {
     double z[2];
     orc_normal2(cfg->seed, chain, iter, slot, (uint32_t)p, z);
@@ -507,6 +569,18 @@ typedef struct {
 static int uturn(int D, const double *rho, const double *rl, const double *rr, const double *minv) {
   /* GeneralisedNoUTurn: dot(rho, M^-1 r_left) <= 0 || dot(rho, M^-1 r_right) <= 0 */
   double a = 0, b = 0;
+  if (tl_dense_minv) {
+    for (int i = 0; i < D; ++i) {
+      double sl = 0, sr = 0;
+      for (int j = 0; j < D; ++j) {
+        sl += tl_dense_minv[(size_t)i * D + j] * rl[j];
+        sr += tl_dense_minv[(size_t)i * D + j] * rr[j];
+      }
+      a += rho[i] * sl;
+      b += rho[i] * sr;
+    }
+    return (a <= 0) || (b <= 0);
+  }
   for (int d = 0; d < D; ++d) {
     a += rho[d] * (minv[d] * rl[d]);
     b += rho[d] * (minv[d] * rr[d]);
@@ -783,6 +857,19 @@ static void welford_push(orc_chain *c, int D, const double *theta) {
   }
 }
 
+/* WelfordCov ([dep AdvancedHMC]): delta = s - mu; mu += delta / n; M += (s - mu_new) delta' */
+static void welford_cov_push(orc_chain *c, int D, const double *theta) {
+  c->wf_n += 1;
+  double *delta = (double *)malloc(sizeof(double) * (size_t)D);
+  for (int d = 0; d < D; ++d) {
+    delta[d] = theta[d] - c->wf_mean[d];
+    c->wf_mean[d] += delta[d] / (double)c->wf_n;
+  }
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) c->wf_cov[(size_t)i * D + j] += (theta[i] - c->wf_mean[i]) * delta[j];
+  free(delta);
+}
+
 static void adapt(const orc_config *cfg, int D, orc_chain *c, double alpha) {
   /* AHMC.adapt!(h, kernel, adaptor, i, nadapts, theta, alpha): src/mcmc/hmc.jl:229-241 */
   const int64_t i = c->iter;
@@ -791,7 +878,20 @@ static void adapt(const orc_config *cfg, int D, orc_chain *c, double alpha) {
   const int ns = orc_window_splits(cfg->n_adapts, &ws, &we, splits, 64);
   da_adapt(c, cfg->delta, alpha);
   const int wend = is_window_end(i, splits, ns);
-  if (i >= ws && i <= we) {
+  if (i >= ws && i <= we && cfg->metric == 2) {
+    /* MassMatrixAdaptor(DenseEuclideanMetric): regularised covariance
+     * (n / (n + 5)) M / (n - 1) + 1e-3 (5 / (n + 5)) I, then the metric is renewed (new Cholesky) */
+    welford_cov_push(c, D, c->theta);
+    if (wend && c->wf_n >= 10) {
+      const double n = (double)c->wf_n;
+      for (int a = 0; a < D; ++a)
+        for (int b = 0; b < D; ++b)
+          c->minv_dense[(size_t)a * D + b] = n / ((n + 5.0) * (n - 1.0)) * c->wf_cov[(size_t)a * D + b] +
+                                             (a == b ? 1e-3 * (5.0 / (n + 5.0)) : 0.0);
+      dense_chol_upper(D, c->minv_dense, c->chol);
+      for (int d = 0; d < D; ++d) c->minv[d] = c->minv_dense[(size_t)d * D + d];
+    }
+  } else if (i >= ws && i <= we) {
     welford_push(c, D, c->theta);
     if (wend && c->wf_n >= 10 && cfg->metric != 1) { /* n_min = 10; UnitMassMatrix: no update */
       const double n = (double)c->wf_n;
@@ -804,6 +904,7 @@ static void adapt(const orc_config *cfg, int D, orc_chain *c, double alpha) {
     c->wf_n = 0;
     memset(c->wf_mean, 0, sizeof(double) * (size_t)D);
     memset(c->wf_m2, 0, sizeof(double) * (size_t)D);
+    if (c->wf_cov) memset(c->wf_cov, 0, sizeof(double) * (size_t)D * D);
   }
   if (i == cfg->n_adapts) c->da_eps = exp(c->da_xbar); /* finalize! */
   c->eps = c->da_eps;
@@ -876,6 +977,7 @@ orc_chain *orc_chain_new(int D) {
 void orc_chain_free(orc_chain *c) {
   if (!c) return;
   free(c->theta);
+  free(c->minv_dense); /* the three dense arrays are one block */
   free(c);
 }
 
@@ -883,6 +985,18 @@ int orc_chain_init(const orc_model *m, const orc_config *cfg, uint32_t chain,
                    const double *theta0, orc_chain *c) {
   const int D = m->D;
   for (int d = 0; d < D; ++d) c->minv[d] = 1.0; /* DiagEuclideanMetric(D): ones */
+  tl_dense_minv = tl_dense_chol = NULL;
+  if (cfg->metric == 2) { /* DenseEuclideanMetric(D): identity */
+    if (!c->minv_dense) {
+      c->minv_dense = (double *)calloc((size_t)D * D * 3, sizeof(double));
+      c->chol = c->minv_dense + (size_t)D * D;
+      c->wf_cov = c->chol + (size_t)D * D;
+    }
+    memset(c->minv_dense, 0, sizeof(double) * (size_t)D * D * 3);
+    for (int d = 0; d < D; ++d) c->minv_dense[(size_t)d * D + d] = c->chol[(size_t)d * D + d] = 1.0;
+    tl_dense_minv = c->minv_dense;
+    tl_dense_chol = c->chol;
+  }
   c->iter = 0;
   c->n_grad_evals = 0;
   c->wf_n = 0;
@@ -912,7 +1026,10 @@ int orc_chain_init(const orc_model *m, const orc_config *cfg, uint32_t chain,
       c->init_tries = t + 1;
     }
   }
-  if (!ok) return -1;
+  if (!ok) {
+    tl_dense_minv = tl_dense_chol = NULL;
+    return -1;
+  }
   if (cfg->algorithm >= 3) { /* SGHMC / SGLD: velocity zero, no step-size search */
     for (int d = 0; d < D; ++d) c->wf_mean[d] = 0.0;
     c->eps = cfg->init_eps;
@@ -922,6 +1039,7 @@ int orc_chain_init(const orc_model *m, const orc_config *cfg, uint32_t chain,
     c->eps = cfg->init_eps;
   c->da_eps = c->eps;
   da_reset(c); /* StepSizeAdaptor(delta, eps): mu = log(10 eps) */
+  tl_dense_minv = tl_dense_chol = NULL;
   return 0;
 }
 
@@ -974,8 +1092,13 @@ void orc_chain_step(const orc_model *m, const orc_config *cfg, uint32_t chain, o
     c->iter += 1;
     return;
   }
+  if (cfg->metric == 2) {
+    tl_dense_minv = c->minv_dense;
+    tl_dense_chol = c->chol;
+  }
   if (cfg->algorithm == 0) nuts_transition(m, cfg, chain, c, stats);
   else hmc_transition(m, cfg, chain, c, stats);
+  tl_dense_minv = tl_dense_chol = NULL;
   c->iter += 1;
   if (cfg->algorithm != 1) adapt(cfg, m->D, c, stats[ST_ACC]);
 }

@@ -91,7 +91,8 @@ typedef struct {
   int algorithm;      /* 0 = NUTS, 1 = HMC (fixed n_leapfrog), 2 = HMCDA (fixed lambda) */
   int n_leapfrog;     /* HMC */
   double lambda;      /* HMCDA */
-  int metric;         /* 0 = DiagEuclideanMetric (NUTS default), 1 = UnitEuclideanMetric (HMC / HMCDA
+  int metric;         /* 0 = DiagEuclideanMetric (NUTS default), 2 = DenseEuclideanMetric,
+                         1 = UnitEuclideanMetric (HMC / HMCDA
                          default, src/mcmc/hmc.jl:76,308,323): windows and dual-averaging restarts
                          as usual, the mass matrix stays the identity */
 } orc_config;
@@ -110,6 +111,8 @@ typedef struct {
   double da_mu, da_xbar, da_hbar, da_eps; int64_t da_m;
   /* Welford variance estimator */
   int64_t wf_n; double *wf_mean, *wf_m2; /* [D] */
+  /* DenseEuclideanMetric (cfg->metric == 2): M^-1, its upper Cholesky factor, Welford M; [D][D] */
+  double *minv_dense, *chol, *wf_cov;
   /* iteration counter i of src/mcmc/hmc.jl:228 */
   int64_t iter;
   int64_t n_grad_evals;
