@@ -80,10 +80,13 @@ extern "C" {
 /* metricT (src/mcmc/hmc.jl:59-80, 285-327, 352-402): NUTS defaults to DiagEuclideanMetric, HMC and
  * HMCDA to UnitEuclideanMetric.  With the unit metric the StanHMCAdaptor keeps its windows (the
  * dual-averaging restarts at their ends: the NaiveHMCAdaptor branch of hmc.jl:456 is dead code, it
- * compares an instance with a type) but the mass matrix stays the identity.  DenseEuclideanMetric
- * is not implemented. */
+ * compares an instance with a type) but the mass matrix stays the identity.  DenseEuclideanMetric:
+ * M^-1 [D][D] per chain, momentum through its Cholesky factor, Welford covariance with the Stan
+ * regulariser at the window ends. */
 #define TNUTS_METRIC_DIAG 0
 #define TNUTS_METRIC_UNIT 1
+#define TNUTS_METRIC_DENSE 2   /* thread-per-chain strategy (gdemo, README regression, eight schools,
+                                  small standard normal) with NUTS / HMC / HMCDA */
 #define TNUTS_ALG_SGHMC 3
 #define TNUTS_ALG_SGLD 4
 
@@ -190,6 +193,9 @@ int tnuts_get_theta(tnuts_engine *e, double *theta);
 int tnuts_constrain(tnuts_engine *e, const double *theta, int64_t n, double *params, double *logp);
 int tnuts_get_stepsize(tnuts_engine *e, double *eps /* [n_chains] */);
 int tnuts_get_inv_metric(tnuts_engine *e, double *minv /* [n_chains][D] */);
+/* TNUTS_METRIC_DENSE: the full M^-1 of every chain, [n_chains][D][D] row-major (tnuts_get_inv_metric
+ * reports its diagonal) */
+int tnuts_get_dense_inv_metric(tnuts_engine *e, double *minv /* [n_chains][D][D] */);
 
 /* LogDensityProblems interface on arbitrary points: theta [n][D] row-major, lp [n],
  * grad [n][D] (grad may be NULL) */

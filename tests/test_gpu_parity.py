@@ -246,3 +246,66 @@ def test_hmc_with_zero_step_size_searches_one(built, name, strategy):
     np.testing.assert_allclose(eng.stepsize(), ref["eps"], rtol=1e-9)
     assert len(np.unique(eng.stepsize())) > 1        # searched per chain, not a constant
     eng.close()
+
+
+def test_dense_metric_matches_oracle(built):
+    """metricT = DenseEuclideanMetric on the thread-per-chain strategy.  (1) every family: identical
+    to the diagonal metric until the first window ends, and to the oracle's dense run over the first
+    transitions; (2) standard normal (linear, non-chaotic dynamics): the whole run INCLUDING the
+    covariance refresh and its Cholesky factor follows the oracle; (3) gdemo known answers."""
+    for name in ("gdemo", "linreg", "eight_schools"):
+        model = small_models()[name]
+        spl = T.NUTS(120, 0.8, metricT="dense")
+        assert spl.metric == 2
+        C, n_tr = 64, 110
+        eng = T.Engine(model, spl, C, 120, seed=41)
+        eng.set_option("keep_theta", 1)
+        eng.init()
+        eng.run(n_tr, 1, 1)
+        out = eng.fetch(theta=True)
+        ref = O.sample_chains(oracle_of(model), oracle_config(spl, 120, 41), C, n_tr)
+        np.testing.assert_array_equal(out["stats"].transpose(2, 0, 1)[:, :8, 0], ref["stats"][:, :8, 0])
+        np.testing.assert_allclose(out["theta"].transpose(2, 0, 1)[:, :8], ref["theta"][:, :8], atol=1e-7)
+        dm = eng.dense_inv_metric()
+        assert dm.shape == (C, model.D, model.D)
+        np.testing.assert_allclose(dm, dm.transpose(0, 2, 1), rtol=1e-12, atol=1e-14)      # symmetric
+        assert np.all(np.linalg.eigvalsh(dm) > 0)                                         # positive definite
+        np.testing.assert_allclose(np.diagonal(dm, axis1=1, axis2=2), eng.inv_metric(), rtol=0, atol=0)
+        eng.close()
+        diag = T.Engine(model, T.NUTS(120, 0.8), C, 120, seed=41, strategy=1)
+        diag.set_option("keep_theta", 1)
+        diag.init()
+        diag.run(99, 1, 1)                   # the first window ends at iteration 100
+        np.testing.assert_array_equal(diag.fetch(theta=True)["theta"], out["theta"][:99])
+        diag.close()
+    # (2) linear dynamics: compare through the metric refresh (windows 7..36 of 40 warm-up iterations)
+    model = T.StdNormal(4)
+    spl = T.NUTS(40, 0.8, metricT="dense")
+    eng = T.Engine(model, spl, 32, 40, seed=7)
+    eng.set_option("keep_theta", 1)
+    eng.init()
+    eng.run(60, 1, 1)
+    out = eng.fetch(theta=True)
+    ref = O.sample_chains(oracle_of(model), oracle_config(spl, 40, 7), 32, 60)
+    th, rth = out["theta"].transpose(2, 0, 1), ref["theta"]
+    err = np.abs(th - rth).max(axis=(1, 2))
+    same = err < 1e-6
+    # a tree decision that falls within rounding of its threshold flips a chain for good
+    assert same.mean() >= 0.8, (same.mean(), np.sort(err)[-8:])
+    np.testing.assert_allclose(eng.stepsize()[same], ref["eps"][same], rtol=1e-8)
+    np.testing.assert_allclose(eng.inv_metric()[same], ref["minv"][same], rtol=1e-8)
+    assert np.any(np.abs(eng.dense_inv_metric()[:, 0, 1]) > 1e-6)       # off-diagonals were estimated
+    eng.close()
+    # (3) test/mcmc/hmc.jl:138-142 with the dense metric; HMCDA runs through the same pieces
+    for spl in (T.NUTS(500, 0.8, metricT="dense"), T.HMCDA(500, 0.65, 0.3, metricT="dense")):
+        ch = T.sample(T.gdemo_default(), spl, T.MCMCThreads(), 1000, 512, seed=3, verbose=False,
+                      diagnostics=True)
+        assert abs(ch["s"].mean() - 49 / 24) < 0.1 and abs(ch["m"].mean() - 7 / 6) < 0.05
+        assert np.max(ch.info["rhat"]) < 1.01
+
+
+def test_dense_metric_unsupported_combinations(built):
+    with pytest.raises(T._lib.TnutsError):
+        T.Engine(small_models()["logistic_small"], T.NUTS(10, 0.8, metricT="dense"), 8, 10, seed=1)
+    with pytest.raises(T._lib.TnutsError):
+        T.Engine(T.EightSchools(), T.NUTS(10, 0.8, metricT="dense"), 8, 10, seed=1, strategy=2)

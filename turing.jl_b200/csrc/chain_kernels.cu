@@ -48,11 +48,32 @@ int thread_init(Engine *e, const double *theta0_dev) {
   TN_DISPATCH_SMALL(e, CALL);
 #undef CALL
   e->launches += 1;
+  if (e->st.minv_dense) {  // DenseEuclideanMetric(D): identity (the step-size search above is the same)
+    k_chain_init_dense<<<148 * 4, 256, 0, e->stream>>>(e->st);
+    e->launches += 1;
+  }
+  TN_CUDA(e, cudaGetLastError());
+  return TNUTS_OK;
+}
+
+static int thread_run_dense(Engine *e) {
+#define CALL(M)                                                                              \
+  do {                                                                                       \
+    const int g_ = grid_for(e->st.C, kChainBlock);                                           \
+    if (e->cfg.algorithm != TNUTS_ALG_NUTS)                                                  \
+      k_chain_run_dense<M, 1, false><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp); \
+    else                                                                                     \
+      k_chain_run_dense<M, 1, true><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp);  \
+  } while (0)
+  TN_DISPATCH_SMALL(e, CALL);
+#undef CALL
+  e->launches += 1;
   TN_CUDA(e, cudaGetLastError());
   return TNUTS_OK;
 }
 
 int thread_run(Engine *e) {
+  if (e->st.minv_dense) return thread_run_dense(e);
   int n_sm = 0;
   TN_CUDA(e, cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, e->device));
   const bool dyn_ok = e->dyn_sched;

@@ -105,13 +105,124 @@ __device__ __forceinline__ bool uturn_d(const double (&rho)[D], const double *rl
 }
 
 // ------------------------------------------------------------------------------------------
+// DenseEuclideanMetric (metricT of NUTS/HMC/HMCDA, src/mcmc/hmc.jl:178-179; AdvancedHMC semantics
+// restated in the oracle): M^-1 and the upper Cholesky factor U of M^-1 (M^-1 = U'U), row-major,
+// per chain.  The functions below overload the diagonal ones on the metric argument, so the
+// transition code is written once (template parameter MT).
+// ------------------------------------------------------------------------------------------
+template <int D>
+struct DenseMetric {
+  double minv[D * D];
+  double U[D * D];
+};
+
+template <int D>
+__device__ __forceinline__ void dense_apply_d(const DenseMetric<D> &met, const double *r, double (&out)[D]) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) s += met.minv[i * D + j] * r[j];
+    out[i] = s;
+  }
+}
+
+template <int D>
+__device__ __forceinline__ double energy_d(double lp, const double (&g)[D], const double (&r)[D],
+                                           const DenseMetric<D> &met) {
+  double k = 0;
+  bool ok = isfinite(lp);
+  double v[D];
+  dense_apply_d<D>(met, r, v);
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    k += r[d] * v[d];
+    ok = ok && isfinite(g[d]);
+  }
+  k *= 0.5;
+  return (ok && isfinite(k)) ? (-lp + k) : CUDART_INF;
+}
+
+template <class M>
+__device__ __forceinline__ void leapfrog_d(const SmallData &md, double (&th)[M::D],
+                                           double (&r)[M::D], double (&g)[M::D],
+                                           const DenseMetric<M::D> &met, double eps, double &lp,
+                                           double &H) {
+  constexpr int D = M::D;
+  const double half = 0.5 * eps;
+#pragma unroll
+  for (int d = 0; d < D; ++d) r[d] = r[d] + half * g[d];
+  double v[D];
+  dense_apply_d<D>(met, r, v);
+#pragma unroll
+  for (int d = 0; d < D; ++d) th[d] = th[d] + eps * v[d];
+  lp = M::lpgrad(md, th, g);
+#pragma unroll
+  for (int d = 0; d < D; ++d) r[d] = r[d] + half * g[d];
+  H = energy_d<D>(lp, g, r, met);
+}
+
+// r = U \ randn(D): back substitution
+template <int D>
+__device__ __forceinline__ void draw_momentum_d(unsigned long long seed, uint32_t chain,
+                                                uint32_t iter, uint32_t slot,
+                                                const DenseMetric<D> &met, double (&r)[D]) {
+#pragma unroll
+  for (int p = 0; 2 * p < D; ++p) {
+    double z0, z1;
+    normal2(seed, chain, iter, slot, (uint32_t)p, z0, z1);
+    r[2 * p] = z0;
+    if (2 * p + 1 < D) r[2 * p + 1] = z1;
+  }
+#pragma unroll
+  for (int d = D - 1; d >= 0; --d) {
+    double t = r[d];
+#pragma unroll
+    for (int e = d + 1; e < D; ++e) t -= met.U[d * D + e] * r[e];
+    r[d] = t / met.U[d * D + d];
+  }
+}
+
+template <int D>
+__device__ __forceinline__ bool uturn_d(const double (&rho)[D], const double *rl, const double *rr,
+                                        const DenseMetric<D> &met) {
+  double a = 0, b = 0;
+  double vl[D], vr[D];
+  dense_apply_d<D>(met, rl, vl);
+  dense_apply_d<D>(met, rr, vr);
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    a += rho[d] * vl[d];
+    b += rho[d] * vr[d];
+  }
+  return (a <= 0) || (b <= 0);
+}
+
+// upper Cholesky factor of met.minv into met.U (same loop order as the oracle's dense_chol_upper)
+template <int D>
+__device__ __forceinline__ void chol_upper_d(DenseMetric<D> &met) {
+  for (int i = 0; i < D * D; ++i) met.U[i] = 0.0;
+  for (int j = 0; j < D; ++j) {
+    double s = met.minv[j * D + j];
+    for (int k = 0; k < j; ++k) s -= met.U[k * D + j] * met.U[k * D + j];
+    const double ujj = sqrt(s);
+    met.U[j * D + j] = ujj;
+    for (int i = j + 1; i < D; ++i) {
+      double t = met.minv[j * D + i];
+      for (int k = 0; k < j; ++k) t -= met.U[k * D + j] * met.U[k * D + i];
+      met.U[j * D + i] = t / ujj;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // NUTS transition.  On entry th/g/lp = current point; on exit = the selected candidate.
 // ------------------------------------------------------------------------------------------
-template <class M>
+template <class M, class MT>
 __device__ __forceinline__ void nuts_transition_d(const SmallData &md, const RunParams &rp,
                                                   uint32_t gchain, uint32_t it,
                                                   double (&th)[M::D], double (&g)[M::D],
-                                                  double &lp, const double (&minv)[M::D],
+                                                  double &lp, const MT &minv,
                                                   double eps, long long &ngrad,
                                                   double (&stats)[TNUTS_NSTAT],
                                                   double *__restrict__ ck_sm /* smem + tid, or null */) {
@@ -282,11 +393,11 @@ __device__ __forceinline__ void nuts_transition_d(const SmallData &md, const Run
 }
 
 // HMC / HMCDA: static trajectory + Metropolis accept (src/mcmc/hmc.jl:425-434)
-template <class M>
+template <class M, class MT>
 __device__ __forceinline__ void hmc_transition_d(const SmallData &md, const RunParams &rp,
                                                  uint32_t gchain, uint32_t it, double (&th)[M::D],
                                                  double (&g)[M::D], double &lp,
-                                                 const double (&minv)[M::D], double eps,
+                                                 const MT &minv, double eps,
                                                  long long &ngrad, double (&stats)[TNUTS_NSTAT]) {
   constexpr int D = M::D;
   int L = rp.n_leapfrog;
@@ -516,11 +627,11 @@ k_chain_run_dyn(SmallData md, ChainState st, DrawBuffers out, RunParams rp, cons
 // ------------------------------------------------------------------------------------------
 // init kernel: initial parameters, phase point, find_good_stepsize, adaptor state
 // ------------------------------------------------------------------------------------------
-template <class M>
+template <class M, class MT>
 __device__ __forceinline__ double find_good_stepsize_d(const SmallData &md, const RunParams &rp,
                                                        uint32_t gchain, const double (&th)[M::D],
                                                        const double (&g)[M::D], double lp,
-                                                       const double (&minv)[M::D],
+                                                       const MT &minv,
                                                        long long &ngrad) {
   constexpr int D = M::D;
   const double a_min = 0.25, a_cross = 0.5, a_max = 0.75, dd = 2.0;
@@ -637,6 +748,154 @@ __global__ void __launch_bounds__(kChainBlock) k_chain_init(SmallData md, ChainS
   st.wf_n[c] = 0;
   st.iter[c] = 0;
   st.n_grad[c] = ngrad;
+}
+
+// ------------------------------------------------------------------------------------------
+// DenseEuclideanMetric variants of the run / init kernels (TNUTS_METRIC_DENSE).  Same loop as
+// chain_run_range -- kept apart on purpose: the diagonal kernel is the headline kernel and sits at
+// 255 registers -- with the mass-matrix part replaced: Welford covariance in st.wf_cov [D*D][C],
+// M^-1 <- (n / (n + 5)) cov + 1e-3 (5 / (n + 5)) I at the window ends, new Cholesky factor.
+// ------------------------------------------------------------------------------------------
+template <class M, int MINB, bool IS_NUTS>
+__global__ void __launch_bounds__(kChainBlock, MINB) k_chain_run_dense(SmallData md, ChainState st,
+                                                                      DrawBuffers out, RunParams rp) {
+  constexpr int D = M::D;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int C = st.C;
+  if (c >= C || st.status[c] != 0) return;
+  const uint32_t gchain = (uint32_t)(rp.chain_offset + c);
+
+  double th[D], g[D];
+  DenseMetric<D> met;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    th[d] = st.theta[(size_t)d * C + c];
+    g[d] = st.grad[(size_t)d * C + c];
+  }
+  for (int i = 0; i < D * D; ++i) {
+    met.minv[i] = st.minv_dense[(size_t)i * C + c];
+    met.U[i] = st.chol[(size_t)i * C + c];
+  }
+  double lp = st.lp[c], eps = st.eps[c];
+  long long iter = st.iter[c], ngrad = st.n_grad[c];
+  double da_mu = st.da_mu[c], da_xbar = st.da_xbar[c], da_hbar = st.da_hbar[c], da_eps = st.da_eps[c];
+  long long da_m = st.da_m[c], wf_n = st.wf_n[c];
+
+  for (long long t = 1; t <= rp.n_transitions; ++t) {
+    const uint32_t it = (uint32_t)(iter + 1);
+    double stats[TNUTS_NSTAT];
+    if (IS_NUTS) nuts_transition_d<M>(md, rp, gchain, it, th, g, lp, met, eps, ngrad, stats, nullptr);
+    else hmc_transition_d<M>(md, rp, gchain, it, th, g, lp, met, eps, ngrad, stats);
+    iter += 1;
+
+    if (rp.algorithm != TNUTS_ALG_HMC && iter <= rp.n_adapts) {
+      {  // Nesterov dual averaging: gamma = 0.05, t0 = 10, kappa = 0.75
+        const double alpha = fmin(stats[ST_ACC], 1.0);
+        const long long mm = da_m + 1;
+        const double eta_h = 1.0 / ((double)mm + 10.0);
+        const double hbar = (1.0 - eta_h) * da_hbar + eta_h * (rp.delta - alpha);
+        const double x = da_mu - hbar * sqrt((double)mm) / 0.05;
+        const double eta_x = pow((double)mm, -0.75);
+        const double xbar = (1.0 - eta_x) * da_xbar + eta_x * x;
+        const double e = exp(x);
+        da_m = mm;
+        if (isfinite(e)) {
+          da_hbar = hbar;
+          da_xbar = xbar;
+          da_eps = e;
+        }
+      }
+      bool wend = false;
+      for (int k = 0; k < rp.n_splits; ++k) wend = wend || (rp.splits[k] == iter);
+      if (iter >= rp.window_start && iter <= rp.window_end) {
+        wf_n += 1;
+        const double n = (double)wf_n;
+        double delta[D], dm[D];   // s - mu_old, s - mu_new
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const size_t o = (size_t)d * C + c;
+          double mean = st.wf_mean[o];
+          delta[d] = th[d] - mean;
+          mean += delta[d] / n;
+          dm[d] = th[d] - mean;
+          st.wf_mean[o] = wend ? 0.0 : mean;
+        }
+        const bool refresh = wend && wf_n >= 10;
+        for (int a = 0; a < D; ++a)
+          for (int b = 0; b < D; ++b) {
+            const size_t o = (size_t)(a * D + b) * C + c;
+            const double cov = st.wf_cov[o] + dm[a] * delta[b];
+            if (refresh)
+              met.minv[a * D + b] = n / ((n + 5.0) * (n - 1.0)) * cov + (a == b ? 1e-3 * (5.0 / (n + 5.0)) : 0.0);
+            st.wf_cov[o] = wend ? 0.0 : cov;
+          }
+        if (refresh) chol_upper_d<D>(met);
+      }
+      if (wend) {
+        da_mu = log(10.0 * da_eps);
+        da_m = 0;
+        da_xbar = 0.0;
+        da_hbar = 0.0;
+        wf_n = 0;
+      }
+      if (iter == rp.n_adapts) da_eps = exp(da_xbar);
+      eps = da_eps;
+    }
+
+    if (rp.first_keep >= 1 && t >= rp.first_keep && (t - rp.first_keep) % rp.thin == 0) {
+      const long long k = (t - rp.first_keep) / rp.thin;
+      double p[D], prior, lik;
+      M::constrain(md, th, p, prior, lik);
+      double *row = out.draws + (size_t)k * out.ncol * C + c;
+#pragma unroll
+      for (int d = 0; d < D; ++d) row[(size_t)d * C] = p[d];
+      row[(size_t)(D + 0) * C] = prior;
+      row[(size_t)(D + 1) * C] = lik;
+      row[(size_t)(D + 2) * C] = prior + lik;
+#pragma unroll
+      for (int s = 0; s < TNUTS_NSTAT; ++s) row[(size_t)(D + 3 + s) * C] = stats[s];
+      if (out.theta != nullptr) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) out.theta[((size_t)k * D + d) * C + c] = th[d];
+      }
+    }
+  }
+
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    st.theta[(size_t)d * C + c] = th[d];
+    st.grad[(size_t)d * C + c] = g[d];
+    st.minv[(size_t)d * C + c] = met.minv[d * D + d];   // tnuts_get_inv_metric reports the diagonal
+  }
+  for (int i = 0; i < D * D; ++i) {
+    st.minv_dense[(size_t)i * C + c] = met.minv[i];
+    st.chol[(size_t)i * C + c] = met.U[i];
+  }
+  st.lp[c] = lp;
+  st.eps[c] = eps;
+  st.iter[c] = iter;
+  st.n_grad[c] = ngrad;
+  st.da_mu[c] = da_mu;
+  st.da_xbar[c] = da_xbar;
+  st.da_hbar[c] = da_hbar;
+  st.da_eps[c] = da_eps;
+  st.da_m[c] = da_m;
+  st.wf_n[c] = wf_n;
+}
+
+// after k_chain_init: identity dense metric, and the step-size search repeated with it (identical
+// to the diagonal search while M^-1 = I, so only the arrays need initialising)
+__global__ void k_chain_init_dense(ChainState st) {
+  const int C = st.C, D = st.D;
+  const long long tot = (long long)D * D * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i / C);
+    const double v = (e / D == e % D) ? 1.0 : 0.0;
+    st.minv_dense[i] = v;
+    st.chol[i] = v;
+    st.wf_cov[i] = 0.0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------

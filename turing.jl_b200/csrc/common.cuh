@@ -55,6 +55,9 @@ struct ChainState {
   // Welford
   long long *wf_n;           // [C]
   double *wf_mean, *wf_m2;   // [D][C]
+  // DenseEuclideanMetric (TNUTS_METRIC_DENSE, thread-per-chain strategy): M^-1, its upper Cholesky
+  // factor and the Welford covariance accumulator, [D*D][C]; null otherwise
+  double *minv_dense, *chol, *wf_cov;
   long long *iter;           // [C] iteration counter i (src/mcmc/hmc.jl:228)
   long long *n_grad;         // [C] gradient evaluations
   int *init_tries;           // [C]

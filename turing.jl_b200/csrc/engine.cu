@@ -180,8 +180,8 @@ int tnuts_create(const tnuts_config *cfg, tnuts_engine **out) {
     return set_error(nullptr, TNUTS_E_CUDA,
                      std::string("tnuts_create: libtnuts is built for sm_100a only; device is ") +
                          prop.name);
-  if (cfg->metric != TNUTS_METRIC_DIAG && cfg->metric != TNUTS_METRIC_UNIT)
-    return set_error(nullptr, TNUTS_E_UNSUPPORTED, "tnuts_create: metric must be TNUTS_METRIC_DIAG or TNUTS_METRIC_UNIT (DenseEuclideanMetric is not implemented)");
+  if (cfg->metric != TNUTS_METRIC_DIAG && cfg->metric != TNUTS_METRIC_UNIT && cfg->metric != TNUTS_METRIC_DENSE)
+    return set_error(nullptr, TNUTS_E_UNSUPPORTED, "tnuts_create: unknown metric");
   Engine *e = new Engine();
   e->cfg = *cfg;
   e->device = cfg->device;
@@ -337,6 +337,11 @@ static int set_model_impl(tnuts_engine *h, const tnuts_model *m, bool device_ptr
   const bool sg = e->cfg.algorithm == TNUTS_ALG_SGHMC || e->cfg.algorithm == TNUTS_ALG_SGLD;
   if (sg && (e->cfg.strategy == STRAT_THREAD || e->cfg.strategy == STRAT_BLOCK))
     return set_error(e, TNUTS_E_UNSUPPORTED, "SGHMC / SGLD run on the batched (lock-step) strategy only");
+  const bool dense = e->cfg.metric == TNUTS_METRIC_DENSE;
+  if (dense && (sg || !thread_ok || (e->cfg.strategy != STRAT_AUTO && e->cfg.strategy != STRAT_THREAD)))
+    return set_error(e, TNUTS_E_UNSUPPORTED,
+                     "DenseEuclideanMetric is implemented for NUTS / HMC / HMCDA on the thread-per-chain "
+                     "strategy (gdemo, README regression, eight schools, small standard normal)");
   if (sg) e->strategy = STRAT_LOCKSTEP;
   else if (e->cfg.strategy == STRAT_THREAD || (e->cfg.strategy == STRAT_AUTO && thread_ok)) e->strategy = STRAT_THREAD;
   else if (e->cfg.strategy == STRAT_BLOCK || (e->cfg.strategy == STRAT_AUTO && block_ok)) e->strategy = STRAT_BLOCK;
@@ -365,6 +370,12 @@ static int set_model_impl(tnuts_engine *h, const tnuts_model *m, bool device_ptr
   if ((rc = dev_alloc(e, pool, &st.n_grad, C))) return rc;
   if ((rc = dev_alloc(e, pool, &st.init_tries, C))) return rc;
   if ((rc = dev_alloc(e, pool, &st.status, C))) return rc;
+  st.minv_dense = st.chol = st.wf_cov = nullptr;
+  if (dense) {
+    if ((rc = dev_alloc(e, pool, &st.minv_dense, D * D * C))) return rc;
+    if ((rc = dev_alloc(e, pool, &st.chol, D * D * C))) return rc;
+    if ((rc = dev_alloc(e, pool, &st.wf_cov, D * D * C))) return rc;
+  }
   if (e->strategy != STRAT_THREAD) {  // the block strategy shares init / point-wise kernels
     if ((rc = lockstep_create(e))) return rc;
   }
@@ -588,6 +599,19 @@ int tnuts_get_inv_metric(tnuts_engine *h, double *minv) {
   return fetch_dc(e, e->st.minv, minv);
 }
 
+int tnuts_get_dense_inv_metric(tnuts_engine *h, double *minv) {
+  Engine *e = (Engine *)h;
+  if (!e || !e->inited || !minv) return set_error(e, TNUTS_E_ARG, "tnuts_get_dense_inv_metric: bad call");
+  if (!e->st.minv_dense) return set_error(e, TNUTS_E_ARG, "tnuts_get_dense_inv_metric: the metric is not dense");
+  TN_CUDA(e, cudaSetDevice(e->device));
+  const size_t C = (size_t)e->st.C, DD = (size_t)e->D * e->D;
+  std::vector<double> tmp(DD * C);   // device layout [D*D][C] -> [C][D][D]
+  TN_CUDA(e, cudaMemcpy(tmp.data(), e->st.minv_dense, 8 * DD * C, cudaMemcpyDeviceToHost));
+  for (size_t c = 0; c < C; ++c)
+    for (size_t i = 0; i < DD; ++i) minv[c * DD + i] = tmp[i * C + c];
+  return TNUTS_OK;
+}
+
 int tnuts_get_stepsize(tnuts_engine *h, double *eps) {
   Engine *e = (Engine *)h;
   if (!e || !e->inited || !eps) return set_error(e, TNUTS_E_ARG, "tnuts_get_stepsize: bad call");
@@ -705,7 +729,8 @@ static constexpr uint32_t kBlobMagic = 0x544e5554u;  // "TUNT"
 
 static size_t blob_bytes(const Engine *e) {
   const size_t C = (size_t)e->st.C, D = (size_t)e->D;
-  return sizeof(BlobHeader) + 8 * (5 * D * C + 6 * C) + 8 * 5 * C;
+  const size_t dense = e->st.minv_dense ? 8 * 3 * D * D * C : 0;
+  return sizeof(BlobHeader) + 8 * (5 * D * C + 6 * C) + 8 * 5 * C + dense;
 }
 
 int tnuts_get_state(tnuts_engine *h, void *blob, size_t *nbytes) {
@@ -738,6 +763,14 @@ int tnuts_get_state(tnuts_engine *h, void *blob, size_t *nbytes) {
   }
   // 11th scalar slot: status/init_tries are not part of the resumable state
   std::memset(p, 0, 8 * C);
+  p += 8 * C;
+  if (st.minv_dense) {
+    const void *dn[] = {st.minv_dense, st.chol, st.wf_cov};
+    for (const void *a : dn) {
+      TN_CUDA(e, cudaMemcpy(p, a, 8 * D * D * C, cudaMemcpyDeviceToHost));
+      p += 8 * D * D * C;
+    }
+  }
   *nbytes = need;
   return TNUTS_OK;
 }
@@ -764,6 +797,14 @@ int tnuts_set_state(tnuts_engine *h, const void *blob, size_t nbytes) {
   for (void *a : sc) {
     TN_CUDA(e, cudaMemcpy(a, p, 8 * C, cudaMemcpyHostToDevice));
     p += 8 * C;
+  }
+  if (st.minv_dense) {
+    p += 8 * C;  // the unused 11th scalar slot
+    void *dn[] = {st.minv_dense, st.chol, st.wf_cov};
+    for (void *a : dn) {
+      TN_CUDA(e, cudaMemcpy(a, p, 8 * D * D * C, cudaMemcpyHostToDevice));
+      p += 8 * D * D * C;
+    }
   }
   TN_CUDA(e, cudaMemset(st.status, 0, sizeof(int) * C));
   {

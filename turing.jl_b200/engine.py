@@ -128,6 +128,12 @@ class Engine:
         check(self.h, self.L.tnuts_get_inv_metric(self.h, _dp(m)))
         return m
 
+    def dense_inv_metric(self):
+        """[n_chains, D, D]: the full M^-1 of a DenseEuclideanMetric engine"""
+        m = np.empty((self.C, self.D, self.D))
+        check(self.h, self.L.tnuts_get_dense_inv_metric(self.h, _dp(m)))
+        return m
+
     def constrain(self, theta):
         th = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
         n = th.shape[0]

@@ -3,13 +3,13 @@ meaning (src/mcmc/hmc.jl:59-80 HMC, :285-327 HMCDA, :352-402 NUTS; src/mcmc/sghm
 PolynomialStepsize; src/Turing.jl:105-107)."""
 
 
-METRICS = {"diag": 0, "DiagEuclideanMetric": 0, "unit": 1, "UnitEuclideanMetric": 1}
+METRICS = {"diag": 0, "DiagEuclideanMetric": 0, "unit": 1, "UnitEuclideanMetric": 1,
+           "dense": 2, "DenseEuclideanMetric": 2}
 
 
 def _metric_id(metricT):
-    """metricT of the reference's constructors (AHMC.DiagEuclideanMetric / UnitEuclideanMetric)"""
-    if metricT in ("dense", "DenseEuclideanMetric"):
-        raise NotImplementedError("DenseEuclideanMetric is not implemented by the engine")
+    """metricT of the reference's constructors (AHMC.DiagEuclideanMetric / UnitEuclideanMetric /
+    DenseEuclideanMetric; the dense one runs on the thread-per-chain strategy only)"""
     try:
         return METRICS[metricT]
     except KeyError:
