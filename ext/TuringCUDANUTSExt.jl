@@ -56,10 +56,14 @@ struct CUDANUTS{AD} <: Hamiltonian
     n_adapts::Int; δ::Float64; max_depth::Int; Δ_max::Float64; ϵ::Float64; adtype::AD
     family::Int32; data::NamedTuple; device::Int32
     options::NamedTuple   # engine knobs passed to tnuts_set_option, e.g. (logistic_tc = 1,)
+    metric::Int32         # TNUTS_METRIC_*: the sampler's metricT (src/mcmc/hmc.jl:404-406)
 end
+metric_id(::Type{<:AdvancedHMC.DiagEuclideanMetric}) = Int32(0)
+metric_id(::Type{<:AdvancedHMC.UnitEuclideanMetric}) = Int32(1)
+metric_id(::Type{<:AdvancedHMC.DenseEuclideanMetric}) = Int32(2)   # thread-per-chain families only
 CUDANUTS(s::NUTS; family, data, device=0, options=NamedTuple()) =
     CUDANUTS(s.n_adapts, s.δ, s.max_depth, s.Δ_max, s.ϵ, s.adtype, Int32(family), data, Int32(device),
-             options)
+             options, metric_id(Turing.Inference.getmetricT(s)))
 
 # ---- engine handle --------------------------------------------------------------------------
 mutable struct Engine
@@ -67,7 +71,7 @@ mutable struct Engine
 end
 function Engine(spl::CUDANUTS, nchains::Int, nadapts::Int, seed::UInt64)
     cfg = Ref(TnutsConfig(0, spl.δ, spl.max_depth, spl.Δ_max, spl.ϵ, nadapts, 0, 0.0, seed,
-                          nchains, 0, spl.device, 1, 0, 0, Int32(0) #= TNUTS_METRIC_DIAG: NUTS default =#,
+                          nchains, 0, spl.device, 1, 0, 0, spl.metric,
                           ntuple(_ -> Int32(0), 4)))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(C_NULL, ccall((:tnuts_create, libtnuts), Cint, (Ref{TnutsConfig}, Ref{Ptr{Cvoid}}), cfg, h))
