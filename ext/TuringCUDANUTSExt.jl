@@ -16,6 +16,7 @@ module TuringCUDANUTSExt
 using Turing
 using Turing: AbstractMCMC, Random, LogDensityProblems, DynamicPPL
 using Turing.Inference: Hamiltonian, NUTS
+using Turing: AdvancedHMC
 import MCMCChains
 
 const libtnuts = get(ENV, "TNUTS_LIBRARY", "libtnuts.so")
