@@ -16,7 +16,7 @@ module TuringCUDANUTSExt
 using Turing
 using Turing: AbstractMCMC, Random, LogDensityProblems, DynamicPPL
 using Turing.Inference: Hamiltonian, NUTS
-using Turing: AdvancedHMC
+using Turing.Inference: AdvancedHMC   # `import AdvancedHMC` in src/mcmc/Inference.jl:31
 import MCMCChains
 
 const libtnuts = get(ENV, "TNUTS_LIBRARY", "libtnuts.so")
