@@ -451,7 +451,7 @@ static int run_segments(Engine *e, int64_t n_transitions, int64_t first_keep, in
     // last transition of this segment: the one that produces draw k_end - 1 (or the very end)
     long long t_end = (keep == 0 || k_end >= keep) ? n_transitions : first_keep + (k_end - 1) * thin;
     if (k_done >= keep) t_end = n_transitions;
-    if (e->strategy == STRAT_THREAD && e->sort_chains && e->cfg.algorithm == TNUTS_ALG_NUTS) {
+    if (e->strategy == STRAT_THREAD && e->sort_chains && e->cfg.algorithm == TNUTS_ALG_NUTS && !e->st.minv_dense) {
       // thread-per-chain: once the step sizes are final, sort the chains by step size so
       // that a warp's 32 chains grow trees of similar length; cut the segment at that point
       const long long to_adapt_end = e->cfg.n_adapts - (e->host_iter + t_done);
