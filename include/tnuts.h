@@ -183,7 +183,12 @@ int tnuts_fetch_draws(tnuts_engine *e, double *draws);
  *                 tensor cores with bf16x3 operand planes -- fp32-grade dot products, fp64
  *                 accumulation of the log-likelihood -- instead of the fp64 DMMA kernel.
  *                 Stated bounds (tests/test_gpu_tc.py): |d lp| <= 3e-7 |lp|,
- *                 |d grad| <= 1e-4 |grad|.  Set before tnuts_init. */
+ *                 |d grad| <= 1e-4 |grad|.  Set before tnuts_init.
+ *   "time_kernels" (0/1, default 0) see tnuts_kernel_times
+ *   "persist"     (0/1, default 1) "logistic_tc" on one GPU: once <= 512 chains are unfinished, the
+ *                 rest of a tnuts_run is ONE persistent cooperative kernel (gradient, reduction and
+ *                 NUTS state machine per leapfrog, grid barriers instead of launches); bit-identical
+ *                 to the host-pumped path */
 int tnuts_set_option(tnuts_engine *e, const char *name, double value);
 
 /* current linked-space position of every chain, [n_chains][D] row-major */
@@ -224,6 +229,18 @@ int64_t tnuts_num_kernel_launches(const tnuts_engine *e);
 double tnuts_device_seconds(const tnuts_engine *e);     /* CUDA-event time of last tnuts_run */
 double tnuts_init_device_seconds(const tnuts_engine *e);/* CUDA-event time of last tnuts_init */
 int tnuts_init_tries_max(const tnuts_engine *e);        /* worst chain's init attempts  */
+
+/* measurement aid (option "time_kernels" = 1, set before tnuts_run): CUDA-event time, on the engine's
+ * stream, of the launches of the dominant kernel inside the last tnuts_run -- lock-step strategy:
+ * the family's batched gradient kernel (k_logistic_tc / k_logistic_mma / ...); the other strategies
+ * run ONE kernel per call, so they report the run time.  *seconds is the total over the run, estimated
+ * from a systematic sample of *sampled of the *launches launches; *tile_launches is the number of
+ * 128-chain x row-chunk-set tiles those launches covered (tcgen05 path).  *persist_seconds /
+ * *persist_pumps: time of, and pumps executed by, the persistent tail kernel (option "persist"),
+ * which fuses gradient, reduction and state machine and is not part of *seconds.  Any pointer may
+ * be NULL. */
+int tnuts_kernel_times(const tnuts_engine *e, double *seconds, int64_t *launches, int64_t *sampled,
+                       int64_t *tile_launches, double *persist_seconds, int64_t *persist_pumps);
 
 /* measurement aid: time `reps` gradient evaluations of all chains at their current positions
  * with CUDA events on the engine's stream (lock-step strategy) */

@@ -67,6 +67,14 @@ def lib():
         L.orc_sample_chains.argtypes = [C.POINTER(_Model), C.POINTER(_Config), C.c_int, C.c_int,
                                         _dp, C.c_int64, C.c_int64, C.c_int64, _dp, _dp, _dp, _dp,
                                         _dp, _dp]
+        L.orc_sample_chain_ids.restype = C.c_int64
+        L.orc_sample_chain_ids.argtypes = [C.POINTER(_Model), C.POINTER(_Config), C.c_int, C.c_int,
+                                           C.POINTER(C.c_uint32), _dp, C.c_int64, C.c_int64, C.c_int64,
+                                           _dp, _dp, _dp, _dp, _dp, _dp]
+        L.orc_resume_chains.restype = C.c_int64
+        L.orc_resume_chains.argtypes = [C.POINTER(_Model), C.POINTER(_Config), C.c_int, C.c_int,
+                                        C.c_uint32, _dp, _dp, _dp, C.c_int64, C.c_int64, C.c_int64,
+                                        C.c_int64, _dp, _dp, _dp, _dp, _dp]
         L.orc_leapfrog_trajectory.restype = None
         L.orc_leapfrog_trajectory.argtypes = [C.POINTER(_Model), _dp, _dp, _dp, C.c_double, C.c_int,
                                               _dp, _dp, _dp]
@@ -150,9 +158,13 @@ def normal2(seed, chain, it, slot, sub):
 
 
 def sample_chains(model, cfg, n_chains, n_transitions, first_keep=1, thin=1, theta0=None,
-                  n_threads=0):
+                  n_threads=0, chain_ids=None):
     """Returns dict(theta[C,K,D], params[C,K,P], logp[C,K,3], stats[C,K,NSTAT], eps[C], minv[C,D],
-    n_grad)."""
+    n_grad).  chain_ids: global ids of the chains to run (default 0..n_chains-1)."""
+    ids = None
+    if chain_ids is not None:
+        ids = np.ascontiguousarray(chain_ids, dtype=np.uint32)
+        n_chains = ids.size
     D = model.D
     nkeep = (n_transitions - first_keep) // thin + 1 if n_transitions >= first_keep >= 1 else 0
     th = np.zeros((n_chains, nkeep, D))
@@ -162,12 +174,33 @@ def sample_chains(model, cfg, n_chains, n_transitions, first_keep=1, thin=1, the
     eps = np.zeros(n_chains)
     minv = np.zeros((n_chains, D))
     t0 = None if theta0 is None else np.ascontiguousarray(theta0, dtype=np.float64)
-    n = lib().orc_sample_chains(C.byref(model._c), C.byref(cfg), n_chains, n_threads, _d(t0),
-                                n_transitions, first_keep, thin, _d(th), _d(pa), _d(lp), _d(st),
-                                _d(eps), _d(minv))
+    n = lib().orc_sample_chain_ids(C.byref(model._c), C.byref(cfg), n_chains, n_threads,
+                                   ids.ctypes.data_as(C.POINTER(C.c_uint32)) if ids is not None else None,
+                                   _d(t0), n_transitions, first_keep, thin, _d(th), _d(pa), _d(lp),
+                                   _d(st), _d(eps), _d(minv))
     if n < 0:
         raise RuntimeError("oracle: failed to find valid initial parameters")
     return dict(theta=th, params=pa, logp=lp, stats=st, eps=eps, minv=minv, n_grad=int(n))
+
+
+def resume_chains(model, cfg, theta, eps, minv, iter0, n_transitions, first_keep=1, thin=1,
+                  n_threads=0, chain_id0=0):
+    """continue adapted chains: theta [C,D], eps [C], minv [C,D]; returns the same dict as
+    sample_chains plus final_theta [C,D]"""
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    eps = np.ascontiguousarray(eps, dtype=np.float64)
+    minv = np.ascontiguousarray(minv, dtype=np.float64)
+    n_chains, D = theta.shape
+    nkeep = (n_transitions - first_keep) // thin + 1 if n_transitions >= first_keep >= 1 else 0
+    th = np.zeros((n_chains, nkeep, D))
+    pa = np.zeros((n_chains, nkeep, D))
+    lp = np.zeros((n_chains, nkeep, 3))
+    st = np.zeros((n_chains, nkeep, NSTAT))
+    fin = np.zeros((n_chains, D))
+    n = lib().orc_resume_chains(C.byref(model._c), C.byref(cfg), n_chains, n_threads, chain_id0,
+                                _d(theta), _d(eps), _d(minv), iter0, n_transitions, first_keep, thin,
+                                _d(th), _d(pa), _d(lp), _d(st), _d(fin))
+    return dict(theta=th, params=pa, logp=lp, stats=st, final_theta=fin, n_grad=int(n))
 
 
 def leapfrog_trajectory(model, theta, r, minv, eps, L):

@@ -45,11 +45,6 @@ static double log1pexp(double x) {
   if (x < 33.3) return x + exp(-x);
   return x;
 }
-static double logistic(double x) {
-  if (x >= 0) return 1.0 / (1.0 + exp(-x));
-  double e = exp(x);
-  return e / (1.0 + e);
-}
 
 /* gdemo: s ~ InverseGamma(2,3); m ~ Normal(0,sqrt(s)); x_i ~ Normal(m,sqrt(s))
  * test/test_utils/models.jl:15-21.  theta = (log s, m). hyper = {alpha, beta}. */
@@ -126,7 +121,42 @@ static double lp_eight_schools(const orc_model *md, const double *th, double *g)
 }
 
 /* Bayesian logistic regression: beta ~ MvNormal(0, sd^2 I); y_i ~ BernoulliLogit(x_i . beta).
- * hyper = {sd}.  X row-major [N][D]. */
+ * hyper = {sd}.  X row-major [N][D].
+ * One pass over the rows per gradient (eta_i = x_i . beta, then g += r_i x_i), which is what one
+ * task of the reference does per leapfrog.  The dot product runs in ORC_LANES interleaved partial
+ * sums with a fixed combination order, so the value does not depend on the vector ISA the
+ * compiler picks (the clones below only differ in how many lanes one instruction carries);
+ * log1pexp and logistic share one exp:  e = exp(-|eta|),  log1pexp = max(eta, 0) + log1p(e),
+ * logistic = 1 / (1 + e) or e / (1 + e)  (StatsFuns' branches agree with this to 1 ulp). */
+#define ORC_LANES 8
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target_clones("default", "avx", "avx2", "avx512f")))
+#endif
+static double lp_logistic_rows(const double *X, const double *y, int64_t N, int D, const double *th,
+                               double *g) {
+  double lp = 0.0;
+  const int Dv = D & ~(ORC_LANES - 1);
+  for (int64_t i = 0; i < N; ++i) {
+    const double *x = X + i * (int64_t)D;
+    double acc[ORC_LANES];
+    for (int l = 0; l < ORC_LANES; ++l) acc[l] = 0.0;
+    for (int d = 0; d < Dv; d += ORC_LANES) {
+#pragma omp simd
+      for (int l = 0; l < ORC_LANES; ++l) acc[l] += x[d + l] * th[d + l];
+    }
+    double eta = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    for (int d = Dv; d < D; ++d) eta += x[d] * th[d];
+    const double e = exp(-fabs(eta));
+    lp += y[i] * eta - ((eta > 0.0 ? eta : 0.0) + log1p(e));
+    if (g) {
+      const double r = y[i] - (eta >= 0.0 ? 1.0 / (1.0 + e) : e / (1.0 + e));
+#pragma omp simd
+      for (int d = 0; d < D; ++d) g[d] += r * x[d];
+    }
+  }
+  return lp;
+}
+
 static double lp_logistic(const orc_model *md, const double *th, double *g) {
   const double sd = md->hyper[0];
   const int D = md->D;
@@ -135,17 +165,7 @@ static double lp_logistic(const orc_model *md, const double *th, double *g) {
     lp -= 0.5 * th[d] * th[d] / (sd * sd);
     if (g) g[d] = -th[d] / (sd * sd);
   }
-  for (int64_t i = 0; i < md->N; ++i) {
-    const double *x = md->X + i * (int64_t)D;
-    double eta = 0;
-    for (int d = 0; d < D; ++d) eta += x[d] * th[d];
-    lp += md->y[i] * eta - log1pexp(eta);
-    if (g) {
-      const double r = md->y[i] - logistic(eta);
-      for (int d = 0; d < D; ++d) g[d] += r * x[d];
-    }
-  }
-  return lp;
+  return lp + lp_logistic_rows(md->X, md->y, md->N, D, th, g);
 }
 
 /* hierarchical linear regression (centred): mu_a, mu_b ~ Normal(0, sdm);
@@ -840,8 +860,9 @@ static void da_adapt(orc_chain *c, double delta, double alpha) {
   const double eta_x = pow((double)mm, -kappa);
   const double xbar = (1.0 - eta_x) * c->da_xbar + eta_x * x;
   const double eps = exp(x);
-  c->da_m = mm;
-  if (isfinite(eps)) { /* non-finite eps: keep the previous eps, x_bar, H_bar */
+  if (isfinite(eps)) { /* non-finite eps: keep the previous m, eps, x_bar, H_bar (adapt_stepsize!
+                          reverts the whole state) */
+    c->da_m = mm;
     c->da_hbar = hbar;
     c->da_xbar = xbar;
     c->da_eps = eps;
@@ -1127,10 +1148,11 @@ int64_t orc_chain_run(const orc_model *m, const orc_config *cfg, uint32_t chain,
   return k;
 }
 
-int64_t orc_sample_chains(const orc_model *m, const orc_config *cfg, int n_chains, int n_threads,
-                          const double *theta0, int64_t n_transitions, int64_t first_keep,
-                          int64_t thin, double *out_theta, double *out_params, double *out_logp,
-                          double *out_stats, double *out_final_eps, double *out_final_minv) {
+int64_t orc_sample_chain_ids(const orc_model *m, const orc_config *cfg, int n_chains, int n_threads,
+                             const uint32_t *chain_ids, const double *theta0, int64_t n_transitions,
+                             int64_t first_keep, int64_t thin, double *out_theta, double *out_params,
+                             double *out_logp, double *out_stats, double *out_final_eps,
+                             double *out_final_minv) {
   const int D = m->D, P = orc_num_params(m);
   int64_t nkeep = 0;
   if (n_transitions >= first_keep && first_keep >= 1) nkeep = (n_transitions - first_keep) / thin + 1;
@@ -1141,11 +1163,12 @@ int64_t orc_sample_chains(const orc_model *m, const orc_config *cfg, int n_chain
 #endif
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : total) reduction(| : fail)
   for (int ch = 0; ch < n_chains; ++ch) {
+    const uint32_t id = chain_ids ? chain_ids[ch] : (uint32_t)ch; /* global chain id: RNG address */
     orc_chain *c = orc_chain_new(D);
-    if (orc_chain_init(m, cfg, (uint32_t)ch, theta0 ? theta0 + (size_t)ch * D : NULL, c) != 0) {
+    if (orc_chain_init(m, cfg, id, theta0 ? theta0 + (size_t)ch * D : NULL, c) != 0) {
       fail |= 1;
     } else {
-      orc_chain_run(m, cfg, (uint32_t)ch, c, n_transitions, first_keep, thin,
+      orc_chain_run(m, cfg, id, c, n_transitions, first_keep, thin,
                     out_theta ? out_theta + (size_t)ch * nkeep * D : NULL,
                     out_params ? out_params + (size_t)ch * nkeep * P : NULL,
                     out_logp ? out_logp + (size_t)ch * nkeep * 3 : NULL,
@@ -1157,4 +1180,52 @@ int64_t orc_sample_chains(const orc_model *m, const orc_config *cfg, int n_chain
     orc_chain_free(c);
   }
   return fail ? -1 : total;
+}
+
+int64_t orc_sample_chains(const orc_model *m, const orc_config *cfg, int n_chains, int n_threads,
+                          const double *theta0, int64_t n_transitions, int64_t first_keep,
+                          int64_t thin, double *out_theta, double *out_params, double *out_logp,
+                          double *out_stats, double *out_final_eps, double *out_final_minv) {
+  return orc_sample_chain_ids(m, cfg, n_chains, n_threads, NULL, theta0, n_transitions, first_keep, thin,
+                              out_theta, out_params, out_logp, out_stats, out_final_eps, out_final_minv);
+}
+
+/* Continue already adapted chains (the HMCState of src/mcmc/hmc.jl:10-23 restored, nadapts = 0 as in
+ * hmc.jl:135-152): chain ch starts at theta[ch], with step size eps[ch], diagonal M^-1 minv[ch] and
+ * iteration counter iter0 (the Philox iteration index of its next transition is iter0 + 1).
+ * Used by bench.py's CPU legs to time a bounded block of post-warm-up transitions; global chain
+ * ids are chain_id0 + ch.  out_final_theta [chains][D] may be NULL.  Returns the gradient
+ * evaluations of this call (one per chain for the restored phase point included). */
+int64_t orc_resume_chains(const orc_model *m, const orc_config *cfg, int n_chains, int n_threads,
+                          uint32_t chain_id0, const double *theta, const double *eps,
+                          const double *minv, int64_t iter0, int64_t n_transitions,
+                          int64_t first_keep, int64_t thin, double *out_theta, double *out_params,
+                          double *out_logp, double *out_stats, double *out_final_theta) {
+  const int D = m->D, P = orc_num_params(m);
+  int64_t nkeep = 0;
+  if (n_transitions >= first_keep && first_keep >= 1) nkeep = (n_transitions - first_keep) / thin + 1;
+  int64_t total = 0;
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
+  for (int ch = 0; ch < n_chains; ++ch) {
+    orc_chain *c = orc_chain_new(D);
+    memcpy(c->theta, theta + (size_t)ch * D, sizeof(double) * (size_t)D);
+    memcpy(c->minv, minv + (size_t)ch * D, sizeof(double) * (size_t)D);
+    c->lp = orc_logdensity_and_gradient(m, c->theta, c->grad);
+    c->n_grad_evals = 1;
+    c->eps = c->da_eps = eps[ch];
+    da_reset(c);
+    c->iter = iter0;
+    orc_chain_run(m, cfg, chain_id0 + (uint32_t)ch, c, n_transitions, first_keep, thin,
+                  out_theta ? out_theta + (size_t)ch * nkeep * D : NULL,
+                  out_params ? out_params + (size_t)ch * nkeep * P : NULL,
+                  out_logp ? out_logp + (size_t)ch * nkeep * 3 : NULL,
+                  out_stats ? out_stats + (size_t)ch * nkeep * ORC_NSTAT : NULL);
+    if (out_final_theta) memcpy(out_final_theta + (size_t)ch * D, c->theta, sizeof(double) * (size_t)D);
+    total += c->n_grad_evals;
+    orc_chain_free(c);
+  }
+  return total;
 }

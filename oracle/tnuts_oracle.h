@@ -146,6 +146,22 @@ int64_t orc_sample_chains(const orc_model *m, const orc_config *cfg, int n_chain
                           int64_t thin, double *out_theta, double *out_params, double *out_logp,
                           double *out_stats, double *out_final_eps, double *out_final_minv);
 
+/* the same for an arbitrary set of global chain ids (the ids address the random streams): lets a
+ * test compare a few chains of a 65 536-chain engine run without running the others */
+int64_t orc_sample_chain_ids(const orc_model *m, const orc_config *cfg, int n_chains, int n_threads,
+                             const uint32_t *chain_ids, const double *theta0, int64_t n_transitions,
+                             int64_t first_keep, int64_t thin, double *out_theta, double *out_params,
+                             double *out_logp, double *out_stats, double *out_final_eps,
+                             double *out_final_minv);
+
+/* continue adapted chains from (theta, eps, diagonal M^-1, iteration counter): the resume path of
+ * src/mcmc/hmc.jl:135-152 (nadapts = 0 when cfg->n_adapts <= iter0).  Layouts as above. */
+int64_t orc_resume_chains(const orc_model *m, const orc_config *cfg, int n_chains, int n_threads,
+                          uint32_t chain_id0, const double *theta, const double *eps,
+                          const double *minv, int64_t iter0, int64_t n_transitions,
+                          int64_t first_keep, int64_t thin, double *out_theta, double *out_params,
+                          double *out_logp, double *out_stats, double *out_final_theta);
+
 /* building blocks exposed for parity tests */
 /* fixed-momentum L-step leapfrog trajectory; traj_theta/traj_r [L+1][D] (incl. start),
  * traj_H [L+1].  AdvancedHMC step(Leapfrog) restated. */

@@ -1,0 +1,6 @@
+set -x
+timeout 900 python -m pytest tests/test_gpu_tc.py tests/test_gpu_shapes.py -q > gpurun_out/r2_pytest3.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest3.log
+tail -15 gpurun_out/r2_pytest3.log
+TNUTS_PUMP_TRACE=1 timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/r2_bench3.json 2> gpurun_out/r2_bench3.err; echo "bench rc=$?"
+grep -v "^\[tnuts pump\] [0-9]" gpurun_out/r2_bench3.err | tail -6
+cat gpurun_out/r2_bench3.json

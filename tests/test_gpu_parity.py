@@ -141,26 +141,6 @@ def test_init_matches_oracle(built, name, strategy):
     eng.close()
 
 
-def test_flat_scheduled_thread_kernel_matches_oracle(built):
-    """chain_flat.cuh (experimental, off by default: measured slower than the nested kernel on
-    B200) must still be the same algorithm"""
-    model = T.EightSchools()
-    spl = T.NUTS(30, 0.8)
-    eng = T.Engine(model, spl, 96, 30, seed=5, strategy=1)
-    eng.set_option("flat", 1)
-    eng.set_option("flat_batch", 7)
-    eng.set_option("keep_theta", 1)
-    eng.init()
-    eng.run(42, 1, 1)
-    out = eng.fetch(theta=True)
-    ref = O.sample_chains(oracle_of(model), oracle_config(spl, 30, 5), 96, 42)
-    st = out["stats"].transpose(2, 0, 1)
-    for col in (0, 6, 7):
-        np.testing.assert_array_equal(st[:, :8, col], ref["stats"][:, :8, col])
-    np.testing.assert_allclose(out["theta"].transpose(2, 0, 1)[:, :8], ref["theta"][:, :8], atol=1e-7)
-    eng.close()
-
-
 def test_strategies_agree_bitwise_on_tree_stats(built):
     """the two execution strategies are the same algorithm: identical n_steps / depth for a
     whole short run, positions equal to rounding"""

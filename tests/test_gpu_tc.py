@@ -135,3 +135,32 @@ def test_tc_serves_hmc_hmcda_sghmc_and_resume(built):
                     verbose=False)
     assert np.array_equal(first.value, full.value[:15])
     assert np.array_equal(rest.value, full.value[15:])
+
+
+@pytest.mark.parametrize("N,D,C,spl", [
+    (700, 10, 200, T.NUTS(20, 0.8)),        # <= 512 chains: persistent from the first pump
+    (20000, 100, 300, T.NUTS(15, 0.8)),     # 313 row tiles: the cut uses the whole grid
+    (5000, 33, 1300, T.NUTS(20, 0.8)),      # host-pumped until <= 512 chains are left, then persistent
+    (3000, 64, 130, T.HMC(0.01, 7)),        # static trajectories
+    (900, 12, 520, T.HMCDA(30, 0.65, 0.1)),
+])
+def test_persistent_tail_kernel_is_bit_identical_to_the_host_pumped_path(built, N, D, C, spl):
+    """tc_persist.cuh: gradient + reduction + NUTS state machine per leapfrog inside one cooperative
+    kernel, same row cut, same summation order, same refresh schedule -> the very same chains"""
+    model = T.models.synthetic_logistic(N, D, seed=N % 97)
+    nad = spl.n_adapts if spl.adaptive else 0
+    res = []
+    for persist in (1, 0):
+        e = T.Engine(model, spl, C, nad, seed=5)
+        e.set_option("logistic_tc", 1)
+        e.set_option("persist", persist)
+        e.set_option("time_kernels", 1)
+        e.init()
+        e.run(nad + 12, 1, 1)
+        res.append((e.fetch_draws(), e.get_state(), e.grad_evals, e.kernel_times()))
+        e.close()
+    (da, sa, ga, ka), (db, sb, gb, kb) = res
+    assert ka[5] > 0 and kb[5] == 0          # the persistent kernel really ran / really did not
+    assert ga == gb
+    assert np.array_equal(da, db, equal_nan=True)
+    assert np.array_equal(sa, sb)

@@ -140,13 +140,15 @@ def test_sghmc_sgld_constructors():
 
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the driver's reference arm) runs without a GPU and prints exactly
-    ONE JSON line on stdout with the contract's keys"""
+    ONE JSON line on stdout with the contract's keys (eight schools here: the default configs[2]
+    workload takes minutes of host time per chain)"""
     import json
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0", "--ref-budget", "1"], capture_output=True, text=True, timeout=300)
+                          "--warmup", "0", "--workload", "eight_schools", "--ref-quick", "--no-cache"],
+                         capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, out.stdout
@@ -158,3 +160,28 @@ def test_bench_reference_arm_contract():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "grad_evals/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
+
+
+def test_bench_cpu_block_steps_continue_the_full_job(tmp_path, monkeypatch):
+    """the CPU arm of the configs[2] bench: whole schedule on `cores` chains (cached for the other arm),
+    then steps that continue the adapted chains -- here on a small logistic model"""
+    import importlib.util
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    monkeypatch.setattr(b.tempfile, "gettempdir", lambda: str(tmp_path))
+    model = T.models.synthetic_logistic(300, 6, seed=3)
+    model.N = 300
+    spl = T.NUTS(0.8)
+    # make the small model take the "heavy" path (cores chains, block steps)
+    monkeypatch.setattr(b, "host_cores", lambda: 2)
+    full, st = b.cpu_full_job("logistic_test", model, spl, 1000, quick=True)
+    assert full["cached"] is False and full["chains"] == 256 and full["grad_evals"] > 0
+    full2, st2 = b.cpu_full_job("logistic_test", model, spl, 1000, quick=True)
+    assert isinstance(full2["cached"], str) and np.array_equal(st["theta"], st2["theta"])
+    g, dt = b.cpu_block(model, spl, full, st, 3)
+    assert g > 3 * full["chains"] and dt > 0
+    cb = b.cpu_baseline_object(full, g / dt, "blocks")
+    assert cb["kind"] == "port" and cb["whole_job_grad_evals_per_sec"] == full["value"]

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import oracle as O
+import turing_jl_b200 as T
 from oracle import diagnostics as dg
 
 from helpers import golden_cases, model_from_golden, oracle_of
@@ -236,3 +237,19 @@ def test_dense_metric_oracle():
     r = O.sample_chains(gd, O.make_config(delta=0.65, n_adapts=300, seed=6, metric=2, algorithm=2, lambda_=0.3),
                         8, 1500, first_keep=301)
     assert abs(r["params"][:, :, 1].mean() - 7 / 6) < 0.15
+
+
+def test_resume_continues_bit_for_bit_and_chain_ids_address_the_streams():
+    """orc_resume_chains (bench.py's CPU step unit) == the uninterrupted run; orc_sample_chain_ids
+    runs any subset of the global chain ids"""
+    m = T.models.synthetic_logistic(300, 7, seed=2)
+    om = oracle_of(m)
+    cfg = O.make_config(delta=0.8, n_adapts=30, seed=5)
+    a = O.sample_chains(om, cfg, 6, 60)
+    b = O.sample_chains(om, cfg, 6, 40)
+    r = O.resume_chains(om, cfg, b["theta"][:, -1], b["eps"], b["minv"], 40, 20)
+    assert np.array_equal(r["theta"], a["theta"][:, 40:])
+    assert np.array_equal(r["stats"][..., 0], a["stats"][:, 40:, 0])
+    assert b["n_grad"] + r["n_grad"] == a["n_grad"] + 6      # one re-evaluation per restored chain
+    sub = O.sample_chains(om, cfg, 0, 60, chain_ids=[4, 1])
+    assert np.array_equal(sub["theta"][0], a["theta"][4]) and np.array_equal(sub["theta"][1], a["theta"][1])

@@ -77,6 +77,9 @@ SYMBOLS = {
     "tnuts_init_device_seconds": (C.c_double, [_H]),
     "tnuts_init_tries_max": (C.c_int, [_H]),
     "tnuts_get_dense_inv_metric": (C.c_int, [_H, _dp]),
+    "tnuts_kernel_times": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_int64),
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_int64)]),
     "tnuts_bench_gradient": (C.c_int, [_H, C.c_int32, C.POINTER(C.c_double)]),
     "tnuts_comm_unique_id": (C.c_int, [C.c_void_p]),
     "tnuts_comm_init": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),

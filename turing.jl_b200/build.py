@@ -12,6 +12,10 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libtnuts.so")
 
+# per-file extra flags: the persistent pump kernel reads, in one phase, what another SM wrote in the
+# previous one, so its global loads must bypass the (non-coherent) L1
+EXTRA_FLAGS = {"persist.cu": ["-Xptxas", "-dlcm=cg"]}
+
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -71,7 +75,8 @@ def build(force=False, verbose=False):
         if (not force and os.path.exists(obj)
                 and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t)):
             return obj, ""
-        r = subprocess.run([nvcc, *flags, "-c", src, "-o", obj], capture_output=True, text=True)
+        extra = EXTRA_FLAGS.get(os.path.basename(src), [])
+        r = subprocess.run([nvcc, *flags, *extra, "-c", src, "-o", obj], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stderr))
         return obj, r.stderr

@@ -500,8 +500,8 @@ k_block_run(ModelDev m, HierStatsDev hs, ChainState st, RunParams rp, double *dr
         const double eta_x = pow((double)mm, -0.75);
         const double xbar = (1.0 - eta_x) * da_xbar + eta_x * x;
         const double e = exp(x);
-        da_m = mm;
-        if (isfinite(e)) {
+        if (isfinite(e)) {  // a non-finite step size reverts m, x_bar, H_bar and eps (AdvancedHMC adapt_stepsize!)
+          da_m = mm;
           da_hbar = hbar;
           da_xbar = xbar;
           da_eps = e;

@@ -3,7 +3,6 @@
 
 #include <algorithm>
 
-#include "chain_flat.cuh"
 #include "chain_kernels.cuh"
 #include "engine.cuh"
 
@@ -82,9 +81,7 @@ int thread_run(Engine *e) {
     const int g_ = grid_for(e->st.C, kChainBlock);                                           \
     const int *pm_ = e->perm_valid ? e->perm : nullptr;                                      \
     const size_t sm_ = e->ck_smem ? chain_ck_smem_bytes<M::D>() : 0;                         \
-    if (e->flat && e->cfg.algorithm == TNUTS_ALG_NUTS)                                       \
-      k_chain_run_flat<M, 2><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_); \
-    else if (e->cfg.algorithm != TNUTS_ALG_NUTS)                                             \
+    if (e->cfg.algorithm != TNUTS_ALG_NUTS)                                               \
       k_chain_run<M, 2, false><<<g_, kChainBlock, 0, e->stream>>>(e->small, e->st, e->out, e->rp, pm_, 0); \
     else if (dyn_ok) {                                                                       \
       int per_sm_ = 0;                                                                       \

@@ -499,8 +499,8 @@ __device__ __forceinline__ void chain_run_range(const SmallData &md, const Chain
         const double eta_x = pow((double)mm, -0.75);
         const double xbar = (1.0 - eta_x) * da_xbar + eta_x * x;
         const double e = exp(x);
-        da_m = mm;
-        if (isfinite(e)) {
+        if (isfinite(e)) {  // a non-finite step size reverts m, x_bar, H_bar and eps (AdvancedHMC adapt_stepsize!)
+          da_m = mm;
           da_hbar = hbar;
           da_xbar = xbar;
           da_eps = e;
@@ -798,8 +798,8 @@ __global__ void __launch_bounds__(kChainBlock, MINB) k_chain_run_dense(SmallData
         const double eta_x = pow((double)mm, -0.75);
         const double xbar = (1.0 - eta_x) * da_xbar + eta_x * x;
         const double e = exp(x);
-        da_m = mm;
-        if (isfinite(e)) {
+        if (isfinite(e)) {  // a non-finite step size reverts m, x_bar, H_bar and eps (AdvancedHMC adapt_stepsize!)
+          da_m = mm;
           da_hbar = hbar;
           da_xbar = xbar;
           da_eps = e;

@@ -92,7 +92,6 @@ struct RunParams {
   long long splits[24];
   // this call
   long long n_transitions, first_keep, thin;
-  int flat_batch;  // lanes that must wait before a warp runs a transition boundary (flat kernel)
   int unit_metric; // TNUTS_METRIC_UNIT: the adaptation windows run, the mass matrix stays the identity
 };
 

@@ -207,7 +207,6 @@ int tnuts_create(const tnuts_config *cfg, tnuts_engine **out) {
   rp.lambda = cfg->lambda;
   rp.seed = cfg->seed;
   rp.chain_offset = cfg->chain_offset;
-  rp.flat_batch = 12;
   rp.unit_metric = cfg->metric == TNUTS_METRIC_UNIT ? 1 : 0;
   window_schedule(cfg->n_adapts, rp);
   *out = (tnuts_engine *)e;
@@ -529,12 +528,11 @@ int tnuts_set_option(tnuts_engine *h, const char *name, double value) {
   const std::string n(name);
   if (n == "keep_theta") e->keep_theta = value != 0.0;
   else if (n == "sort_chains") e->sort_chains = value != 0.0;
-  else if (n == "flat") e->flat = value != 0.0;
-  else if (n == "flat_batch") e->rp.flat_batch = (int)value;
   else if (n == "dyn_sched") e->dyn_sched = value != 0.0;
   else if (n == "ck_smem") e->ck_smem = value != 0.0;
   else if (n == "logistic_tc") e->logistic_tc = value != 0.0;
-
+  else if (n == "time_kernels") e->time_kernels = value != 0.0;
+  else if (n == "persist") e->persist = value != 0.0;
   else return set_error(e, TNUTS_E_ARG, "tnuts_set_option: unknown option " + n);
   return TNUTS_OK;
 }
@@ -724,7 +722,9 @@ struct BlobHeader {
   int32_t C, D, family, algorithm;
   int64_t n_adapts;
   uint64_t seed;
+  int32_t metric, chain_offset;
 };
+static constexpr uint32_t kBlobVersion = 2u;
 static constexpr uint32_t kBlobMagic = 0x544e5554u;  // "TUNT"
 
 static size_t blob_bytes(const Engine *e) {
@@ -744,8 +744,8 @@ int tnuts_get_state(tnuts_engine *h, void *blob, size_t *nbytes) {
   if (*nbytes < need) return set_error(e, TNUTS_E_ARG, "tnuts_get_state: buffer too small");
   TN_CUDA(e, cudaSetDevice(e->device));
   const size_t C = (size_t)e->st.C, D = (size_t)e->D;
-  BlobHeader hd{kBlobMagic, 1u, (int32_t)C, (int32_t)D, e->model.family, e->cfg.algorithm,
-                e->cfg.n_adapts, e->cfg.seed};
+  BlobHeader hd{kBlobMagic, kBlobVersion, (int32_t)C, (int32_t)D, e->model.family, e->cfg.algorithm,
+                e->cfg.n_adapts, e->cfg.seed, e->cfg.metric, e->cfg.chain_offset};
   char *p = (char *)blob;
   std::memcpy(p, &hd, sizeof(hd));
   p += sizeof(hd);
@@ -783,6 +783,16 @@ int tnuts_set_state(tnuts_engine *h, const void *blob, size_t nbytes) {
   std::memcpy(&hd, blob, sizeof(hd));
   if (hd.magic != kBlobMagic || hd.C != e->st.C || hd.D != e->D || hd.family != e->model.family)
     return set_error(e, TNUTS_E_ARG, "tnuts_set_state: blob does not match this engine");
+  if (hd.version != kBlobVersion)
+    return set_error(e, TNUTS_E_ARG, "tnuts_set_state: blob was written by another version of the library");
+  // The arrays mean different things per sampler (SGHMC keeps its velocity where NUTS keeps the
+  // Welford mean) and per metric, and the random streams are addressed by (seed, global chain id):
+  // a blob from another sampler / metric / seed / shard would continue a different chain silently.
+  if (hd.algorithm != e->cfg.algorithm || hd.metric != e->cfg.metric)
+    return set_error(e, TNUTS_E_ARG, "tnuts_set_state: blob comes from another sampler or metric");
+  if (hd.seed != e->cfg.seed || hd.chain_offset != e->cfg.chain_offset)
+    return set_error(e, TNUTS_E_ARG, "tnuts_set_state: blob comes from another seed or chain shard "
+                                     "(create the engine with the blob's seed and chain_offset)");
   TN_CUDA(e, cudaSetDevice(e->device));
   const size_t C = (size_t)e->st.C, D = (size_t)e->D;
   const char *p = (const char *)blob + sizeof(hd);
@@ -888,6 +898,19 @@ int tnuts_init_tries_max(const tnuts_engine *h) {
   int m = 0;
   for (int x : v) m = x > m ? x : m;
   return m;
+}
+
+int tnuts_kernel_times(const tnuts_engine *h, double *seconds, int64_t *launches, int64_t *sampled,
+                       int64_t *tile_launches, double *persist_seconds, int64_t *persist_pumps) {
+  const Engine *e = (const Engine *)h;
+  if (!e) return TNUTS_E_ARG;
+  if (seconds) *seconds = e->strategy == STRAT_LOCKSTEP ? e->kernel_seconds : e->last_run_seconds;
+  if (launches) *launches = e->strategy == STRAT_LOCKSTEP ? e->kernel_launches : 1;
+  if (sampled) *sampled = e->strategy == STRAT_LOCKSTEP ? e->kernel_sampled : 1;
+  if (tile_launches) *tile_launches = e->kernel_tile_launches;
+  if (persist_seconds) *persist_seconds = e->persist_seconds;
+  if (persist_pumps) *persist_pumps = e->persist_pumps;
+  return TNUTS_OK;
 }
 
 int tnuts_bench_gradient(tnuts_engine *h, int32_t reps, double *seconds) {

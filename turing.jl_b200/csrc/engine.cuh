@@ -52,7 +52,6 @@ struct Engine {
   size_t perm_tmp_bytes = 0;
   bool perm_valid = false, sort_chains = true;
   long long host_iter = 0;  // transitions done since init (identical for every chain)
-  bool flat = false;  // flat-scheduled thread-per-chain kernel (chain_flat.cuh)
   bool dyn_sched = true;   // thread-per-chain: task queue over (transition sub-range, chain group)
   int *dyn_work = nullptr; // [1 + groups]: task counter, per-group completed sub-ranges
   bool ck_smem = true;     // thread-per-chain NUTS: lowest checkpoint levels in shared memory
@@ -60,6 +59,17 @@ struct Engine {
   // logistic regression: likelihood gradient on the tcgen05 tensor cores (bf16x3 planes, fp32-grade
   // dot products, logistic_tc.cuh) instead of the fp64 DMMA kernel; opt-in, D <= 128
   bool logistic_tc = false;
+  // measurement aid (option "time_kernels"): CUDA-event time of the dominant kernel's launches inside
+  // tnuts_run (lock-step strategy: the family's batched gradient kernel), a systematic sample
+  bool time_kernels = false;
+  double kernel_seconds = 0.0;      // estimated total over the last run (sampled sum x stride)
+  long long kernel_launches = 0;    // gradient-kernel launches of the last run
+  long long kernel_sampled = 0;     // launches actually bracketed by events
+  long long kernel_tile_launches = 0;  // sum over launches of 128-chain tiles (tcgen05 path)
+  // the tail of a lock-step run as one persistent cooperative kernel (tc_persist.cuh); option "persist"
+  bool persist = true;
+  double persist_seconds = 0.0;     // CUDA-event time of the persistent launches of the last run
+  long long persist_pumps = 0;      // pumps (leapfrogs of every unfinished chain) they executed
 
   LockstepState *ls = nullptr;
   DiagWork *diag = nullptr;
@@ -109,10 +119,6 @@ int lockstep_point_constrain(Engine *e, const double *theta_dev, long long n, do
 int lockstep_point_leapfrog(Engine *e, const double *theta_dev, const double *r_dev,
                             const double *minv_dev, double eps, int L, long long n,
                             double *tt_dev, double *tr_dev, double *tH_dev);
-
-// comm.cu
-int comm_allreduce_sum(Engine *e, double *buf, size_t n);
-void comm_destroy(Engine *e);
 
 // comm.cu
 int comm_allreduce_sum(Engine *e, double *buf, size_t n);

@@ -22,6 +22,11 @@
 namespace tnuts {
 
 int comm_allreduce_sum(Engine *e, double *buf, size_t n);  // comm.cu (no-op when world == 1)
+namespace tc { struct Data; }
+// persist.cu: the tail of a run as one persistent cooperative kernel (tc_persist.cuh)
+int tc_persist_run(Engine *e, const tc::Data &td, double *part, int stride, int *count_done_dev, int *h_done,
+                   long long pump0, long long max_pumps, int listed_done, int n_max, long long *pumps,
+                   int *n_done);
 
 template <class T>
 static int ls_alloc(Engine *e, std::vector<void *> *pool, T **p, size_t n) {
@@ -103,6 +108,71 @@ static int logistic_plan(const ModelDev &m, int cap, LogiPlan *p) {
 
 static tc::Data *tc_data_of(Engine *e);
 
+// Option "time_kernels": CUDA events around a systematic sample of the gradient-kernel launches of
+// a run (every stride-th launch; when the event pool is full, every other sample is dropped and the
+// stride doubles), so that bench.py can state the kernel's time inside its own timed region.
+struct KernelTimer {
+  static constexpr int kCap = 2048;
+  std::vector<cudaEvent_t> ev;   // 2 per sample
+  std::vector<long long> idx;    // launch index of every sample
+  long long stride = 1, launches = 0, tiles = 0;
+  bool armed = false;            // this launch is bracketed
+  void begin_run() {
+    idx.clear();
+    stride = 1;
+    launches = tiles = 0;
+  }
+  void before(cudaStream_t s) {
+    armed = false;
+    if (launches % stride == 0) {
+      if ((int)idx.size() == kCap) {  // thin out: keep the samples on the doubled stride
+        stride *= 2;
+        size_t w = 0;
+        for (size_t r = 0; r < idx.size(); ++r)
+          if (idx[r] % stride == 0) {
+            std::swap(ev[2 * w], ev[2 * r]);
+            std::swap(ev[2 * w + 1], ev[2 * r + 1]);
+            idx[w++] = idx[r];
+          }
+        idx.resize(w);
+      }
+      if (launches % stride == 0) {
+        const size_t k = idx.size();
+        while (ev.size() < 2 * (k + 1)) {
+          cudaEvent_t x;
+          if (cudaEventCreate(&x) != cudaSuccess) return;
+          ev.push_back(x);
+        }
+        idx.push_back(launches);
+        cudaEventRecord(ev[2 * k], s);
+        armed = true;
+      }
+    }
+  }
+  void after(cudaStream_t s, long long n_tiles) {
+    if (armed) cudaEventRecord(ev[2 * idx.size() - 1], s);
+    armed = false;
+    launches += 1;
+    tiles += n_tiles;
+  }
+  // call after the stream has been synchronised
+  void finish(Engine *e) {
+    double tot = 0.0;
+    for (size_t k = 0; k < idx.size(); ++k) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev[2 * k], ev[2 * k + 1]) == cudaSuccess) tot += ms * 1e-3;
+    }
+    e->kernel_sampled = (long long)idx.size();
+    e->kernel_launches = launches;
+    e->kernel_tile_launches = tiles;
+    e->kernel_seconds = idx.empty() ? 0.0 : tot * ((double)launches / (double)idx.size());
+  }
+  ~KernelTimer() {
+    for (cudaEvent_t x : ev) cudaEventDestroy(x);
+  }
+};
+static KernelTimer *timer_of(Engine *e);
+
 static int grad_launch(Engine *e, const double *th, int C, double *lp, double *g, const int *list,
                        const int *count, int n_all, int n_max, GradWork *gw) {
   const ModelDev &m = e->model;
@@ -138,8 +208,13 @@ static int grad_launch(Engine *e, const double *th, int C, double *lp, double *g
         tc::cut_for(m.N, (n_max + tc::kChainsPerCta - 1) / tc::kChainsPerCta, &chunks, &rpc_);
         if ((size_t)chunks * stride * ((size_t)D + 1) > gw->part_elems)
           return set_error(e, TNUTS_E_UNSUPPORTED, "logistic_tc: partial buffer too small");
+        KernelTimer *kt = e->time_kernels ? timer_of(e) : nullptr;
+        if (kt) kt->before(e->stream);
         TN_CUDA(e, tc::launch(*td, m.N, D, th, C, list, count, n_all, n_max, gw->part, stride, e->stream));
+        if (kt) kt->after(e->stream, (n_max + tc::kChainsPerCta - 1) / tc::kChainsPerCta);
       } else {
+      KernelTimer *kt = e->time_kernels ? timer_of(e) : nullptr;
+      if (kt) kt->before(e->stream);
       const dim3 grid((n_max + lp_.tch - 1) / lp_.tch, (chunks + lp_.ng - 1) / lp_.ng);
 #define TN_LOGI(NWN, NWM, MT, TR, NG)                                                                 \
   do {                                                                                                \
@@ -165,6 +240,7 @@ static int grad_launch(Engine *e, const double *th, int C, double *lp, double *g
       else if (lp_.mt == 13) TN_LOGI(8, 1, 13, 64, 1);
       else TN_LOGI(8, 1, 16, 64, 1);
 #undef TN_LOGI
+      if (kt) kt->after(e->stream, (n_max + lp_.tch - 1) / lp_.tch);
       }
       if (e->world > 1 && e->cfg.row_shards > 1) {
         const dim3 rg((n_max + 127) / 128, D + 1);
@@ -199,9 +275,7 @@ static int gradwork_alloc(Engine *e, GradWork *gw, int cap, std::vector<void *> 
   int max_chunks = lp_.chunks;
   tc::Plan tp;
   if (tc::plan(e->model.N, e->model.D, &tp)) {
-    int c1, r1;
-    tc::cut_for(e->model.N, 1, &c1, &r1);  // the finest cut
-    if (c1 > max_chunks) max_chunks = c1;
+    if (tc::kSMs > max_chunks) max_chunks = tc::kSMs;  // the finest cut of tc::cut_for
   }
   gw->part_elems = (size_t)max_chunks * gw->stride * ((size_t)e->model.D + 1);
   const size_t D1 = (size_t)e->model.D + 1;
@@ -220,10 +294,12 @@ struct LockstepExt {
   LockstepState ls;  // first member: Engine::ls points here
   GradWork gw;
   tc::Data tcd;      // logistic regression on tcgen05 (option "logistic_tc"), built on first use
+  KernelTimer timer; // option "time_kernels"
   std::vector<void *> allocs;
 };
 static LockstepExt *ext_of(Engine *e) { return reinterpret_cast<LockstepExt *>(e->ls); }
 static tc::Data *tc_data_of(Engine *e) { return &ext_of(e)->tcd; }
+static KernelTimer *timer_of(Engine *e) { return &ext_of(e)->timer; }
 
 // ------------------------------------------------------------------------------------------
 int lockstep_create(Engine *e) {
@@ -639,6 +715,13 @@ int lockstep_run(Engine *e) {
   const bool lockstep_ranks = (e->world > 1 && e->cfg.row_shards > 1) ||
                               (e->logistic_tc && e->model.family == TNUTS_LOGISTIC);
   int done = 0;
+  // option "persist" (default on): tcgen05 logistic likelihood on one GPU (the per-leapfrog NCCL
+  // all-reduce of row shards cannot run inside the persistent kernel)
+  const bool persist_ok = e->persist && e->logistic_tc && e->model.family == TNUTS_LOGISTIC &&
+                          !(e->world > 1 && e->cfg.row_shards > 1);
+  e->persist_seconds = 0.0;
+  e->persist_pumps = 0;
+  if (e->time_kernels) timer_of(e)->begin_run();
   static const bool trace = getenv("TNUTS_PUMP_TRACE") != nullptr;
   long long pumps_done = 0;
   for (long long pump = 0; pump < max_pumps; ++pump) {
@@ -669,6 +752,42 @@ int lockstep_run(Engine *e) {
       e->launches += 2;
       listed_done = done;
       n_max = C - done;
+      if (persist_ok && n_max <= tc::kPersistMaxTiles * tc::kChainsPerCta) {
+        // The listed chains fit one wave of (chain tile, row chunk) CTAs: the rest of the run is ONE
+        // persistent cooperative kernel (tc_persist.cuh), same arithmetic and same refresh schedule.
+        tc::Data *td = tc_data_of(e);
+        if (!td->ready) {
+          const char *msg = tc::prepare(e->model.X, e->model.y, e->model.N, e->model.D, e->stream, td);
+          if (msg) {
+            rc = set_error(e, TNUTS_E_UNSUPPORTED, msg);
+            break;
+          }
+          e->launches += 2;
+        }
+        GradWork *gw = gw_of(e);
+        cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+        if (e->time_kernels) {
+          cudaEventCreate(&pe0);
+          cudaEventCreate(&pe1);
+          cudaEventRecord(pe0, e->stream);
+        }
+        long long ran = 0;
+        int nd = 0;
+        rc = tc_persist_run(e, *td, gw->part, gw->stride, ls->count + 1, ls->h_count, pump, max_pumps, listed_done,
+                            n_max, &ran, &nd);
+        if (e->time_kernels) {
+          float ms = 0.f;
+          if (!rc && cudaEventRecord(pe1, e->stream) == cudaSuccess && cudaEventSynchronize(pe1) == cudaSuccess &&
+              cudaEventElapsedTime(&ms, pe0, pe1) == cudaSuccess)
+            e->persist_seconds += ms * 1e-3;
+          cudaEventDestroy(pe0);
+          cudaEventDestroy(pe1);
+        }
+        e->persist_pumps += ran;
+        pumps_done = pump + ran;
+        if (trace) fprintf(stderr, "[tnuts pump] persistent kernel from pump %lld: %lld pumps, done=%d\n", pump, ran, nd);
+        break;   // the completion check below reports chains the pump budget left unfinished
+      }
     }
     if (pump > 0) {  // on the first pump no leaf is pending yet
       if ((rc = grad_launch(e, ls->zt, C, ls->ts.zlp, ls->zg, ls->list, ls->count, C, n_max, gw_of(e)))) break;
@@ -687,6 +806,15 @@ int lockstep_run(Engine *e) {
   if (trace) fprintf(stderr, "[tnuts pump] finished after %lld pumps\n", pumps_done);
   if (rc) return rc;
   TN_CUDA(e, cudaGetLastError());
+  // The loop is bounded (max_pumps): make sure every chain really finished, otherwise the rows of
+  // the kept-draw buffer that were never written would be reported as draws.
+  TN_CUDA(e, cudaMemcpyAsync(ls->h_count + 1, ls->count + 1, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  TN_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (e->time_kernels) timer_of(e)->finish(e);
+  if (ls->h_count[1] < C)
+    return set_error(e, TNUTS_E_UNSUPPORTED,
+                     "tnuts_run: " + std::to_string(C - ls->h_count[1]) + " chains did not finish their transitions within the "
+                     "pump budget (HMCDA with a collapsing step size: lambda / eps leapfrogs per transition)");
   return TNUTS_OK;
 }
 

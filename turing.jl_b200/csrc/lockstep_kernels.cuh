@@ -21,6 +21,49 @@ __device__ __forceinline__ double ls_logaddexp(double a, double b) {
   return mx + log1p(exp(-fabs(a - b)));
 }
 
+// A "team" is the 256 threads that own one tile of 8 chains.  In the stand-alone kernels it is the
+// whole CTA; inside the persistent pump kernel (tc_persist.cuh) it is 8 warps of a larger CTA that
+// synchronise on a named barrier.  tid() is the thread's index inside its team.
+struct BlockTeam {
+  static constexpr bool kContiguous = true;   // the tile's 8 chains are consecutive (64 B per d)
+  __device__ static __forceinline__ int tid() { return threadIdx.x; }
+  __device__ static __forceinline__ void sync() { __syncthreads(); }
+  __device__ static __forceinline__ int sync_or(int p) { return __syncthreads_or(p); }
+  __device__ static __forceinline__ int sync_and(int p) { return __syncthreads_and(p); }
+};
+template <int BAR, int TID0>
+struct NamedTeam {
+  static constexpr bool kContiguous = false;  // chains picked from the work list
+  __device__ static __forceinline__ int tid() { return (int)threadIdx.x - TID0; }
+  __device__ static __forceinline__ void sync() {
+    asm volatile("bar.sync %0, %1;" ::"r"(BAR), "r"(kTileThreads) : "memory");
+  }
+  __device__ static __forceinline__ int sync_or(int p) {
+    int r;
+    asm volatile(
+        "{\n\t.reg .pred q, r;\n\t"
+        "setp.ne.s32 q, %1, 0;\n\t"
+        "bar.red.or.pred r, %2, %3, q;\n\t"
+        "selp.s32 %0, 1, 0, r;\n\t}"
+        : "=r"(r)
+        : "r"(p), "r"(BAR), "r"(kTileThreads)
+        : "memory");
+    return r;
+  }
+  __device__ static __forceinline__ int sync_and(int p) {
+    int r;
+    asm volatile(
+        "{\n\t.reg .pred q, r;\n\t"
+        "setp.ne.s32 q, %1, 0;\n\t"
+        "bar.red.and.pred r, %2, %3, q;\n\t"
+        "selp.s32 %0, 1, 0, r;\n\t}"
+        : "=r"(r)
+        : "r"(p), "r"(BAR), "r"(kTileThreads)
+        : "memory");
+    return r;
+  }
+};
+
 struct Tile {
   int c, cl, dl;
   __device__ Tile() {
@@ -28,23 +71,30 @@ struct Tile {
     dl = threadIdx.x >> 3;
     c = blockIdx.x * kTileC + cl;
   }
+  // thread `tid` of a team; its chain id is given (any chain: the tile need not be contiguous)
+  __device__ Tile(int tid, int chain) {
+    cl = tid & (kTileC - 1);
+    dl = tid >> 3;
+    c = chain;
+  }
 };
 
 // sum over the 32 d-lanes of each chain for NR values at once; result valid in every thread
-template <int NR>
+template <int NR, class TM = BlockTeam>
 __device__ __forceinline__ void tile_reduce(double (&v)[NR], double *smem /* [NR][8][8] */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, cl = threadIdx.x & 7;
+  const int tid = TM::tid();
+  const int lane = tid & 31, warp = tid >> 5, cl = tid & 7;
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     v[r] += __shfl_xor_sync(0xffffffffu, v[r], 8);
     v[r] += __shfl_xor_sync(0xffffffffu, v[r], 16);
   }
-  __syncthreads();  // protect smem reuse between consecutive calls
+  TM::sync();  // protect smem reuse between consecutive calls
   if (lane < 8) {
 #pragma unroll
     for (int r = 0; r < NR; ++r) smem[(r * 8 + warp) * 8 + lane] = v[r];
   }
-  __syncthreads();
+  TM::sync();
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     double s = 0.0;
@@ -125,6 +175,7 @@ static __device__ void ls_prior_small(const ModelDev &m, const double *th, int C
 }
 
 // tile-level user-space log-probs for any family; th = [D][C] column c; lp = linked log joint
+template <class TM = BlockTeam>
 __device__ __forceinline__ void ls_user_logp(const ModelDev &m, const double *th, int C, const Tile &t,
                                              bool in, double lp, double *red, double &prior,
                                              double &lik) {
@@ -136,7 +187,7 @@ __device__ __forceinline__ void ls_user_logp(const ModelDev &m, const double *th
         const double x = th[(size_t)d * C + t.c];
         q[0] += x * x;
       }
-    tile_reduce<1>(q, red);
+    tile_reduce<1, TM>(q, red);
     const double sd = m.hyper[0];
     prior = -0.5 * m.D * kLog2Pi - m.D * log(sd) - 0.5 * q[0] / (sd * sd);
     lik = lp - prior;
@@ -154,7 +205,7 @@ __device__ __forceinline__ void ls_user_logp(const ModelDev &m, const double *th
         q[1] += eb * eb;
       }
     }
-    tile_reduce<2>(q, red);
+    tile_reduce<2, TM>(q, red);
     if (in) {
       const double sdm = m.hyper[0], s0 = m.hyper[1];
       const double la = th[(size_t)2 * C + t.c], lb = th[(size_t)3 * C + t.c], ly = th[(size_t)4 * C + t.c];
@@ -261,13 +312,14 @@ k_sg_step(ChainState st, RunParams rp, ModelDev m, DrawBuffers out, long long k_
 // Per-chain scalar logic is computed redundantly by the chain's 32 threads (identical inputs
 // => identical results); every reduction over d is executed CTA-uniformly.
 // ------------------------------------------------------------------------------------------
-static __global__ void __launch_bounds__(kTileThreads)
-k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers out, int *n_done,
-          int *h_done /* mapped pinned host word */) {
-  __shared__ double red[2 * 64];
-  __shared__ int s_maxlev;
-  const Tile t;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *(volatile int *)h_done = *(volatile int *)n_done;
+// The per-chain state machine for one tile of 8 chains, executed by a team of 256 threads.
+// `t` carries the thread's chain id (t.c >= st.C: no chain in this lane) and d-lane;
+// `red` is [2 * 64] doubles and `s_maxlev_p` one int of shared memory private to the team.
+template <class TM>
+__device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, LockstepState ls, RunParams rp,
+                                             ModelDev m, DrawBuffers out, int *n_done, double *red,
+                                             int *s_maxlev_p) {
+  int &s_maxlev = *s_maxlev_p;
   const int C = st.C, D = st.D;
   TreeScalars &s = ls.ts;
   const size_t DC = (size_t)D * C;
@@ -283,19 +335,21 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
   const bool in = t.c < C && st.status[t.c] == 0;
   int phase = in ? s.phase[t.c] : 2;
   // a CTA whose 8 chains have all finished has nothing to do (the tail of a run is mostly such CTAs)
-  if (__syncthreads_and(phase == 2)) return;
+  if (TM::sync_and(phase == 2)) return;
   // The kernel is a chain of dependent passes over this chain's columns with a block reduction
   // between them, and the gradient kernel that ran just before has pushed those columns out of L2
   // (ncu: long-scoreboard stall 21 per issue, L2 hit rate 45 %).  Start all the misses at once:
   // one prefetch per 32-byte sector (4 chains) of every array the common leaf path reads.
-  if (phase == 1 && (t.cl & 3) == 0) {
-    for (int d = t.dl; d < D; d += kTileD) {
-      const size_t o = (size_t)d * C + t.c;
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(zg_ + o));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(zr_ + o));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(minv_ + o));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(rhos_ + o));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(zt_ + o));
+  if (TM::kContiguous) {
+    if (phase == 1 && (t.cl & 3) == 0) {
+      for (int d = t.dl; d < D; d += kTileD) {
+        const size_t o = (size_t)d * C + t.c;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(zg_ + o));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(zr_ + o));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(minv_ + o));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(rhos_ + o));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(zt_ + o));
+      }
     }
   }
   const uint32_t gchain = (uint32_t)(rp.chain_offset + t.c);
@@ -332,7 +386,7 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
       a1[1] += isfinite(g) ? 0.0 : 1.0;
     }
   }
-  tile_reduce<2>(a1, red);
+  tile_reduce<2, TM>(a1, red);
   const bool hmc = rp.algorithm != TNUTS_ALG_NUTS;
   bool accept = false, divergent = false, term_s = false, sub_done = false;
   bool trans_end = false;
@@ -397,10 +451,10 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
   const int ntrail = __ffs(~(unsigned)n) - 1;
   const int idx_min = idx_max - ntrail + 1;
   const int nlev = (leaf && !hmc && odd && !divergent) ? (idx_max - idx_min + 1) : 0;
-  if (threadIdx.x == 0) s_maxlev = 0;
-  __syncthreads();
+  if (TM::tid() == 0) s_maxlev = 0;
+  TM::sync();
   if (t.dl == 0 && nlev > 0) atomicMax(&s_maxlev, nlev);
-  __syncthreads();
+  TM::sync();
   const int maxlev = s_maxlev;
   double dots[2 * kMaxLevels];
 #pragma unroll
@@ -435,7 +489,7 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
   }
   for (int q = 0; q < maxlev; ++q) {  // CTA-uniform trip count
     double pr[2] = {dots[2 * q], dots[2 * q + 1]};
-    tile_reduce<2>(pr, red);
+    tile_reduce<2, TM>(pr, red);
     if (q < nlev && ((pr[0] <= 0.0) || (pr[1] <= 0.0))) term_s = true;
   }
   if (leaf && !hmc) {
@@ -444,7 +498,7 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
   }
 
   // ================= [B] end of a doubling =================
-  if (__syncthreads_or(leaf && sub_done)) {
+  if (TM::sync_or(leaf && sub_done)) {
     const bool me = leaf && sub_done;
     bool take = false;
     if (me && !term_s) {
@@ -474,7 +528,7 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
         d2[1 - v] += rho * (mi * eo[DC + o]);
       }
     }
-    tile_reduce<2>(d2, red);
+    tile_reduce<2, TM>(d2, red);
     if (me) {
       if (v) elp1 = zlp; else elp0 = zlp;
       if (!term_s) {
@@ -508,7 +562,7 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
   }
 
   // ================= [T] end of a transition =================
-  if (__syncthreads_or(trans_end)) {
+  if (TM::sync_or(trans_end)) {
     long long k_slot = -1;
     bool adapt = false, in_window = false, wend = false;
     long long wf_n = 0;
@@ -557,10 +611,10 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
       stats[ST_NUMERR] = (double)numerr;
       stats[ST_EPS] = eps;
     }
-    if (__syncthreads_or(trans_end && k_slot >= 0)) {
+    if (TM::sync_or(trans_end && k_slot >= 0)) {
       const bool rec = trans_end && k_slot >= 0;
       double prior, lik;
-      ls_user_logp(m, thC_, C, t, rec, rec ? lpC : 0.0, red, prior, lik);
+      ls_user_logp<TM>(m, thC_, C, t, rec, rec ? lpC : 0.0, red, prior, lik);
       if (rec) {
         double *row = out.draws + (size_t)k_slot * out.ncol * C + t.c;
     #pragma unroll 4
@@ -591,8 +645,8 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
         const double eta_x = pow((double)mm, -0.75);
         const double xbar = (1.0 - eta_x) * da_xbar + eta_x * x;
         const double e = exp(x);
-        da_m = mm;
-        if (isfinite(e)) {
+        if (isfinite(e)) {  // a non-finite step size reverts m, x_bar, H_bar and eps (AdvancedHMC adapt_stepsize!)
+          da_m = mm;
           da_hbar = hbar;
           da_xbar = xbar;
           da_eps = e;
@@ -632,7 +686,7 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
   }
 
   // ================= [S] start of a transition =================
-  if (__syncthreads_or(start_transition)) {
+  if (TM::sync_or(start_transition)) {
     double acc[1] = {0.0};
     double lp0 = 0.0;
     if (start_transition) {
@@ -663,7 +717,7 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
         rhos_[o] = 0.0;
       }
     }
-    tile_reduce<1>(acc, red);
+    tile_reduce<1, TM>(acc, red);
     if (start_transition) {
       const double K = 0.5 * acc[0];
       H0 = (isfinite(lp0) && isfinite(K)) ? (-lp0 + K) : CUDART_INF;
@@ -715,6 +769,16 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
     }
     if (leaf) st.n_grad[t.c] += 1;
   }
+}
+
+static __global__ void __launch_bounds__(kTileThreads)
+k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers out, int *n_done,
+          int *h_done /* mapped pinned host word */) {
+  __shared__ double red[2 * 64];
+  __shared__ int s_maxlev;
+  const Tile t;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *(volatile int *)h_done = *(volatile int *)n_done;
+  ls_pump_body<BlockTeam>(t, st, ls, rp, m, out, n_done, red, &s_maxlev);
 }
 
 // arm a run: every chain gets its transition window [iter0, iter_end) and phase 0

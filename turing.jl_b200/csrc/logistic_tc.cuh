@@ -47,6 +47,7 @@ namespace tc {
 constexpr int kChainsPerCta = 128;
 constexpr int kStages = 4;
 constexpr int kTmemCols = 512;
+constexpr int kPersistMaxTiles = 4;   // the persistent tail kernel (tc_persist.cuh) serves <= 4 chain tiles
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -175,7 +176,7 @@ __host__ __device__ constexpr uint32_t instr_desc(int n, int b_mn_major) {
 // ------------------------------------------------------------------------------------------
 // one-time data preparation: X (fp64 [N][D]) -> three bf16 planes [3][N][Dp8], y -> float [Npad]
 // ------------------------------------------------------------------------------------------
-__global__ void k_tc_split_x(const double *__restrict__ X, long long nrows, int D, int Dp8,
+static __global__ void k_tc_split_x(const double *__restrict__ X, long long nrows, int D, int Dp8,
                              __nv_bfloat16 *__restrict__ Xb) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long plane = nrows * Dp8;
@@ -194,7 +195,7 @@ __global__ void k_tc_split_x(const double *__restrict__ X, long long nrows, int 
   Xb[plane + i] = m;
   Xb[2 * plane + i] = l;
 }
-__global__ void k_tc_convert_y(const double *__restrict__ y, long long nrows, long long npad, float *__restrict__ yf) {
+static __global__ void k_tc_convert_y(const double *__restrict__ y, long long nrows, long long npad, float *__restrict__ yf) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < npad) yf[i] = i < nrows ? (float)y[i] : 0.f;
 }
@@ -222,86 +223,91 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *v) {
                : "memory");
 }
 
+// The kernel's machinery as a per-thread context with one method per warp role, so that the
+// stand-alone gradient kernel below and the persistent pump kernel (tc_persist.cuh) run the very same
+// MMA schedule.  A "pass" is one gradient evaluation of this CTA's (chain tile, row chunk); the
+// mbarrier phases are derived from RUNNING counters (tt0 = number of row tiles this CTA has processed
+// in earlier passes, pass = number of earlier passes), so passes can follow each other without
+// re-initialising anything.
 template <int KP>
-__global__ void __launch_bounds__(kThreads, 1)
-k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict__ yf, long long nrows, int D,
-              const double *__restrict__ th, int C, const int *__restrict__ list, const int *__restrict__ count,
-              int n_all, int rows_per_chunk, double *__restrict__ part /* [chunks][D+1][cap] */, int cap,
-              float *__restrict__ dbg, int xmode) {
-  constexpr int T = kT;
-#ifndef TNUTS_TC_EXPERIMENTS
-  xmode = 0;  // timing experiments (scripts/tc_logistic_check.cu) only: skip MMA passes / arithmetic / planes
-#endif
+struct TcCore {
   static_assert(KP == 64 || KP == 128, "feature padding is 64 or 128");
-  constexpr int NKB = KP / 64;                      // 128-byte boxes along the feature axis
-  constexpr uint32_t BOX_BYTES = T * 128;           // [T rows][64 bf16]
-  constexpr uint32_t PLANE_BYTES = NKB * BOX_BYTES; // one bf16 plane of the X tile
-  constexpr uint32_t STAGE_BYTES = 3 * PLANE_BYTES;
-  constexpr uint32_t TH_PLANE = KP / 2;             // TMEM columns of one Theta plane
-  constexpr uint32_t COL_TH = 0, COL_G = 3 * TH_PLANE, COL_BUF = COL_G + KP;
-  constexpr uint32_t BUF_COLS = (kG2Planes * T / 2 > T) ? kG2Planes * T / 2 : T;  // eta (T cols), then R planes
+  static constexpr int T = kT;
+  static constexpr int NKB = KP / 64;                      // 128-byte boxes along the feature axis
+  static constexpr uint32_t BOX_BYTES = T * 128;           // [T rows][64 bf16]
+  static constexpr uint32_t PLANE_BYTES = NKB * BOX_BYTES; // one bf16 plane of the X tile
+  static constexpr uint32_t STAGE_BYTES = 3 * PLANE_BYTES;
+  static constexpr uint32_t TH_PLANE = KP / 2;             // TMEM columns of one Theta plane
+  static constexpr uint32_t COL_TH = 0, COL_G = 3 * TH_PLANE, COL_BUF = COL_G + KP;
+  static constexpr uint32_t BUF_COLS = (kG2Planes * T / 2 > T) ? kG2Planes * T / 2 : T;  // eta (T cols), then R planes
   // three eta/R buffers: GEMM1 runs two tiles ahead, so neither GEMM1(t+2) nor the epilogue of
   // tile t+1 ever waits for the epilogue of tile t
-  constexpr int NBUF = kG2Planes == 2 ? 3 : 2;
+  static constexpr int NBUF = kG2Planes == 2 ? 3 : 2;
   static_assert(COL_BUF + NBUF * BUF_COLS <= kTmemCols, "TMEM budget");
-  constexpr int NEPI = 32 * kEpiWarps;
+  static constexpr int NEPI = 32 * kEpiWarps;
+  static constexpr int NBARS = 2 * kStages + 2 * 3 + 2;
 
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * kStages + 2 * 3 + 2];
-  __shared__ uint32_t tmem_slot;
-  __shared__ double lp_part[kEpiWarps / 4][kChainsPerCta];
+  uint32_t stage0, bar0, tmem;
+  int warp, lane, D, ks1, n2;
+  int xmode;   // timing experiments (scripts/tc_logistic_check.cu) only; 0 in the product build
 
-  const int n = count ? *count : n_all;
-  const int k0 = blockIdx.x * kChainsPerCta;
-  if (k0 >= n) return;
-  const int chunk = blockIdx.y;
-  const long long rbeg = (long long)chunk * rows_per_chunk;
-  if (rbeg >= nrows) return;
-  const long long rend = (rbeg + rows_per_chunk < nrows) ? rbeg + rows_per_chunk : nrows;
-  const int ntile = (int)((rend - rbeg + T - 1) / T);
+  __device__ __forceinline__ uint32_t bar_full(int s) const { return bar0 + 8u * s; }
+  __device__ __forceinline__ uint32_t bar_empty(int s) const { return bar0 + 8u * (kStages + s); }
+  __device__ __forceinline__ uint32_t bar_eta(int b) const { return bar0 + 8u * (2 * kStages + b); }
+  __device__ __forceinline__ uint32_t bar_r(int b) const { return bar0 + 8u * (2 * kStages + 3 + b); }
+  __device__ __forceinline__ uint32_t bar_theta() const { return bar0 + 8u * (2 * kStages + 6); }
+  __device__ __forceinline__ uint32_t bar_g() const { return bar0 + 8u * (2 * kStages + 7); }
 
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
-  const int lane = threadIdx.x & 31;
-  const uint32_t stage0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar0 = smem_u32(bars);
-  auto bar_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_empty = [&](int s) { return bar0 + 8u * (kStages + s); };
-  auto bar_eta = [&](int b) { return bar0 + 8u * (2 * kStages + b); };
-  auto bar_r = [&](int b) { return bar0 + 8u * (2 * kStages + 3 + b); };
-  const uint32_t bar_theta = bar0 + 8u * (2 * kStages + 6);
-  const uint32_t bar_g = bar0 + 8u * (2 * kStages + 7);
-
-  if (warp == 0 && elect_one()) tma_prefetch_desc(&mapX);
-  if (warp == 1) {
-    if (elect_one()) {
-      for (int s = 0; s < kStages; ++s) {
-        mbar_init(bar_full(s), 1);
-        mbar_init(bar_empty(s), 1);
+  // barrier init + TMEM allocation; ends with a CTA-wide synchronisation
+  __device__ __forceinline__ void setup(uint8_t *smem_raw, uint64_t *bars, uint32_t *tmem_slot,
+                                        const CUtensorMap *mapX, int D_) {
+    warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
+    lane = threadIdx.x & 31;
+    stage0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    bar0 = smem_u32(bars);
+    D = D_;
+    ks1 = (D + 15) >> 4;          // GEMM1 k-steps (16 features each)
+    n2 = (D + 15) & ~15;          // GEMM2 N
+    xmode = 0;
+    if (warp == 0 && elect_one()) tma_prefetch_desc(mapX);
+    if (warp == 1) {
+      if (elect_one()) {
+        for (int s = 0; s < kStages; ++s) {
+          mbar_init(bar_full(s), 1);
+          mbar_init(bar_empty(s), 1);
+        }
+        for (int b = 0; b < NBUF; ++b) {
+          mbar_init(bar_eta(b), 1);
+          mbar_init(bar_r(b), NEPI / 2);
+        }
+        mbar_init(bar_theta(), NEPI);
+        mbar_init(bar_g(), 1);
+        fence_barrier_init();
       }
-      for (int b = 0; b < NBUF; ++b) {
-        mbar_init(bar_eta(b), 1);
-        mbar_init(bar_r(b), NEPI / 2);
-      }
-      mbar_init(bar_theta, NEPI);
-      mbar_init(bar_g, 1);
-      fence_barrier_init();
+      __syncwarp();
+      tmem_alloc(smem_u32(tmem_slot), kTmemCols);
     }
-    __syncwarp();
-    tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tmem = *tmem_slot;
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_slot;
 
-  const int ks1 = (D + 15) >> 4;          // GEMM1 k-steps (16 features each)
-  const int n2 = (D + 15) & ~15;          // GEMM2 N
+  __device__ __forceinline__ void teardown() {
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+      tc_fence_after();
+      tmem_dealloc(tmem, kTmemCols);
+    }
+  }
 
-  if (warp == 0) {
-    // ===== TMA producer (warp-uniform control flow, one elected lane issues) =====
+  // ===== warp 0: TMA producer (warp-uniform control flow, one elected lane issues) =====
+  __device__ __forceinline__ void produce(const CUtensorMap *mapX, long long rbeg, int ntile, uint32_t tt0) {
     for (int t = 0; t < ntile; ++t) {
-      const int s = t % kStages;
-      const uint32_t ph = (uint32_t)(t / kStages) & 1u;
+      const uint32_t tt = tt0 + (uint32_t)t;
+      const int s = (int)(tt % kStages);
+      const uint32_t ph = (tt / kStages) & 1u;
       mbar_wait(bar_empty(s), ph ^ 1u);
       if (elect_one()) {
         const int npl = (xmode & 4) ? 1 : 3;   // experiment: one plane only (timing of the X stream)
@@ -312,94 +318,105 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
         for (int pl = 0; pl < 3; ++pl)
 #pragma unroll
           for (int kb = 0; kb < NKB; ++kb)
-            if (pl < npl) tma_load_3d(dst + pl * PLANE_BYTES + kb * BOX_BYTES, &mapX, bar_full(s), kb * 64, row0, pl);
+            if (pl < npl) tma_load_3d(dst + pl * PLANE_BYTES + kb * BOX_BYTES, mapX, bar_full(s), kb * 64, row0, pl);
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer (warp-uniform control flow, one elected lane issues) =====
-    const uint32_t idesc1 = instr_desc(T, 0);
-    const uint32_t idesc2 = instr_desc(n2, 1);
+  }
+
+  // ===== warp 1: MMA issuer (warp-uniform control flow, one elected lane issues) =====
+  __device__ __forceinline__ void gemm1(int t, uint32_t tt0) const {
     // descriptor words: hi = SBO 1024 | version 1 | SWIZZLE_128B; lo = address | LBO
     constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
-    constexpr uint32_t LBO_K = (16u >> 4) << 16, LBO_MN = (BOX_BYTES >> 4) << 16;
+    constexpr uint32_t LBO_K = (16u >> 4) << 16;
     // the six plane products, smallest first: (A plane, B plane)
     constexpr int PA[6] = {2, 1, 0, 1, 0, 0};
     constexpr int PB[6] = {0, 1, 2, 0, 1, 0};
+    const uint32_t idesc1 = instr_desc(T, 0);
     const int q0 = (xmode & 2) ? 5 : 0;
-    auto gemm1 = [&](int t) {
-      const int s = t % kStages;
-      mbar_wait(bar_full(s), (uint32_t)(t / kStages) & 1u);
-      tc_fence_after();
-      const uint32_t d_col = tmem + COL_BUF + (uint32_t)(t % NBUF) * BUF_COLS;
-      const uint32_t xs = (stage0 + (uint32_t)s * STAGE_BYTES) >> 4;
-      if (elect_one()) {
+    const uint32_t tt = tt0 + (uint32_t)t;
+    const int s = (int)(tt % kStages);
+    mbar_wait(bar_full(s), (tt / kStages) & 1u);
+    tc_fence_after();
+    const uint32_t d_col = tmem + COL_BUF + (tt % NBUF) * BUF_COLS;
+    const uint32_t xs = (stage0 + (uint32_t)s * STAGE_BYTES) >> 4;
+    if (elect_one()) {
 #pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          if (q < q0) continue;
-          const uint32_t a_col = tmem + COL_TH + PA[q] * TH_PLANE;
-          const uint32_t b_lo = (xs + PB[q] * (PLANE_BYTES >> 4)) | LBO_K;
+      for (int q = 0; q < 6; ++q) {
+        if (q < q0) continue;
+        const uint32_t a_col = tmem + COL_TH + PA[q] * TH_PLANE;
+        const uint32_t b_lo = (xs + PB[q] * (PLANE_BYTES >> 4)) | LBO_K;
 #pragma unroll
-          for (int ks = 0; ks < KP / 16; ++ks) {
-            if (ks < ks1) {
-              const uint32_t lo = b_lo + (uint32_t)(ks >> 2) * (BOX_BYTES >> 4) + (uint32_t)(ks & 3) * 2u;
-              mma_bf16_ts(d_col, a_col + (uint32_t)ks * 8u, ((uint64_t)DESC_HI << 32) | lo, idesc1,
-                          (q > q0 || ks > 0) ? 1u : 0u);
-            }
+        for (int ks = 0; ks < KP / 16; ++ks) {
+          if (ks < ks1) {
+            const uint32_t lo = b_lo + (uint32_t)(ks >> 2) * (BOX_BYTES >> 4) + (uint32_t)(ks & 3) * 2u;
+            mma_bf16_ts(d_col, a_col + (uint32_t)ks * 8u, ((uint64_t)DESC_HI << 32) | lo, idesc1,
+                        (q > q0 || ks > 0) ? 1u : 0u);
           }
         }
-        tc_commit(bar_eta(t % NBUF));
       }
-      __syncwarp();
-    };
-    auto gemm2 = [&](int t) {
-      const int s = t % kStages;
-      mbar_wait(bar_r(t % NBUF), (uint32_t)(t / NBUF) & 1u);
-      tc_fence_after();
-      const uint32_t r_col = tmem + COL_BUF + (uint32_t)(t % NBUF) * BUF_COLS;
-      const uint32_t xs = (stage0 + (uint32_t)s * STAGE_BYTES) >> 4;
-      if (elect_one()) {
-        // the gradient only steers the leapfrog map: with kG2Planes == 2 it keeps the products
-        // down to 2^-16 (R_m*X_h, R_h*X_m, R_h*X_h), comparable to its fp32 accumulation error
-        constexpr int NQ2 = kG2Planes == 3 ? 6 : 3;
-        constexpr int PA2[6] = {2, 1, 0, 1, 0, 0}, PB2[6] = {0, 1, 2, 0, 1, 0};
-        constexpr int PA3[3] = {1, 0, 0}, PB3[3] = {0, 1, 0};
-        const int q20 = (xmode & 2) ? NQ2 - 1 : 0;
-#pragma unroll
-        for (int q = 0; q < NQ2; ++q) {
-          if (q < q20) continue;
-          const int pa = kG2Planes == 3 ? PA2[q] : PA3[q], pb = kG2Planes == 3 ? PB2[q] : PB3[q];
-          const uint32_t a_col = r_col + pa * (T / 2);
-          const uint32_t b_lo = (xs + pb * (PLANE_BYTES >> 4)) | LBO_MN;
-#pragma unroll
-          for (int rs = 0; rs < T / 16; ++rs)
-            mma_bf16_ts(tmem + COL_G, a_col + (uint32_t)rs * 8u, ((uint64_t)DESC_HI << 32) | (b_lo + (uint32_t)rs * 128u),
-                        idesc2, (t > 0 || q > q20 || rs > 0) ? 1u : 0u);
-        }
-        tc_commit(bar_empty(s));
-      }
-      __syncwarp();
-    };
-    mbar_wait(bar_theta, 0);
-    tc_fence_after();
-    for (int t = 0; t < NBUF - 1 && t < ntile; ++t) gemm1(t);
-    for (int t = 0; t < ntile; ++t) {
-      if (t + NBUF - 1 < ntile) gemm1(t + NBUF - 1);
-      gemm2(t);
+      tc_commit(bar_eta((int)(tt % NBUF)));
     }
-    if (elect_one()) tc_commit(bar_g);
     __syncwarp();
-  } else {
-    // ===== epilogue warps: lane quarter wq (hardware: warp % 4), column group cg =====
-    const int wq = warp & 3, cg = (warp - 2) >> 2;
-    const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
-    const int kl = wq * 32 + lane;
-    const int k = k0 + kl;
-    const bool live = k < n;
-    const int c = live ? (list ? list[k] : k) : 0;
-    // Theta -> TMEM, three packed bf16 planes; this warp: features [32 cg, 32 cg + 32)
-    if (32 * cg < 16 * ks1) {
-      const int d0 = 32 * cg;
+  }
+  __device__ __forceinline__ void gemm2(int t, uint32_t tt0) const {
+    constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+    constexpr uint32_t LBO_MN = (BOX_BYTES >> 4) << 16;
+    const uint32_t idesc2 = instr_desc(n2, 1);
+    const uint32_t tt = tt0 + (uint32_t)t;
+    const int s = (int)(tt % kStages);
+    mbar_wait(bar_r((int)(tt % NBUF)), (tt / NBUF) & 1u);
+    tc_fence_after();
+    const uint32_t r_col = tmem + COL_BUF + (tt % NBUF) * BUF_COLS;
+    const uint32_t xs = (stage0 + (uint32_t)s * STAGE_BYTES) >> 4;
+    if (elect_one()) {
+      // the gradient only steers the leapfrog map: with kG2Planes == 2 it keeps the products
+      // down to 2^-16 (R_m*X_h, R_h*X_m, R_h*X_h), comparable to its fp32 accumulation error
+      constexpr int NQ2 = kG2Planes == 3 ? 6 : 3;
+      constexpr int PA2[6] = {2, 1, 0, 1, 0, 0}, PB2[6] = {0, 1, 2, 0, 1, 0};
+      constexpr int PA3[3] = {1, 0, 0}, PB3[3] = {0, 1, 0};
+      const int q20 = (xmode & 2) ? NQ2 - 1 : 0;
+#pragma unroll
+      for (int q = 0; q < NQ2; ++q) {
+        if (q < q20) continue;
+        const int pa = kG2Planes == 3 ? PA2[q] : PA3[q], pb = kG2Planes == 3 ? PB2[q] : PB3[q];
+        const uint32_t a_col = r_col + pa * (T / 2);
+        const uint32_t b_lo = (xs + pb * (PLANE_BYTES >> 4)) | LBO_MN;
+#pragma unroll
+        for (int rs = 0; rs < T / 16; ++rs)
+          mma_bf16_ts(tmem + COL_G, a_col + (uint32_t)rs * 8u, ((uint64_t)DESC_HI << 32) | (b_lo + (uint32_t)rs * 128u),
+                      idesc2, (t > 0 || q > q20 || rs > 0) ? 1u : 0u);
+      }
+      tc_commit(bar_empty(s));
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ void mma(int ntile, uint32_t tt0, uint32_t pass) const {
+    mbar_wait(bar_theta(), pass & 1u);
+    tc_fence_after();
+    for (int t = 0; t < NBUF - 1 && t < ntile; ++t) gemm1(t, tt0);
+    for (int t = 0; t < ntile; ++t) {
+      if (t + NBUF - 1 < ntile) gemm1(t + NBUF - 1, tt0);
+      gemm2(t, tt0);
+    }
+    if (elect_one()) tc_commit(bar_g());
+    __syncwarp();
+  }
+
+  // ===== warps 2-17: epilogue.  lane quarter wq (hardware: warp % 4), column group cg =====
+  __device__ __forceinline__ int wq() const { return warp & 3; }
+  __device__ __forceinline__ int cg() const { return (warp - 2) >> 2; }
+  __device__ __forceinline__ int kl() const { return wq() * 32 + lane; }   // chain slot inside the tile
+  __device__ __forceinline__ uint32_t lane_addr() const { return tmem + ((uint32_t)(wq() * 32) << 16); }
+
+  // Theta -> TMEM, three packed bf16 planes; this warp: features [32 cg, 32 cg + 32) of chain column
+  // c of th ([D][C]); `cg_loads` selects an L2 load (the persistent kernel re-reads positions that
+  // other SMs wrote during the same launch)
+  template <bool CG_LOADS>
+  __device__ __forceinline__ void epi_theta(const double *th, int C, int c, bool live) const {
+    const int cgi = cg();
+    if (32 * cgi < 16 * ks1) {
+      const int d0 = 32 * cgi;
       uint32_t vh[16], vm[16], vl[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -407,39 +424,46 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int d = d0 + 2 * j + i;
-          a[i] = (live && d < D) ? (float)th[(size_t)d * C + c] : 0.f;
+          const double *p = th + (size_t)d * C + c;
+          a[i] = (live && d < D) ? (float)(CG_LOADS ? __ldcg(p) : *p) : 0.f;
         }
         split3(a[0], a[1], vh[j], vm[j], vl[j]);
       }
-      tmem_st16(lane_addr + COL_TH + 0 * TH_PLANE + d0 / 2, vh);
-      tmem_st16(lane_addr + COL_TH + 1 * TH_PLANE + d0 / 2, vm);
-      tmem_st16(lane_addr + COL_TH + 2 * TH_PLANE + d0 / 2, vl);
+      tmem_st16(lane_addr() + COL_TH + 0 * TH_PLANE + d0 / 2, vh);
+      tmem_st16(lane_addr() + COL_TH + 1 * TH_PLANE + d0 / 2, vm);
+      tmem_st16(lane_addr() + COL_TH + 2 * TH_PLANE + d0 / 2, vl);
       tc_wait_st();
     }
     tc_fence_before();
-    mbar_arrive(bar_theta);
+    mbar_arrive(bar_theta());
+  }
 
-    // Two groups of 8 warps alternate tiles (group = tile parity), each warp takes
-    // 32 of the tile's 64 rows for its 32 chains.  The groups run half a period apart, so while one
-    // sits in TMEM load/store or barrier latency the other one has arithmetic to issue.
-    const int grp = cg & 1, half = cg >> 1;
+  // Two groups of 8 warps alternate tiles (group = parity of the running tile index), each warp takes
+  // 32 of the tile's 64 rows for its 32 chains.  The groups run half a period apart, so while one
+  // sits in TMEM load/store or barrier latency the other one has arithmetic to issue.
+  // Returns this thread's share of the log-likelihood of the pass.
+  __device__ __forceinline__ double epi_tiles(const float *__restrict__ yf, long long nrows, long long rbeg,
+                                              int ntile, uint32_t tt0, float *dbg, bool dbg_cta) const {
+    const int grp = cg() & 1, half = cg() >> 1;
     double lp = 0.0;
     constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
-    for (int t = grp; t < ntile; t += 2) {
+    for (int t = 0; t < ntile; ++t) {
+      const uint32_t tt = tt0 + (uint32_t)t;
+      if ((int)(tt & 1u) != grp) continue;
       const long long row0 = rbeg + (long long)t * T + 32 * half;   // this warp's 32 rows
       const float4 *yp = reinterpret_cast<const float4 *>(yf + row0);
-      const int bi = t % NBUF;
-      const uint32_t buf = lane_addr + COL_BUF + (uint32_t)bi * BUF_COLS;
-      mbar_wait(bar_eta(bi), (uint32_t)(t / NBUF) & 1u);
+      const int bi = (int)(tt % NBUF);
+      const uint32_t buf = lane_addr() + COL_BUF + (uint32_t)bi * BUF_COLS;
+      mbar_wait(bar_eta(bi), (tt / NBUF) & 1u);
       tc_fence_after();
       uint32_t v[32];
       tmem_ld16(buf + 32 * half, v);
       tmem_ld16(buf + 32 * half + 16, v + 16);
       tc_wait_ld();
-      const bool dump = dbg && blockIdx.x == 0 && blockIdx.y == 0 && t == 0;
+      const bool dump = dbg && dbg_cta && t == 0;
       if (dump) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dbg[kl * T + 32 * half + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) dbg[kl() * T + 32 * half + j] = __uint_as_float(v[j]);
       }
       const int nvalid = (nrows - row0 >= 32) ? 32 : (int)(nrows - row0);  // <= 0: rows past the data
       uint32_t ph[16], pm[16], pl[16];
@@ -474,7 +498,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
         tile_sum += tsum;   // 32 terms of size O(1): fp32 is exact enough, fp64 from here on
         if (dump) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) dbg[128 * T + kl * T + 32 * half + 4 * j4 + i] = rr[i];
+          for (int i = 0; i < 4; ++i) dbg[128 * T + kl() * T + 32 * half + 4 * j4 + i] = rr[i];
         }
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
@@ -489,7 +513,7 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
       }
       lp += (double)tile_sum;
       // both warps of this (lane quarter, group) must have read eta before either overwrites it
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + wq + 4 * grp), "r"(64) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + wq() + 4 * grp), "r"(64) : "memory");
       tmem_st16(buf + 0 * (T / 2) + 16 * half, ph);
       tmem_st16(buf + 1 * (T / 2) + 16 * half, pm);
       if (kG2Planes == 3) tmem_st16(buf + 2 * (T / 2) + 16 * half, pl);
@@ -497,17 +521,23 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
       tc_fence_before();
       mbar_arrive(bar_r(bi));
     }
-    // G -> partial sums (fp64), chain slot fastest; this warp: features [32 cg, 32 cg + 32)
-    lp_part[cg][kl] = lp;
-    mbar_wait(bar_g, 0);
+    return lp;
+  }
+
+  // G -> partial sums (fp64), chain slot fastest; this warp: features [32 cg, 32 cg + 32);
+  // pc = part + chunk * (D + 1) * cap, k = chain slot in the work list
+  __device__ __forceinline__ void epi_store(double *pc, int cap, int k, bool live, double lp,
+                                            double (*lp_part)[kChainsPerCta], uint32_t pass) const {
+    const int cgi = cg();
+    lp_part[cgi][kl()] = lp;
+    mbar_wait(bar_g(), pass & 1u);
     tc_fence_after();
-    double *pc = part + (size_t)chunk * (D + 1) * cap;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int d0 = 32 * cg + 16 * h;
+      const int d0 = 32 * cgi + 16 * h;
       if (d0 < n2) {
         uint32_t g[16];
-        tmem_ld16(lane_addr + COL_G + d0, g);
+        tmem_ld16(lane_addr() + COL_G + d0, g);
         tc_wait_ld();
         if (live) {
 #pragma unroll
@@ -516,20 +546,57 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
         }
       }
     }
-    asm volatile("bar.sync %0, %1;" ::"r"(9 + wq), "r"(32 * (kEpiWarps / 4)) : "memory");
-    if (cg == 0 && live) {
+    asm volatile("bar.sync %0, %1;" ::"r"(9 + wq()), "r"(32 * (kEpiWarps / 4)) : "memory");
+    if (cgi == 0 && live) {
       double s = 0.0;
 #pragma unroll
-      for (int q = 0; q < kEpiWarps / 4; ++q) s += lp_part[q][kl];
+      for (int q = 0; q < kEpiWarps / 4; ++q) s += lp_part[q][kl()];
       pc[(size_t)D * cap + k] = s;
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem, kTmemCols);
+};
+
+template <int KP>
+__global__ void __launch_bounds__(kThreads, 1)
+k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict__ yf, long long nrows, int D,
+              const double *__restrict__ th, int C, const int *__restrict__ list, const int *__restrict__ count,
+              int n_all, int rows_per_chunk, double *__restrict__ part /* [chunks][D+1][cap] */, int cap,
+              float *__restrict__ dbg, int xmode) {
+  using Core = TcCore<KP>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[Core::NBARS];
+  __shared__ uint32_t tmem_slot;
+  __shared__ double lp_part[kEpiWarps / 4][kChainsPerCta];
+
+  const int n = count ? *count : n_all;
+  const int k0 = blockIdx.x * kChainsPerCta;
+  if (k0 >= n) return;
+  const int chunk = blockIdx.y;
+  const long long rbeg = (long long)chunk * rows_per_chunk;
+  if (rbeg >= nrows) return;
+  const long long rend = (rbeg + rows_per_chunk < nrows) ? rbeg + rows_per_chunk : nrows;
+  const int ntile = (int)((rend - rbeg + Core::T - 1) / Core::T);
+
+  Core core;
+  core.setup(smem_raw, bars, &tmem_slot, &mapX, D);
+#ifdef TNUTS_TC_EXPERIMENTS
+  core.xmode = xmode;  // timing experiments (scripts/tc_logistic_check.cu): skip MMA passes / arithmetic / planes
+#else
+  dbg = nullptr;
+#endif
+  if (core.warp == 0) {
+    core.produce(&mapX, rbeg, ntile, 0u);
+  } else if (core.warp == 1) {
+    core.mma(ntile, 0u, 0u);
+  } else {
+    const int k = k0 + core.kl();
+    const bool live = k < n;
+    const int c = live ? (list ? list[k] : k) : 0;
+    core.template epi_theta<false>(th, C, c, live);
+    const double lp = core.epi_tiles(yf, nrows, rbeg, ntile, 0u, dbg, blockIdx.x == 0 && blockIdx.y == 0);
+    core.epi_store(part + (size_t)chunk * (D + 1) * cap, cap, k, live, lp, lp_part, 0u);
   }
+  core.teardown();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -555,19 +622,38 @@ inline bool plan(long long nrows, int D, Plan *p) {
   return true;
 }
 
-// Row cut for a launch over n_tiles chain tiles: with few chains left the rows are cut finer so
-// that the grid still fills the 148 SMs.  A function of (N, n_tiles) only.  The summation order of
-// a chain's gradient therefore depends on how many chains run beside it: in this mode a run is
-// reproducible for a fixed (seed, chain count, sharding), not across different chain counts
-// (the fp64 path keeps that stronger property).
+// Row cut for a launch over n_tiles chain tiles (128 chains each).  The grid is n_tiles x chunks
+// CTAs, one per SM at a time, so the launch takes ceil(n_tiles * chunks / 148) waves of
+// (row tiles per chunk + a fixed per-CTA cost) each: 5 chain tiles x 37 chunks = 185 CTAs would run
+// two waves for 1.25 waves of work.  Pick the chunk count that minimises that product; with few
+// chains left the rows are cut finer so that the grid still fills the chip.  A function of
+// (N, n_tiles) only.  The summation order of a chain's gradient therefore depends on how many
+// chains run beside it: in this mode a run is reproducible for a fixed (seed, chain count,
+// sharding), not across different chain counts (the fp64 path keeps that stronger property).
+constexpr int kSMs = 148;
+constexpr int kCtaFixedTiles = 5;   // launch + TMEM alloc + Theta load + G store, in row-tile times
 inline void cut_for(long long nrows, int n_tiles, int *chunks, int *rpc) {
   const long long tiles = (nrows + kT - 1) / kT;
-  long long want = n_tiles >= 4 ? 37 : n_tiles >= 2 ? 74 : 148;
-#ifdef TNUTS_TC_EXPERIMENTS
-  if (const char *ov = getenv("TNUTS_TC_CHUNKS")) want = atoi(ov);
-#endif
-  if (want > tiles) want = tiles;
-  const long long tpc = (tiles + want - 1) / want;
+  if (n_tiles < 1) n_tiles = 1;
+  long long best_c = 1, best_cost = -1;
+  const long long cmax = tiles < kSMs ? tiles : kSMs;
+  for (long long c = 1; c <= cmax; ++c) {
+    const long long tpc = (tiles + c - 1) / c;
+    const long long real_c = (tiles + tpc - 1) / tpc;           // chunks that actually hold rows
+    const long long waves = ((long long)n_tiles * real_c + kSMs - 1) / kSMs;
+    // the partial sums of every chunk are read back once by the reduction kernel: a small cost
+    // per chunk keeps the cut from being finer than it needs to be
+    const long long cost = waves * (tpc + kCtaFixedTiles) * 64 + real_c;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best_c = c;
+    }
+  }
+  // tuning knob for experiments: TNUTS_TC_CHUNKS=c forces the chunk count, TNUTS_TC_FIXED=f the
+  // per-CTA fixed cost of the model above
+  static const int forced = [] { const char *v = getenv("TNUTS_TC_CHUNKS"); return v ? atoi(v) : 0; }();
+  if (forced > 0) best_c = forced < cmax ? forced : cmax;
+  const long long tpc = (tiles + best_c - 1) / best_c;
   *rpc = (int)(tpc * kT);
   *chunks = (int)((nrows + *rpc - 1) / *rpc);
 }

@@ -16,6 +16,7 @@
 //   k_hier_tile ........... hierarchical regression from per-group centred sufficient
 //                           statistics: O(D) per chain, streaming over [D][C].
 #pragma once
+#include "logistic_finish.cuh"
 #include "lockstep_kernels.cuh"
 
 namespace tnuts {
@@ -412,14 +413,14 @@ k_logistic_reduce_finish(ModelDev m, const double *__restrict__ part, int chunks
   for (; ch < chunks; ++ch) s += p[(size_t)ch * cs];
   const double sd = m.hyper[0], is2 = 1.0 / (sd * sd);
   if (d < D) {
-    g[(size_t)d * C + c] = s - th[(size_t)d * C + c] * is2;
+    g[(size_t)d * C + c] = logistic_finish_grad(s, th[(size_t)d * C + c], is2);
   } else {
     double q = 0.0;
     for (int j = 0; j < D; ++j) {
       const double t = th[(size_t)j * C + c];
-      q += t * t;
+      q = __fma_rn(t, t, q);
     }
-    lp_out[c] = s + (-0.5 * D * kLog2Pi - D * log(sd) - 0.5 * q * is2);
+    lp_out[c] = logistic_finish_lp(s, q, is2, D, sd);
   }
 }
 

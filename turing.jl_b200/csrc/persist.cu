@@ -1,0 +1,69 @@
+// persist.cu -- host side of the persistent pump kernel (tc_persist.cuh).  Its own translation unit
+// because it is compiled with -Xptxas -dlcm=cg: inside the persistent kernel one SM reads what
+// another wrote a phase earlier, so global loads must not be served from a (non-coherent) L1.
+#include "tc_persist.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "engine.cuh"
+
+namespace tnuts {
+
+// Runs pumps [pump0, ...) of the current lock-step run until every chain has finished (or the pump
+// budget is spent).  The work list must have been refreshed by the caller for `listed_done`, and
+// n_max = C - listed_done must fit kPersistMaxTiles chain tiles.  Synchronises the stream.
+// *pumps: pumps executed; *n_done: finished chains at the end.
+int tc_persist_run(Engine *e, const tc::Data &td, double *part, int stride, int *count_done_dev, int *h_done,
+                   long long pump0, long long max_pumps, int listed_done, int n_max, long long *pumps,
+                   int *n_done) {
+  const ModelDev &m = e->model;
+  LockstepState *ls = e->ls;
+  int n_sm = 0;
+  TN_CUDA(e, cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, e->device));
+  if (n_sm < tc::kSMs) return set_error(e, TNUTS_E_UNSUPPORTED, "persistent pump: fewer SMs than the row cut assumes");
+  tc::PersistCut cut{};
+  for (int nt = 1; nt <= tc::kPersistMaxTiles; ++nt) tc::cut_for(m.N, nt, &cut.chunks[nt], &cut.rpc[nt]);
+  // barrier counter + out_state in one small allocation
+  unsigned long long *scratch = nullptr;
+  TN_CUDA(e, cudaMallocAsync((void **)&scratch, 8 * 16, e->stream));
+  TN_CUDA(e, cudaMemsetAsync(scratch, 0, 8 * 16, e->stream));
+  tc::PersistArgs pa{};
+  pa.pump0 = pump0;
+  pa.max_pumps = max_pumps;
+  pa.listed_done = listed_done;
+  pa.n_max = n_max;
+  pa.gbar = scratch;
+  pa.n_done = count_done_dev;
+  pa.h_done = h_done;
+  pa.out_state = (long long *)(scratch + 1);
+  long long nrows = m.N;
+  int cap = stride;
+  const float *yf = td.yf;
+  void *args[] = {(void *)&td.map, (void *)&yf, (void *)&nrows, (void *)&part, (void *)&cap, (void *)&e->st,
+                  (void *)ls,      (void *)&e->rp, (void *)&e->model, (void *)&e->out, (void *)&cut, (void *)&pa};
+  const void *fn = td.pl.kp == 128 ? (const void *)tc::k_tc_persist<128> : (const void *)tc::k_tc_persist<64>;
+  TN_CUDA(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)td.pl.smem));
+  TN_CUDA(e, cudaLaunchCooperativeKernel(fn, dim3(tc::kSMs), dim3(tc::kThreads), args, td.pl.smem, e->stream));
+  e->launches += 1;
+  long long st4[11] = {0};
+  TN_CUDA(e, cudaMemcpyAsync(st4, pa.out_state, sizeof(st4), cudaMemcpyDeviceToHost, e->stream));
+  cudaError_t s = cudaStreamSynchronize(e->stream);
+  cudaFreeAsync(scratch, e->stream);
+  if (s != cudaSuccess)
+    return set_error(e, TNUTS_E_CUDA, std::string("persistent pump kernel: ") + cudaGetErrorString(s));
+  *pumps = st4[0];
+  *n_done = (int)st4[2];
+  static const bool trace = getenv("TNUTS_PUMP_TRACE") != nullptr;
+  if (trace && st4[0] > 0) {
+    const double k = 1e-3 / (double)st4[0];
+    fprintf(stderr,
+            "[tnuts persist] %lld pumps, us per pump at CTA 0: gradient %.1f | barrier %.1f | reduce %.1f | barrier %.1f | "
+            "state machine %.1f | barrier %.1f | list refreshes %.1f\n",
+            st4[0], st4[4] * k, st4[5] * k, st4[6] * k, st4[7] * k, st4[8] * k, st4[9] * k, st4[10] * k);
+  }
+  return TNUTS_OK;
+}
+
+}  // namespace tnuts

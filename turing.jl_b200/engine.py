@@ -193,6 +193,15 @@ class Engine:
         check(self.h, self.L.tnuts_bench_gradient(self.h, int(reps), C.byref(s)))
         return s.value / reps
 
+    def kernel_times(self):
+        """(seconds, launches, sampled, tile_launches, persist_seconds, persist_pumps): the gradient
+        kernel's launches and the persistent tail kernel inside the last run (option "time_kernels")"""
+        s, n, k, t = C.c_double(0.0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        ps, pp = C.c_double(0.0), C.c_int64(0)
+        check(self.h, self.L.tnuts_kernel_times(self.h, C.byref(s), C.byref(n), C.byref(k), C.byref(t),
+                                                C.byref(ps), C.byref(pp)))
+        return s.value, n.value, k.value, t.value, ps.value, pp.value
+
     def comm_init(self, unique_id, world, rank):
         check(self.h, self.L.tnuts_comm_init(self.h, unique_id, world, rank))
 

@@ -113,6 +113,9 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
     if initial_state is not None:
         seed64 = initial_state["seed"]
 
+    # AHMCAdaptor (src/mcmc/hmc.jl:447-465): `iszero(alg.n_adapts)` gives NoAdaptation whatever
+    # `nadapts` the call passes; the discard schedule above still follows the keyword
+    _engine_nadapts = 0 if (spl.adaptive and spl.n_adapts == 0) else _nadapts
     devices = list(devices) if devices else [0]
     ndev = len(devices)
     if n_chains < ndev:
@@ -127,7 +130,7 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
     tm = {}
     engines = []
     for i, dev in enumerate(devices):
-        engines.append(Engine(model, spl, bounds[i + 1] - bounds[i], _nadapts, seed64, device=dev,
+        engines.append(Engine(model, spl, bounds[i + 1] - bounds[i], _engine_nadapts, seed64, device=dev,
                               chain_offset=chain_offset + bounds[i], strategy=strategy))
         for k, v in (engine_options or {}).items():
             engines[-1].set_option(k, v)
@@ -150,7 +153,8 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
             first = None
             if initial_state is not None:
                 e.set_state(initial_state["blobs"][i])
-                n_tr, first_keep = N * thinning, thinning
+                # mcmcsample keeps the very first step from the restored state, then thins
+                n_tr, first_keep = 1 + (N - 1) * thinning, 1
             else:
                 try:
                     e.init(None if theta0 is None else theta0[lo:hi])
