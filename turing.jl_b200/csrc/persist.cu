@@ -5,7 +5,9 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <string>
+#include <vector>
 
 #include "engine.cuh"
 
@@ -27,8 +29,9 @@ int tc_persist_run(Engine *e, const tc::Data &td, double *part, int stride, int 
   for (int nt = 1; nt <= tc::kPersistMaxTiles; ++nt) tc::cut_for(m.N, nt, &cut.chunks[nt], &cut.rpc[nt]);
   // barrier counter + out_state in one small allocation
   unsigned long long *scratch = nullptr;
-  TN_CUDA(e, cudaMallocAsync((void **)&scratch, 8 * 16, e->stream));
-  TN_CUDA(e, cudaMemsetAsync(scratch, 0, 8 * 16, e->stream));
+  const size_t n_scratch = 16 + 3 * (size_t)tc::kSMs;
+  TN_CUDA(e, cudaMallocAsync((void **)&scratch, 8 * n_scratch, e->stream));
+  TN_CUDA(e, cudaMemsetAsync(scratch, 0, 8 * n_scratch, e->stream));
   tc::PersistArgs pa{};
   pa.pump0 = pump0;
   pa.max_pumps = max_pumps;
@@ -38,6 +41,8 @@ int tc_persist_run(Engine *e, const tc::Data &td, double *part, int stride, int 
   pa.n_done = count_done_dev;
   pa.h_done = h_done;
   pa.out_state = (long long *)(scratch + 1);
+  static const bool trace = getenv("TNUTS_PUMP_TRACE") != nullptr;
+  pa.cta_times = trace ? (long long *)(scratch + 16) : nullptr;
   long long nrows = m.N;
   int cap = stride;
   const float *yf = td.yf;
@@ -48,15 +53,25 @@ int tc_persist_run(Engine *e, const tc::Data &td, double *part, int stride, int 
   TN_CUDA(e, cudaLaunchCooperativeKernel(fn, dim3(tc::kSMs), dim3(tc::kThreads), args, td.pl.smem, e->stream));
   e->launches += 1;
   long long st4[11] = {0};
+  std::vector<long long> ct(3 * (size_t)tc::kSMs, 0);
   TN_CUDA(e, cudaMemcpyAsync(st4, pa.out_state, sizeof(st4), cudaMemcpyDeviceToHost, e->stream));
+  if (trace) TN_CUDA(e, cudaMemcpyAsync(ct.data(), scratch + 16, 8 * ct.size(), cudaMemcpyDeviceToHost, e->stream));
   cudaError_t s = cudaStreamSynchronize(e->stream);
   cudaFreeAsync(scratch, e->stream);
   if (s != cudaSuccess)
     return set_error(e, TNUTS_E_CUDA, std::string("persistent pump kernel: ") + cudaGetErrorString(s));
   *pumps = st4[0];
   *n_done = (int)st4[2];
-  static const bool trace = getenv("TNUTS_PUMP_TRACE") != nullptr;
   if (trace && st4[0] > 0) {
+    long long mx[3] = {0, 0, 0}, sm[3] = {0, 0, 0};
+    for (int b = 0; b < tc::kSMs; ++b)
+      for (int i = 0; i < 3; ++i) {
+        mx[i] = std::max(mx[i], ct[3 * b + i]);
+        sm[i] += ct[3 * b + i];
+      }
+    fprintf(stderr, "[tnuts persist] us per pump inside the phases, busiest CTA / mean CTA: gradient %.1f / %.1f | reduce %.1f / %.1f | "
+            "state machine %.1f / %.1f\n", mx[0] * 1e-3 / st4[0], sm[0] * 1e-3 / st4[0] / tc::kSMs, mx[1] * 1e-3 / st4[0],
+            sm[1] * 1e-3 / st4[0] / tc::kSMs, mx[2] * 1e-3 / st4[0], sm[2] * 1e-3 / st4[0] / tc::kSMs);
     const double k = 1e-3 / (double)st4[0];
     fprintf(stderr,
             "[tnuts persist] %lld pumps, us per pump at CTA 0: gradient %.1f | barrier %.1f | reduce %.1f | barrier %.1f | "

@@ -45,6 +45,7 @@ struct PersistArgs {
   unsigned long long *gbar;    // grid barrier counter, zero at launch
   int *n_done;                 // finished chains (device)
   int *h_done;                 // mapped pinned mirror of n_done for the host's progress trace
+  long long *cta_times;        // [grid][3] ns every CTA spent inside G, R, P (barrier waits excluded)
   long long *out_state;        // [4] pumps executed, gradient passes of CTA 0, final n_done, reason;
                                // [4..10] ns CTA 0 spent in G, barrier, R, barrier, P, barrier, refresh
 };
@@ -130,7 +131,7 @@ k_tc_persist(const __grid_constant__ CUtensorMap mapX, const float *__restrict__
   long long tph[7] = {0, 0, 0, 0, 0, 0, 0};
   auto now = [] {
     unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
     return (long long)t;
   };
   long long tmark = now();
@@ -212,7 +213,15 @@ k_tc_persist(const __grid_constant__ CUtensorMap mapX, const float *__restrict__
           ls.zg[(size_t)d * C + c] = logistic_finish_grad(s, __ldcg(ls.zt + (size_t)d * C + c), is2);
         } else {
           double qq = 0.0;
-          for (int j = 0; j < D; ++j) {
+          int j = 0;
+          for (; j + 20 <= D; j += 20) {          // twenty loads in flight, squared and summed in order
+            double a[20];
+#pragma unroll
+            for (int i = 0; i < 20; ++i) a[i] = __ldcg(ls.zt + (size_t)(j + i) * C + c);
+#pragma unroll
+            for (int i = 0; i < 20; ++i) qq = __fma_rn(a[i], a[i], qq);
+          }
+          for (; j < D; ++j) {
             const double t = __ldcg(ls.zt + (size_t)j * C + c);
             qq = __fma_rn(t, t, qq);
           }
@@ -226,7 +235,7 @@ k_tc_persist(const __grid_constant__ CUtensorMap mapX, const float *__restrict__
     lap(3);
 
     // ---- P: per-chain state machine, 8 listed chains per CTA ----
-    if (b == 0 && threadIdx.x == 0) *(volatile int *)pa.h_done = __ldcg(pa.n_done);
+    if (b == 0 && threadIdx.x == 0 && (p & 63) == 0) *(volatile int *)pa.h_done = __ldcg(pa.n_done);
     if (etid >= 0 && etid < kTileThreads && 8 * b < n) {
       const int slot = 8 * b + (etid & (kTileC - 1));
       const int chain = slot < n ? __ldcg(ls.list + slot) : C;
@@ -242,6 +251,11 @@ k_tc_persist(const __grid_constant__ CUtensorMap mapX, const float *__restrict__
       reason = 2;
       break;
     }
+  }
+  if (threadIdx.x == 0 && pa.cta_times) {
+    pa.cta_times[3 * b + 0] = tph[0];
+    pa.cta_times[3 * b + 1] = tph[2];
+    pa.cta_times[3 * b + 2] = tph[4];
   }
   if (b == 0 && threadIdx.x == 0) {
     pa.out_state[0] = p - pa.pump0;
