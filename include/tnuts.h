@@ -67,6 +67,13 @@ extern "C" {
 #define TNUTS_LOGISTIC 3       /* Bayesian logistic regression                       */
 #define TNUTS_HIER_LINREG 4    /* hierarchical (varying intercept+slope) regression  */
 #define TNUTS_STD_NORMAL 5     /* x ~ Normal() iid                                   */
+#define TNUTS_BETA_BERNOULLI 6 /* test/mcmc/hmc.jl:24-43: p ~ Beta(a, b); obs[i] ~ Bernoulli(p);
+                                  theta = logit(p); y[N] = observations, hyper = {a, b}      */
+#define TNUTS_DIRICHLET_CATEGORICAL 7 /* test/mcmc/hmc.jl:45-62: ps ~ Dirichlet(K1, al1);
+                                  pd ~ Dirichlet(K2, al2); obs[i] ~ Categorical(ps).  Each simplex
+                                  links by stick breaking: D = K1 - 1 + K2 - 1 linked dimensions,
+                                  tnuts_num_params = K1 + K2 chain columns.  y[N] = categories 1..K1,
+                                  hyper = {K1, al1, K2, al2}; (K1, K2) in {(2,4), (3,0), (2,0)}   */
 
 /* algorithms (src/mcmc/hmc.jl:425-441) */
 #define TNUTS_ALG_NUTS 0

@@ -8,7 +8,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libtnuts_oracle.so")
 
-GDEMO, LINREG, EIGHT_SCHOOLS, LOGISTIC, HIER_LINREG, STD_NORMAL = range(6)
+GDEMO, LINREG, EIGHT_SCHOOLS, LOGISTIC, HIER_LINREG, STD_NORMAL, BETA_BERNOULLI, DIRICHLET_CATEGORICAL = range(8)
 NSTAT = 9
 STAT_NAMES = ("n_steps", "acceptance_rate", "log_density", "hamiltonian_energy",
               "hamiltonian_energy_error", "max_hamiltonian_energy_error", "tree_depth",
@@ -55,6 +55,8 @@ def lib():
         L = C.CDLL(_LIB_PATH)
         L.orc_logdensity_and_gradient.restype = C.c_double
         L.orc_logdensity_and_gradient.argtypes = [C.POINTER(_Model), _dp, _dp]
+        L.orc_num_params.restype = C.c_int
+        L.orc_num_params.argtypes = [C.POINTER(_Model)]
         L.orc_constrain_and_logp.restype = None
         L.orc_constrain_and_logp.argtypes = [C.POINTER(_Model), _dp, _dp, _dp]
         L.orc_philox4x32_10.restype = None
@@ -121,9 +123,14 @@ class OracleModel:
             lps[i] = lib().orc_logdensity_and_gradient(C.byref(self._c), _d(theta[i]), _d(gs[i]))
         return lps, gs
 
+    @property
+    def P(self):
+        """user-space parameters (D, except K per K-simplex)"""
+        return lib().orc_num_params(C.byref(self._c))
+
     def constrain(self, theta):
         theta = np.ascontiguousarray(theta, dtype=np.float64)
-        p = np.empty(self.D)
+        p = np.empty(self.P)
         lp3 = np.empty(3)
         lib().orc_constrain_and_logp(C.byref(self._c), _d(theta), _d(p), _d(lp3))
         return p, lp3
@@ -168,7 +175,7 @@ def sample_chains(model, cfg, n_chains, n_transitions, first_keep=1, thin=1, the
     D = model.D
     nkeep = (n_transitions - first_keep) // thin + 1 if n_transitions >= first_keep >= 1 else 0
     th = np.zeros((n_chains, nkeep, D))
-    pa = np.zeros((n_chains, nkeep, D))
+    pa = np.zeros((n_chains, nkeep, model.P))
     lp = np.zeros((n_chains, nkeep, 3))
     st = np.zeros((n_chains, nkeep, NSTAT))
     eps = np.zeros(n_chains)
@@ -193,7 +200,7 @@ def resume_chains(model, cfg, theta, eps, minv, iter0, n_transitions, first_keep
     n_chains, D = theta.shape
     nkeep = (n_transitions - first_keep) // thin + 1 if n_transitions >= first_keep >= 1 else 0
     th = np.zeros((n_chains, nkeep, D))
-    pa = np.zeros((n_chains, nkeep, D))
+    pa = np.zeros((n_chains, nkeep, model.P))
     lp = np.zeros((n_chains, nkeep, 3))
     st = np.zeros((n_chains, nkeep, NSTAT))
     fin = np.zeros((n_chains, D))

@@ -36,7 +36,11 @@
 /* ------------------------------------------------------------------------------------------
  * Log densities.  theta is in linked space; positive variables link by log.
  * ------------------------------------------------------------------------------------------ */
-int orc_num_params(const orc_model *m) { return m->D; }
+int orc_num_params(const orc_model *m) {
+  /* a K-simplex has K - 1 linked dimensions (stick breaking) and K user-space parameters */
+  if (m->family == ORC_DIRICHLET_CATEGORICAL) return (int)m->hyper[0] + (int)m->hyper[2];
+  return m->D;
+}
 
 static double log1pexp(double x) {
   /* StatsFuns.log1pexp, used by BinomialLogit: src/stdlib/distributions.jl:77 */
@@ -221,6 +225,77 @@ static double lp_hier(const orc_model *md, const double *th, double *g) {
   return lp;
 }
 
+/* ---- the two constrained-support models of the reference's HMC tests --------------------------
+ * test/mcmc/hmc.jl:24-43  "constrained bounded":  p ~ Beta(a, b); obs[i] ~ Bernoulli(p)
+ *   theta = logit(p) (Bijectors' Logit link on (0, 1)); log|det J_invlink| = log p + log(1 - p).
+ *   lp = (a + s) log p + (b + f) log(1 - p) - log B(a, b),  s / f = number of ones / zeros.
+ *   hyper = {a, b}; y[N] = observations (0 / 1).
+ * test/mcmc/hmc.jl:45-62  "constrained simplex":  ps ~ Dirichlet(K1, al1); pd ~ Dirichlet(K2, al2);
+ *   obs[i] ~ Categorical(ps)
+ *   Each simplex x of size K links by stick breaking (Bijectors' SimplexBijector, the Stan
+ *   transform):  z_k = logistic(y_k - log(K - k)), x_k = z_k rem_k, rem_1 = 1,
+ *   rem_{k+1} = rem_k (1 - z_k), x_K = rem_K;  log|det J_invlink| = sum_k log z_k + log(1 - z_k) +
+ *   log rem_k.  hyper = {K1, al1, K2, al2}; y[N] = observed categories 1..K1.  D = K1 - 1 + K2 - 1.
+ * Both are sums of a log sigma(u) + b log sigma(-u) terms, u = theta_d - shift_d. */
+static double log_sigmoid(double u) { /* log logistic(u), stable in both tails */
+  return u >= 0 ? -log1p(exp(-u)) : u - log1p(exp(u));
+}
+static double sigmoid(double u) {
+  if (u >= 0) return 1.0 / (1.0 + exp(-u));
+  const double e = exp(u);
+  return e / (1.0 + e);
+}
+
+static double lp_beta_bernoulli(const orc_model *md, const double *th, double *g) {
+  const double a = md->hyper[0], b = md->hyper[1];
+  double s = 0, f = 0;
+  for (int64_t i = 0; i < md->N; ++i) {
+    if (md->y[i] != 0.0) s += 1.0;
+    else f += 1.0;
+  }
+  const double u = th[0], p = sigmoid(u);
+  if (g) g[0] = (a + s) * (1.0 - p) - (b + f) * p;
+  return (a + s) * log_sigmoid(u) + (b + f) * log_sigmoid(-u) - (lgamma(a) + lgamma(b) - lgamma(a + b));
+}
+
+/* one Dirichlet(K, al) block with category counts cnt[K] (NULL: no observations): adds its lp,
+ * writes K - 1 gradient entries */
+static double lp_simplex_block(int K, double al, const double *cnt, const double *y, double *g) {
+  double lp = lgamma(K * al) - K * lgamma(al);
+  double tail = (al - 1.0) + (cnt ? cnt[K - 1] : 0.0); /* sum of c_k over k > j, c_k = al - 1 + n_k */
+  for (int j = K - 2; j >= 0; --j) {                  /* stick j (0-based): K - 1 - j categories after it */
+    const double cj = (al - 1.0) + (cnt ? cnt[j] : 0.0);
+    const double aj = cj + 1.0, bj = tail + 1.0 + (double)(K - 2 - j);
+    const double u = y[j] - log((double)(K - 1 - j));
+    const double z = sigmoid(u);
+    lp += aj * log_sigmoid(u) + bj * log_sigmoid(-u);
+    if (g) g[j] = aj * (1.0 - z) - bj * z;
+    tail += cj;
+  }
+  return lp;
+}
+
+static double lp_dirichlet_categorical(const orc_model *md, const double *th, double *g) {
+  const int K1 = (int)md->hyper[0], K2 = (int)md->hyper[2];
+  const double al1 = md->hyper[1], al2 = md->hyper[3];
+  double cnt[64];
+  for (int k = 0; k < K1; ++k) cnt[k] = 0.0;
+  for (int64_t i = 0; i < md->N; ++i) cnt[(int)md->y[i] - 1] += 1.0;
+  double lp = lp_simplex_block(K1, al1, cnt, th, g);
+  if (K2 > 0) lp += lp_simplex_block(K2, al2, NULL, th + (K1 - 1), g ? g + (K1 - 1) : NULL);
+  return lp;
+}
+
+static void simplex_invlink(int K, const double *y, double *x) {
+  double rem = 1.0;
+  for (int j = 0; j < K - 1; ++j) {
+    const double z = sigmoid(y[j] - log((double)(K - 1 - j)));
+    x[j] = z * rem;
+    rem *= 1.0 - z;
+  }
+  x[K - 1] = rem;
+}
+
 static double lp_std_normal(const orc_model *md, const double *th, double *g) {
   double lp = -0.5 * md->D * LOG_2PI;
   for (int d = 0; d < md->D; ++d) {
@@ -238,6 +313,8 @@ double orc_logdensity_and_gradient(const orc_model *m, const double *theta, doub
     case ORC_LOGISTIC: return lp_logistic(m, theta, grad);
     case ORC_HIER_LINREG: return lp_hier(m, theta, grad);
     case ORC_STD_NORMAL: return lp_std_normal(m, theta, grad);
+    case ORC_BETA_BERNOULLI: return lp_beta_bernoulli(m, theta, grad);
+    case ORC_DIRICHLET_CATEGORICAL: return lp_dirichlet_categorical(m, theta, grad);
   }
   return NAN;
 }
@@ -338,6 +415,26 @@ void orc_constrain_and_logp(const orc_model *md, const double *th, double *p, do
         p[d] = th[d];
         prior -= 0.5 * th[d] * th[d];
       }
+    } break;
+    case ORC_BETA_BERNOULLI: {
+      const double a = md->hyper[0], b = md->hyper[1];
+      const double lpp = log_sigmoid(th[0]), lq = log_sigmoid(-th[0]);
+      p[0] = sigmoid(th[0]);
+      prior = (a - 1.0) * lpp + (b - 1.0) * lq - (lgamma(a) + lgamma(b) - lgamma(a + b));
+      for (int64_t i = 0; i < md->N; ++i) lik += md->y[i] != 0.0 ? lpp : lq;
+    } break;
+    case ORC_DIRICHLET_CATEGORICAL: {
+      const int K1 = (int)md->hyper[0], K2 = (int)md->hyper[2];
+      const double al1 = md->hyper[1], al2 = md->hyper[3];
+      simplex_invlink(K1, th, p);
+      prior = lgamma(K1 * al1) - K1 * lgamma(al1);
+      for (int k = 0; k < K1; ++k) prior += (al1 - 1.0) * log(p[k]);
+      if (K2 > 0) {
+        simplex_invlink(K2, th + (K1 - 1), p + K1);
+        prior += lgamma(K2 * al2) - K2 * lgamma(al2);
+        for (int k = 0; k < K2; ++k) prior += (al2 - 1.0) * log(p[K1 + k]);
+      }
+      for (int64_t i = 0; i < md->N; ++i) lik += log(p[(int)md->y[i] - 1]);
     } break;
   }
   lp3[0] = prior;

@@ -34,7 +34,10 @@ enum {
   ORC_EIGHT_SCHOOLS = 2,  /* BASELINE.json configs[1] */
   ORC_LOGISTIC = 3,       /* BASELINE.json configs[2], configs[4] */
   ORC_HIER_LINREG = 4,    /* BASELINE.json configs[3] */
-  ORC_STD_NORMAL = 5      /* test/main.jl:39-48, x ~ Normal() iid, D free */
+  ORC_STD_NORMAL = 5,     /* test/main.jl:39-48, x ~ Normal() iid, D free */
+  ORC_BETA_BERNOULLI = 6, /* test/mcmc/hmc.jl:24-43: p ~ Beta(a, b); obs ~ Bernoulli(p); logit link */
+  ORC_DIRICHLET_CATEGORICAL = 7 /* test/mcmc/hmc.jl:45-62: ps ~ Dirichlet(K1, al1), pd ~ Dirichlet(K2, al2),
+                                   obs ~ Categorical(ps); stick-breaking simplex link */
 };
 
 typedef struct {
@@ -49,7 +52,7 @@ typedef struct {
   double hyper[8];    /* family specific prior hyper-parameters */
 } orc_model;
 
-/* number of user-space (constrained) parameters == D for all families here */
+/* number of user-space (constrained) parameters: D, except K per K-simplex (K - 1 linked dims) */
 int orc_num_params(const orc_model *m);
 
 /* (a9) lp and gradient of getlogjoint_internal in linked space

@@ -95,7 +95,66 @@ def lj_stdnormal(th, data):
     return mp.fsum(normal_lpdf(t, 0, 1) for t in th)
 
 
-FAMS = {"gdemo": (0, lj_gdemo), "linreg": (1, lj_linreg), "eight_schools": (2, lj_eight),
+def beta_lpdf(x, a, b):
+    return (a - 1) * mp.log(x) + (b - 1) * mp.log(1 - x) - (mp.loggamma(a) + mp.loggamma(b) - mp.loggamma(a + b))
+
+
+def dirichlet_lpdf(x, al):
+    K = len(x)
+    return mp.loggamma(K * al) - K * mp.loggamma(al) + (al - 1) * mp.fsum(mp.log(v) for v in x)
+
+
+def simplex_invlink(y):
+    """Bijectors' SimplexBijector (the Stan stick-breaking transform): K - 1 reals -> K-simplex"""
+    K = len(y) + 1
+    x, rem = [], mp.mpf(1)
+    for k, yk in enumerate(y):
+        z = 1 / (1 + mp.exp(-(yk - mp.log(K - 1 - k))))
+        x.append(z * rem)
+        rem = rem * (1 - z)
+    return x + [rem]
+
+
+def simplex_logabsdetjac(y):
+    """log |det d x_{1..K-1} / d y| from the DEFINITION: numerical Jacobian at 50 digits"""
+    n = len(y)
+    J = mp.zeros(n, n)
+    for j in range(n):
+        def col(t, j=j):
+            v = list(y)
+            v[j] = t
+            return simplex_invlink(v)
+        for i in range(n):
+            J[i, j] = mp.diff(lambda t, i=i, j=j: col(t)[i], y[j])
+    return mp.log(abs(mp.det(J)))
+
+
+def lj_beta_bernoulli(th, data):
+    """test/mcmc/hmc.jl:24-43: p ~ Beta(a, b); obs[i] ~ Bernoulli(p); logit link"""
+    a, b = data["hyper"]
+    p = 1 / (1 + mp.exp(-th[0]))
+    lp = beta_lpdf(p, a, b)
+    for o in data["y"]:
+        lp += mp.log(p) if o != 0 else mp.log(1 - p)
+    return lp + mp.log(p) + mp.log(1 - p)      # log |d p / d theta|
+
+
+def lj_dirichlet_cat(th, data):
+    """test/mcmc/hmc.jl:45-62: ps ~ Dirichlet(K1, al1); pd ~ Dirichlet(K2, al2); obs[i] ~ Categorical(ps)"""
+    K1, al1, K2, al2 = data["hyper"]
+    K1, K2 = int(K1), int(K2)
+    y1, y2 = list(th[:K1 - 1]), list(th[K1 - 1:])
+    ps = simplex_invlink(y1)
+    lp = dirichlet_lpdf(ps, al1) + simplex_logabsdetjac(y1)
+    for o in data["y"]:
+        lp += mp.log(ps[int(o) - 1])
+    if K2 > 0:
+        lp += dirichlet_lpdf(simplex_invlink(y2), al2) + simplex_logabsdetjac(y2)
+    return lp
+
+
+FAMS = {"beta_bernoulli": (6, lj_beta_bernoulli), "dirichlet_categorical": (7, lj_dirichlet_cat),
+        "gdemo": (0, lj_gdemo), "linreg": (1, lj_linreg), "eight_schools": (2, lj_eight),
         "logistic": (3, lj_logistic), "hier": (4, lj_hier), "std_normal": (5, lj_stdnormal)}
 
 
@@ -148,6 +207,15 @@ def main():
     add("hier", {"X": rng.standard_normal(G * 6), "y": rng.standard_normal(G * 6), "group": grp, "G": G,
                  "hyper": [10.0, 5.0]}, (rng.standard_normal((4, 5 + 2 * G)) * 0.8).tolist())
     add("std_normal", {}, [[0.0], [1.25]])
+    # the constrained-support models of the reference's HMC tests (their own data); a separate
+    # generator so that the cases above keep their points
+    r2 = np.random.default_rng(7)
+    add("beta_bernoulli", {"y": [0, 1, 0, 1, 1, 1, 1, 1, 1, 1], "hyper": [2.0, 2.0]},
+        [[0.0], [0.9], [-3.5], [25.0]])
+    add("dirichlet_categorical", {"y": [1, 2, 1, 2, 2, 2, 2, 2, 2, 2], "hyper": [2.0, 3.0, 4.0, 1.0]},
+        [[0.0, 0.0, 0.0, 0.0]] + (r2.standard_normal((4, 4)) * 1.5).tolist())
+    add("dirichlet_categorical", {"y": [3, 1, 3, 2, 3], "hyper": [3.0, 0.7, 0.0, 0.0]},
+        (r2.standard_normal((3, 2)) * 1.2).tolist())
     out = {
         "generator": "tests/golden/make_golden.py (mpmath, 50 digits)",
         "reference_known_answers": {
@@ -158,6 +226,11 @@ def main():
                                      "src": "test/optimisation/Optimisation.jl:299-301"},
             "gdemo_mle": {"s": 0.0625, "m": 1.75, "src": "test/optimisation/Optimisation.jl:246-248"},
             "std_normal_lp_at_0": float(normal_lpdf(mp.mpf(0), 0, 1)),
+            "beta_bernoulli_posterior_mean": {"p": 10 / 14, "atol": 0.1, "sampler": "HMC(1.5, 3), 1000 draws",
+                                              "src": "test/mcmc/hmc.jl:24-43"},
+            "dirichlet_categorical_posterior_mean": {"ps": [5 / 16, 11 / 16], "atol": 0.015,
+                                                     "sampler": "HMC(0.75, 2), 1000 draws",
+                                                     "src": "test/mcmc/hmc.jl:45-62"},
         },
         "cases": cases,
     }

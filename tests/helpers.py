@@ -27,6 +27,11 @@ def model_from_golden(case):
         return T.LogisticRegression(np.array(d["X"]), d["y"], *d["hyper"])
     if name == "hier":
         return T.HierLinearRegression(d["X"], d["y"], d["group"], d["G"], *d["hyper"])
+    if name == "beta_bernoulli":
+        return T.BetaBernoulli(d["y"], *d["hyper"])
+    if name == "dirichlet_categorical":
+        K1, a1, K2, a2 = d["hyper"]
+        return T.DirichletCategorical(d["y"], int(K1), a1, int(K2), a2)
     if name == "std_normal":
         return T.StdNormal(len(case["points"][0]["theta"]))
     raise KeyError(name)

@@ -245,3 +245,32 @@ def test_warns_after_ten_failed_initial_draws(built):
         warnings.simplefilter("always")
         T.sample(T.gdemo_default(), T.NUTS(5, 0.8), T.MCMCThreads(), 4, 8, seed=3, verbose=False)
     assert not any("initial parameters" in str(x.message) for x in w)
+
+
+def test_reference_posterior_pins_of_the_constrained_support_models(built):
+    """the reference's own HMC tests on its own data (test/mcmc/hmc.jl:24-62), every chain held to the
+    reference's tolerance: Beta-Bernoulli mean(p) = 10/14 (atol 0.1) with HMC(1.5, 3); Dirichlet-
+    Categorical mean(ps) = [5/16, 11/16] (atol 0.015) with HMC(0.75, 2); 1000 draws each.  The simplex
+    model has D = 4 linked dimensions and 6 chain columns."""
+    import oracle as O
+    from helpers import oracle_config, oracle_of
+    m1 = T.BetaBernoulli([0, 1, 0, 1, 1, 1, 1, 1, 1, 1])
+    ch = T.sample(m1, T.HMC(1.5, 3), T.MCMCThreads(), 1000, 64, seed=123, verbose=False)
+    assert ch.value.shape == (1000, 1 + 12, 64) and ch.names[0] == "p"
+    assert np.all(np.abs(ch["p"][1:].mean(axis=0) - 10 / 14) < 0.1)
+    ref = O.sample_chains(oracle_of(m1), oracle_config(T.HMC(1.5, 3), 0, 123), 64, 999)
+    np.testing.assert_allclose(ch["p"][1:41].T, ref["params"][:, :40, 0], rtol=1e-9)      # draw for draw
+    m2 = T.DirichletCategorical([1, 2, 1, 2, 2, 2, 2, 2, 2, 2])
+    assert (m2.D, m2.P) == (4, 6)
+    ch = T.sample(m2, T.HMC(0.75, 2), T.MCMCThreads(), 1000, 64, seed=123, verbose=False)
+    assert ch.value.shape == (1000, 6 + 12, 64) and ch.names[:3] == ("ps[1]", "ps[2]", "pd[1]")
+    means = ch.get_params()[1:].mean(axis=0)                                              # [6, chains]
+    assert np.all(np.abs(means[0] - 5 / 16) < 0.015) and np.all(np.abs(means[1] - 11 / 16) < 0.015)
+    np.testing.assert_allclose(ch["ps[1]"] + ch["ps[2]"], 1.0, rtol=1e-12)
+    np.testing.assert_allclose(ch.get_params()[:, 2:].sum(axis=1), 1.0, rtol=1e-12)
+    ref = O.sample_chains(oracle_of(m2), oracle_config(T.HMC(0.75, 2), 0, 123), 64, 999)
+    np.testing.assert_allclose(ch.get_params()[1:41].transpose(2, 0, 1), ref["params"][:, :40], rtol=1e-8)
+    # NUTS with the default diagonal metric on the simplex model, initial_params in user space
+    ch = T.sample(m2, T.NUTS(200, 0.8), T.MCMCThreads(), 500, 32, seed=5, verbose=False,
+                  initial_params=[T.InitFromParams({"ps": [0.5, 0.5], "pd": [0.25] * 4})] * 32)
+    assert abs(ch["ps[1]"].mean() - 5 / 16) < 0.01

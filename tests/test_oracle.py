@@ -8,7 +8,7 @@ import oracle as O
 import turing_jl_b200 as T
 from oracle import diagnostics as dg
 
-from helpers import golden_cases, model_from_golden, oracle_of
+from helpers import golden_cases, model_from_golden, oracle_config, oracle_of
 
 
 @pytest.fixture(scope="module")
@@ -62,9 +62,9 @@ def test_user_space_logp_identities(golden):
             th = np.array(pt["theta"])
             p, lp3 = om.constrain(th)
             assert lp3[2] == pytest.approx(lp3[0] + lp3[1], rel=1e-14)
-            logjac = sum(th[i] for i, n in enumerate(m.param_names) if n in m.positive)
+            logjac = m.logabsdetjac(th)       # log link: sum of the thetas; logit / stick breaking: Bijectors
             assert om.lpgrad(th)[0] == pytest.approx(lp3[2] + logjac, rel=1e-12, abs=1e-12)
-            np.testing.assert_allclose(p, m.invlink(th), rtol=1e-15)
+            np.testing.assert_allclose(p, m.invlink(th), rtol=1e-14)
 
 
 def test_gradient_vs_torch_autograd(golden):
@@ -253,3 +253,19 @@ def test_resume_continues_bit_for_bit_and_chain_ids_address_the_streams():
     assert b["n_grad"] + r["n_grad"] == a["n_grad"] + 6      # one re-evaluation per restored chain
     sub = O.sample_chains(om, cfg, 0, 60, chain_ids=[4, 1])
     assert np.array_equal(sub["theta"][0], a["theta"][4]) and np.array_equal(sub["theta"][1], a["theta"][1])
+
+
+def test_reference_posterior_pins_of_the_constrained_support_models():
+    """test/mcmc/hmc.jl:24-43: p ~ Beta(2,2), ten Bernoulli observations, HMC(1.5, 3), 1000 draws ->
+    mean(p) = 10/14 (atol 0.1); test/mcmc/hmc.jl:45-62: ps ~ Dirichlet(2,3), pd ~ Dirichlet(4,1),
+    ten Categorical observations, HMC(0.75, 2), 1000 draws -> mean(ps) = [5/16, 11/16] (atol 0.015).
+    The reference runs one chain with one seed; here every one of 32 seeded chains must pass."""
+    m1 = T.BetaBernoulli([0, 1, 0, 1, 1, 1, 1, 1, 1, 1])
+    r = O.sample_chains(oracle_of(m1), oracle_config(T.HMC(1.5, 3), 0, 123), 32, 1000)
+    assert np.all(np.abs(r["params"][:, :, 0].mean(axis=1) - 10 / 14) < 0.1)
+    m2 = T.DirichletCategorical([1, 2, 1, 2, 2, 2, 2, 2, 2, 2])
+    r = O.sample_chains(oracle_of(m2), oracle_config(T.HMC(0.75, 2), 0, 123), 32, 1000)
+    means = r["params"].mean(axis=1)
+    assert np.all(np.abs(means[:, :2] - [5 / 16, 11 / 16]) < 0.015)
+    np.testing.assert_allclose(r["params"][:, :, :2].sum(axis=2), 1.0, rtol=1e-12)
+    np.testing.assert_allclose(means[:, 2:].mean(axis=0), 0.25, atol=0.01)      # pd: the uniform prior

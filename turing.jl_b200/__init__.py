@@ -9,7 +9,7 @@ from . import _lib, build, distributed, models  # noqa: F401
 from .chains import Chains, chainscat  # noqa: F401
 from .engine import Engine  # noqa: F401
 from .inference import LogDensityFunction, loadstate, post_sample_hook, sample  # noqa: F401
-from .models import (EightSchools, GDemo, HierLinearRegression, LinearRegression,  # noqa: F401
+from .models import (BetaBernoulli, DirichletCategorical, EightSchools, GDemo, HierLinearRegression, LinearRegression,  # noqa: F401
                      LogisticRegression, StdNormal, gdemo_default)
 from .samplers import (HMC, HMCDA, NUTS, SGHMC, SGLD, InitFromParams, InitFromUniform,  # noqa: F401
                        MCMCDistributed, MCMCSerial, MCMCThreads, PolynomialStepsize)
@@ -17,4 +17,5 @@ from .samplers import (HMC, HMCDA, NUTS, SGHMC, SGLD, InitFromParams, InitFromUn
 __all__ = ["sample", "NUTS", "HMC", "HMCDA", "SGHMC", "SGLD", "PolynomialStepsize", "MCMCThreads", "MCMCSerial", "MCMCDistributed",
            "Chains", "chainscat", "loadstate", "LogDensityFunction", "Engine", "InitFromParams",
            "InitFromUniform", "GDemo", "gdemo_default", "LinearRegression", "EightSchools",
-           "LogisticRegression", "HierLinearRegression", "StdNormal", "models"]
+           "LogisticRegression", "HierLinearRegression", "StdNormal", "BetaBernoulli", "DirichletCategorical",
+           "models"]

@@ -19,6 +19,10 @@ namespace tnuts {
     else if (_f == TNUTS_STD_NORMAL && _D == 2) { CALL(StdNormal<2>); }                \
     else if (_f == TNUTS_STD_NORMAL && _D == 4) { CALL(StdNormal<4>); }                \
     else if (_f == TNUTS_STD_NORMAL && _D == 10) { CALL(StdNormal<10>); }              \
+    else if (_f == TNUTS_BETA_BERNOULLI && _D == 1) { CALL(BetaBernoulli); }           \
+    else if (_f == TNUTS_DIRICHLET_CATEGORICAL && _D == 4 && (e)->P == 6) { CALL(DirichletCat24); } \
+    else if (_f == TNUTS_DIRICHLET_CATEGORICAL && _D == 2 && (e)->P == 3) { CALL(DirichletCat30); } \
+    else if (_f == TNUTS_DIRICHLET_CATEGORICAL && _D == 1 && (e)->P == 2) { CALL(DirichletCat20); } \
     else return set_error((e), TNUTS_E_UNSUPPORTED, "no thread-per-chain kernel for this family/D"); \
   } while (0)
 
@@ -30,6 +34,8 @@ bool thread_strategy_supported(const Engine *e) {
   if (f == TNUTS_LINREG) return D == 3 && N <= 16;
   if (f == TNUTS_EIGHT_SCHOOLS) return D == 10 && N == 8;
   if (f == TNUTS_STD_NORMAL) return D == 1 || D == 2 || D == 4 || D == 10;
+  if (f == TNUTS_BETA_BERNOULLI) return D == 1;
+  if (f == TNUTS_DIRICHLET_CATEGORICAL) return (D == 4 && e->P == 6) || (D == 2 && e->P == 3) || (D == 1 && e->P == 2);
   return false;
 }
 

@@ -541,16 +541,17 @@ __device__ __forceinline__ void chain_run_range(const SmallData &md, const Chain
     // ---- record (ParamsWithStats): constrained params, user-space log-probs, stats ----
     if (rp.first_keep >= 1 && t >= rp.first_keep && (t - rp.first_keep) % rp.thin == 0) {
       const long long k = (t - rp.first_keep) / rp.thin;
-      double p[D], prior, lik;
+      constexpr int P = M::P;   // user-space parameters (a K-simplex: K columns for K - 1 linked dims)
+      double p[P], prior, lik;
       M::constrain(md, th, p, prior, lik);
       double *row = out.draws + (size_t)k * out.ncol * C + c;
 #pragma unroll
-      for (int d = 0; d < D; ++d) row[(size_t)d * C] = p[d];
-      row[(size_t)(D + 0) * C] = prior;
-      row[(size_t)(D + 1) * C] = lik;
-      row[(size_t)(D + 2) * C] = prior + lik;
+      for (int d = 0; d < P; ++d) row[(size_t)d * C] = p[d];
+      row[(size_t)(P + 0) * C] = prior;
+      row[(size_t)(P + 1) * C] = lik;
+      row[(size_t)(P + 2) * C] = prior + lik;
 #pragma unroll
-      for (int s = 0; s < TNUTS_NSTAT; ++s) row[(size_t)(D + 3 + s) * C] = stats[s];
+      for (int s = 0; s < TNUTS_NSTAT; ++s) row[(size_t)(P + 3 + s) * C] = stats[s];
       if (out.theta != nullptr) {
 #pragma unroll
         for (int d = 0; d < D; ++d) out.theta[((size_t)k * D + d) * C + c] = th[d];
@@ -844,16 +845,17 @@ __global__ void __launch_bounds__(kChainBlock, MINB) k_chain_run_dense(SmallData
 
     if (rp.first_keep >= 1 && t >= rp.first_keep && (t - rp.first_keep) % rp.thin == 0) {
       const long long k = (t - rp.first_keep) / rp.thin;
-      double p[D], prior, lik;
+      constexpr int P = M::P;   // user-space parameters (a K-simplex: K columns for K - 1 linked dims)
+      double p[P], prior, lik;
       M::constrain(md, th, p, prior, lik);
       double *row = out.draws + (size_t)k * out.ncol * C + c;
 #pragma unroll
-      for (int d = 0; d < D; ++d) row[(size_t)d * C] = p[d];
-      row[(size_t)(D + 0) * C] = prior;
-      row[(size_t)(D + 1) * C] = lik;
-      row[(size_t)(D + 2) * C] = prior + lik;
+      for (int d = 0; d < P; ++d) row[(size_t)d * C] = p[d];
+      row[(size_t)(P + 0) * C] = prior;
+      row[(size_t)(P + 1) * C] = lik;
+      row[(size_t)(P + 2) * C] = prior + lik;
 #pragma unroll
-      for (int s = 0; s < TNUTS_NSTAT; ++s) row[(size_t)(D + 3 + s) * C] = stats[s];
+      for (int s = 0; s < TNUTS_NSTAT; ++s) row[(size_t)(P + 3 + s) * C] = stats[s];
       if (out.theta != nullptr) {
 #pragma unroll
         for (int d = 0; d < D; ++d) out.theta[((size_t)k * D + d) * C + c] = th[d];
@@ -923,12 +925,13 @@ __global__ void k_point_constrain(SmallData md, const double *theta, long long n
   constexpr int D = M::D;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double th[D], p[D], prior, lik;
+  constexpr int P = M::P;
+  double th[D], p[P], prior, lik;
 #pragma unroll
   for (int d = 0; d < D; ++d) th[d] = theta[i * D + d];
   M::constrain(md, th, p, prior, lik);
 #pragma unroll
-  for (int d = 0; d < D; ++d) params[i * D + d] = p[d];
+  for (int d = 0; d < P; ++d) params[i * P + d] = p[d];
   logp[i * 3 + 0] = prior;
   logp[i * 3 + 1] = lik;
   logp[i * 3 + 2] = prior + lik;

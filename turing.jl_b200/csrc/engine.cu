@@ -141,6 +141,45 @@ static int build_small(Engine *e, const tnuts_model *m) {
     case TNUTS_STD_NORMAL:
       s.cst = -0.5 * m->D * kLog2Pi;
       break;
+    case TNUTS_BETA_BERNOULLI: {
+      const double a = m->hyper[0], b = m->hyper[1];
+      double ones = 0, zeros = 0;
+      for (long long i = 0; i < m->N; ++i) (m->y[i] != 0.0 ? ones : zeros) += 1.0;
+      s.n = 0;
+      s.a[0] = a + ones;
+      s.b[0] = b + zeros;
+      s.h[0] = a;
+      s.h[1] = b;
+      s.h[2] = ones;
+      s.h[3] = zeros;
+      s.cst = -(std::lgamma(a) + std::lgamma(b) - std::lgamma(a + b));
+    } break;
+    case TNUTS_DIRICHLET_CATEGORICAL: {
+      // per linked dimension: lp = sum_d A_d log sigma(u_d) + B_d log sigma(-u_d), u_d = theta_d - c_d
+      // (stick breaking; derivation in oracle/tnuts_oracle.c)
+      const int K[2] = {(int)m->hyper[0], (int)m->hyper[2]};
+      const double al[2] = {m->hyper[1], m->hyper[3]};
+      s.n = 0;
+      for (long long i = 0; i < m->N; ++i) s.cnt[(int)m->y[i] - 1] += 1.0;
+      s.h[0] = al[0];
+      s.h[1] = al[1];
+      s.cst = 0.0;
+      int d0 = 0;
+      for (int blk = 0; blk < 2; ++blk) {
+        const int Kb = K[blk];
+        if (Kb <= 0) continue;
+        s.cst += std::lgamma(Kb * al[blk]) - Kb * std::lgamma(al[blk]);
+        double tail = (al[blk] - 1.0) + (blk == 0 ? s.cnt[Kb - 1] : 0.0);
+        for (int j = Kb - 2; j >= 0; --j) {
+          const double cj = (al[blk] - 1.0) + (blk == 0 ? s.cnt[j] : 0.0);
+          s.a[d0 + j] = cj + 1.0;
+          s.b[d0 + j] = tail + 1.0 + (double)(Kb - 2 - j);
+          s.c[d0 + j] = std::log((double)(Kb - 1 - j));
+          tail += cj;
+        }
+        d0 += Kb - 1;
+      }
+    } break;
     default:
       break;
   }
@@ -270,6 +309,12 @@ static int set_model_impl(tnuts_engine *h, const tnuts_model *m, bool device_ptr
   TN_CUDA(e, cudaSetDevice(e->device));
   e->D = m->D;
   e->P = m->D;
+  if (m->family == TNUTS_DIRICHLET_CATEGORICAL) {   // a K-simplex: K - 1 linked dimensions, K chain columns
+    const int K1 = (int)m->hyper[0], K2 = (int)m->hyper[2];
+    if (K1 < 2 || K2 < 0 || K2 == 1 || K1 + K2 > 16 || m->D != K1 - 1 + (K2 > 0 ? K2 - 1 : 0))
+      return set_error(e, TNUTS_E_ARG, "dirichlet-categorical: hyper = {K1, al1, K2, al2}, D = K1 - 1 + K2 - 1");
+    e->P = K1 + K2;
+  }
   ModelDev &md = e->model;
   md.family = m->family;
   md.D = m->D;
@@ -321,6 +366,19 @@ static int set_model_impl(tnuts_engine *h, const tnuts_model *m, bool device_ptr
       break;
     case TNUTS_STD_NORMAL:
       break;
+    case TNUTS_BETA_BERNOULLI:
+      if (!m->y || m->D != 1 || !(m->hyper[0] > 0) || !(m->hyper[1] > 0))
+        return set_error(e, TNUTS_E_ARG, "beta-bernoulli needs y, D=1, hyper = {a, b} > 0");
+      rc = upload(m->y, N * 8, (const void **)&md.y);
+      break;
+    case TNUTS_DIRICHLET_CATEGORICAL:
+      if (!m->y || !(m->hyper[1] > 0) || (m->hyper[2] > 0 && !(m->hyper[3] > 0)))
+        return set_error(e, TNUTS_E_ARG, "dirichlet-categorical needs y and positive concentrations");
+      for (long long i = 0; i < m->N; ++i)
+        if (!(m->y[i] >= 1.0 && m->y[i] <= m->hyper[0]))
+          return set_error(e, TNUTS_E_ARG, "dirichlet-categorical: observed categories must be in 1..K1");
+      rc = upload(m->y, N * 8, (const void **)&md.y);
+      break;
     default:
       return set_error(e, TNUTS_E_ARG, "tnuts_set_model: unknown family");
   }
@@ -333,6 +391,12 @@ static int set_model_impl(tnuts_engine *h, const tnuts_model *m, bool device_ptr
   const bool block_ok = block_strategy_supported(e);
   if (e->cfg.strategy == STRAT_BLOCK && !block_ok)
     return set_error(e, TNUTS_E_UNSUPPORTED, "one-CTA-per-chain strategy not available for this model");
+  if ((m->family == TNUTS_BETA_BERNOULLI || m->family == TNUTS_DIRICHLET_CATEGORICAL) &&
+      (!thread_ok || (e->cfg.strategy != STRAT_AUTO && e->cfg.strategy != STRAT_THREAD) ||
+       e->cfg.algorithm == TNUTS_ALG_SGHMC || e->cfg.algorithm == TNUTS_ALG_SGLD))
+    return set_error(e, TNUTS_E_UNSUPPORTED,
+                     "the constrained-support test families run on the thread-per-chain strategy (NUTS / HMC / HMCDA); "
+                     "simplex sizes (K1, K2) in {(2,4), (3,0), (2,0)}");
   const bool sg = e->cfg.algorithm == TNUTS_ALG_SGHMC || e->cfg.algorithm == TNUTS_ALG_SGLD;
   if (sg && (e->cfg.strategy == STRAT_THREAD || e->cfg.strategy == STRAT_BLOCK))
     return set_error(e, TNUTS_E_UNSUPPORTED, "SGHMC / SGLD run on the batched (lock-step) strategy only");

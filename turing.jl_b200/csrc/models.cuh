@@ -21,12 +21,15 @@ struct SmallData {
   double cst;      // sum of theta-independent terms of lp
   double cst_lik;  // theta-independent part of the likelihood (user-space output)
   double h[4];     // hyper-parameters
+  double c[16];    // logit-term families: shift of dimension d (u_d = theta_d - c_d)
+  double cnt[16];  // DIRICHLET_CATEGORICAL: observation count of category k
 };
 
 // ---- gdemo: s ~ InverseGamma(al, be); m ~ Normal(0, sqrt(s)); x_i ~ Normal(m, sqrt(s)) ----
 // theta = (log s, m).  test/test_utils/models.jl:15-21
 struct GDemo {
   static constexpr int D = 2;
+  static constexpr int P = D;   // user-space parameters
   static constexpr int family = TNUTS_GDEMO;
   __device__ static double lpgrad(const SmallData &md, const double (&th)[2], double (&g)[2]) {
     const double al = md.h[0], be = md.h[1];
@@ -65,6 +68,7 @@ struct GDemo {
 // y ~ MvNormal(alpha .+ beta .* x, sigma2 * I).  theta = (alpha, beta, log sigma2)
 struct LinReg {
   static constexpr int D = 3;
+  static constexpr int P = D;   // user-space parameters
   static constexpr int family = TNUTS_LINREG;
   __device__ static double lpgrad(const SmallData &md, const double (&th)[3], double (&g)[3]) {
     const double isd2 = md.h[2], ic = md.h[3];
@@ -108,6 +112,7 @@ struct LinReg {
 template <int J>
 struct EightSchools {
   static constexpr int D = J + 2;
+  static constexpr int P = D;   // user-space parameters
   static constexpr int family = TNUTS_EIGHT_SCHOOLS;
   __device__ static double lpgrad(const SmallData &md, const double (&th)[D], double (&g)[D]) {
     const double isd2 = md.h[2], ic = md.h[3];
@@ -151,6 +156,7 @@ struct EightSchools {
 template <int D_>
 struct StdNormal {
   static constexpr int D = D_;
+  static constexpr int P = D;   // user-space parameters
   static constexpr int family = TNUTS_STD_NORMAL;
   __device__ static double lpgrad(const SmallData &md, const double (&th)[D], double (&g)[D]) {
     double lp = md.cst;
@@ -172,5 +178,90 @@ struct StdNormal {
     lik = 0.0;
   }
 };
+
+// ---- constrained-support models of the reference's HMC tests (test/mcmc/hmc.jl:24-62) ----
+// Both log joints are sums of  A_d log sigma(u_d) + B_d log sigma(-u_d),  u_d = theta_d - c_d
+// (logit link for p in (0, 1); stick breaking for a simplex: see oracle/tnuts_oracle.c and
+// tests/golden/make_golden.py, which derives the same densities from the distribution definitions).
+__device__ __forceinline__ double log_sigmoid(double u) {
+  return u >= 0.0 ? -log1p(exp(-u)) : u - log1p(exp(u));
+}
+__device__ __forceinline__ double sigmoid(double u) {
+  if (u >= 0.0) return 1.0 / (1.0 + exp(-u));
+  const double e = exp(u);
+  return e / (1.0 + e);
+}
+
+// p ~ Beta(a, b); obs[i] ~ Bernoulli(p).  theta = logit(p).  md.a[0] = a + #ones, md.b[0] = b + #zeros,
+// md.h = {a, b, #ones, #zeros}, md.cst = -log B(a, b)
+struct BetaBernoulli {
+  static constexpr int D = 1;
+  static constexpr int P = 1;
+  static constexpr int family = TNUTS_BETA_BERNOULLI;
+  __device__ static double lpgrad(const SmallData &md, const double (&th)[1], double (&g)[1]) {
+    const double u = th[0], p = sigmoid(u);
+    g[0] = md.a[0] * (1.0 - p) - md.b[0] * p;
+    return md.a[0] * log_sigmoid(u) + md.b[0] * log_sigmoid(-u) + md.cst;
+  }
+  __device__ static void constrain(const SmallData &md, const double (&th)[1], double (&p)[1], double &prior,
+                                   double &lik) {
+    const double lpp = log_sigmoid(th[0]), lq = log_sigmoid(-th[0]);
+    p[0] = sigmoid(th[0]);
+    prior = (md.h[0] - 1.0) * lpp + (md.h[1] - 1.0) * lq + md.cst;
+    lik = md.h[2] * lpp + md.h[3] * lq;
+  }
+};
+
+// ps ~ Dirichlet(K1, al1); pd ~ Dirichlet(K2, al2); obs[i] ~ Categorical(ps).  theta = stick-breaking
+// coordinates of ps, then of pd.  md.a / md.b / md.c per linked dimension, md.cnt[k] = count of
+// category k, md.h = {al1, al2}, md.cst = sum over the blocks of lgamma(K al) - K lgamma(al)
+template <int K1, int K2>
+struct DirichletCat {
+  static constexpr int D = K1 - 1 + (K2 > 0 ? K2 - 1 : 0);
+  static constexpr int P = K1 + K2;
+  static constexpr int family = TNUTS_DIRICHLET_CATEGORICAL;
+  __device__ static double lpgrad(const SmallData &md, const double (&th)[D], double (&g)[D]) {
+    double lp = md.cst;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double u = th[d] - md.c[d], z = sigmoid(u);
+      lp += md.a[d] * log_sigmoid(u) + md.b[d] * log_sigmoid(-u);
+      g[d] = md.a[d] * (1.0 - z) - md.b[d] * z;
+    }
+    return lp;
+  }
+  template <int K>
+  __device__ static void invlink(const SmallData &md, const double *y, const double *shift, double *x) {
+    double rem = 1.0;
+#pragma unroll
+    for (int j = 0; j < K - 1; ++j) {
+      const double z = sigmoid(y[j] - shift[j]);
+      x[j] = z * rem;
+      rem *= 1.0 - z;
+    }
+    x[K - 1] = rem;
+  }
+  __device__ static void constrain(const SmallData &md, const double (&th)[D], double (&p)[P], double &prior,
+                                   double &lik) {
+    invlink<K1>(md, th, md.c, p);
+    prior = md.cst;
+    lik = 0.0;
+#pragma unroll
+    for (int k = 0; k < K1; ++k) {
+      const double l = log(p[k]);
+      prior += (md.h[0] - 1.0) * l;
+      lik += md.cnt[k] * l;
+    }
+    if (K2 > 0) {
+      invlink<(K2 > 0 ? K2 : 1)>(md, th + (K1 - 1), md.c + (K1 - 1), p + K1);
+#pragma unroll
+      for (int k = 0; k < K2; ++k) prior += (md.h[1] - 1.0) * log(p[K1 + k]);
+    }
+  }
+};
+
+using DirichletCat24 = DirichletCat<2, 4>;   // test/mcmc/hmc.jl:45-62
+using DirichletCat30 = DirichletCat<3, 0>;
+using DirichletCat20 = DirichletCat<2, 0>;
 
 }  // namespace tnuts

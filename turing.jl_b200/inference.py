@@ -139,7 +139,7 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
     errors = [None] * ndev
     # bundle_samples target: (iterations x names x chains); the engine's device layout is
     # identical, so a single-GPU run copies straight into it (pinned host memory)
-    P = model.D
+    P = model.P          # chain columns: D, except K per K-simplex
     nint = len(INTERNALS)
     value = pinned.empty((N, P + nint, n_chains))
     if _discard == 0 and initial_state is None:

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _lib
 
-GDEMO, LINREG, EIGHT_SCHOOLS, LOGISTIC, HIER_LINREG, STD_NORMAL = range(6)
+GDEMO, LINREG, EIGHT_SCHOOLS, LOGISTIC, HIER_LINREG, STD_NORMAL, BETA_BERNOULLI, DIRICHLET_CATEGORICAL = range(8)
 
 
 class Model:
@@ -29,6 +29,12 @@ class Model:
     # --- interface used by sample() ---
     @property
     def D(self):
+        """LogDensityProblems.dimension: length of the linked (unconstrained) vector"""
+        return len(self.param_names)
+
+    @property
+    def P(self):
+        """number of user-space parameters (columns of the chain): D, except K per K-simplex"""
         return len(self.param_names)
 
     def has_discrete_variables(self):
@@ -51,6 +57,12 @@ class Model:
             if n in self.positive:
                 t[..., i] = np.exp(t[..., i])
         return t
+
+    def logabsdetjac(self, theta):
+        """log |det J| of the inverse link at theta: what the linked log density adds to the user-space
+        log joint (Bijectors; positive support links by log, so it is the sum of those thetas)"""
+        t = np.asarray(theta, dtype=np.float64)
+        return float(sum(t[i] for i, n in enumerate(self.param_names) if n in self.positive))
 
     def c_struct(self):
         """tnuts_model with host pointers into this object's arrays (kept alive by self)."""
@@ -173,6 +185,115 @@ class StdNormal(Model):
     def __init__(self, D=1):
         super().__init__()
         self.param_names = ("x",) if D == 1 else tuple("x[%d]" % (i + 1) for i in range(D))
+
+
+class BetaBernoulli(Model):
+    """@model function constrained_test(obs)
+           p ~ Beta(2, 2)
+           for i in 1:length(obs); obs[i] ~ Bernoulli(p); end
+       end                                   (test/mcmc/hmc.jl:24-43)
+    p in (0, 1) links by logit (Bijectors)."""
+    family = BETA_BERNOULLI
+    param_names = ("p",)
+
+    def __init__(self, obs, a=2.0, b=2.0):
+        super().__init__()
+        self.y = _f64(obs)
+        self.N = self.y.size
+        self.hyper = (a, b)
+
+    def link(self, params):
+        p = np.asarray(params, dtype=np.float64)
+        if not (p.min() > 0 and p.max() < 1):
+            raise ValueError("initial value of p must be in (0, 1)")
+        return np.log(p) - np.log1p(-p)
+
+    def invlink(self, theta):
+        return 1.0 / (1.0 + np.exp(-np.asarray(theta, dtype=np.float64)))
+
+    def logabsdetjac(self, theta):
+        t = np.asarray(theta, dtype=np.float64)
+        return float(np.sum(_log_sigmoid(t) + _log_sigmoid(-t)))     # log p + log(1 - p)
+
+
+def _log_sigmoid(u):
+    u = np.asarray(u, dtype=np.float64)
+    return np.where(u >= 0, -np.log1p(np.exp(-np.abs(u))), u - np.log1p(np.exp(-np.abs(u))))
+
+
+def _stick_link(x):
+    """Bijectors' SimplexBijector (the Stan stick-breaking transform): K-simplex -> K - 1 reals"""
+    x = np.asarray(x, dtype=np.float64)
+    K = x.shape[-1]
+    rem = 1.0 - np.concatenate([np.zeros(x.shape[:-1] + (1,)), np.cumsum(x[..., :-2], axis=-1)], axis=-1)
+    z = x[..., :-1] / rem
+    return np.log(z) - np.log1p(-z) + np.log(np.arange(K - 1, 0, -1))
+
+
+def _stick_logabsdetjac(y):
+    y = np.asarray(y, dtype=np.float64)
+    K = y.shape[-1] + 1
+    u = y - np.log(np.arange(K - 1, 0, -1))
+    lz, l1z = _log_sigmoid(u), _log_sigmoid(-u)
+    lrem = np.concatenate([[0.0], np.cumsum(l1z)[:-1]])
+    return float(np.sum(lz + l1z + lrem))
+
+
+def _stick_invlink(y):
+    y = np.asarray(y, dtype=np.float64)
+    K = y.shape[-1] + 1
+    z = 1.0 / (1.0 + np.exp(-(y - np.log(np.arange(K - 1, 0, -1)))))
+    x = np.empty(y.shape[:-1] + (K,))
+    rem = np.ones(y.shape[:-1])
+    for k in range(K - 1):
+        x[..., k] = z[..., k] * rem
+        rem = rem * (1.0 - z[..., k])
+    x[..., K - 1] = rem
+    return x
+
+
+class DirichletCategorical(Model):
+    """@model function constrained_simplex_test(obs12)
+           ps ~ Dirichlet(2, 3)
+           pd ~ Dirichlet(4, 1)
+           for i in 1:length(obs12); obs12[i] ~ Categorical(ps); end
+       end                                   (test/mcmc/hmc.jl:45-62)
+    Each K-simplex links to K - 1 reals by stick breaking, so D = K1 - 1 + K2 - 1 while the chain
+    has P = K1 + K2 parameter columns."""
+    family = DIRICHLET_CATEGORICAL
+
+    def __init__(self, obs, K1=2, alpha1=3.0, K2=4, alpha2=1.0):
+        super().__init__()
+        self.y = _f64(obs)
+        self.N = self.y.size
+        if self.N and not (self.y.min() >= 1 and self.y.max() <= K1):
+            raise ValueError("observed categories must be in 1..K1")
+        self.K1, self.K2 = int(K1), int(K2)
+        self.hyper = (float(K1), alpha1, float(K2), alpha2)
+        self.param_names = (tuple("ps[%d]" % (k + 1) for k in range(self.K1))
+                            + tuple("pd[%d]" % (k + 1) for k in range(self.K2)))
+
+    @property
+    def D(self):
+        return self.K1 - 1 + max(self.K2 - 1, 0)
+
+    def link(self, params):
+        p = np.asarray(params, dtype=np.float64)
+        parts = [_stick_link(p[..., :self.K1])]
+        if self.K2:
+            parts.append(_stick_link(p[..., self.K1:]))
+        return np.concatenate(parts, axis=-1)
+
+    def invlink(self, theta):
+        t = np.asarray(theta, dtype=np.float64)
+        parts = [_stick_invlink(t[..., :self.K1 - 1])]
+        if self.K2:
+            parts.append(_stick_invlink(t[..., self.K1 - 1:]))
+        return np.concatenate(parts, axis=-1)
+
+    def logabsdetjac(self, theta):
+        t = np.asarray(theta, dtype=np.float64)
+        return _stick_logabsdetjac(t[:self.K1 - 1]) + (_stick_logabsdetjac(t[self.K1 - 1:]) if self.K2 else 0.0)
 
 
 # ---- synthetic data of the BASELINE.json configs (SURVEY.md section 8d) ----
