@@ -12,9 +12,8 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libtnuts.so")
 
-# per-file extra flags: the persistent pump kernel reads, in one phase, what another SM wrote in the
-# previous one, so its global loads must bypass the (non-coherent) L1
-EXTRA_FLAGS = {"persist.cu": ["-Xptxas", "-dlcm=cg"]}
+# per-file extra flags (none at present)
+EXTRA_FLAGS = {}
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -1,6 +1,6 @@
-// persist.cu -- host side of the persistent pump kernel (tc_persist.cuh).  Its own translation unit
-// because it is compiled with -Xptxas -dlcm=cg: inside the persistent kernel one SM reads what
-// another wrote a phase earlier, so global loads must not be served from a (non-coherent) L1.
+// persist.cu -- host side of the persistent pump kernel (tc_persist.cuh), in its own translation unit
+// (the kernel instantiates the whole tcgen05 core and the NUTS state machine: it compiles in parallel
+// with lockstep.cu).
 #include "tc_persist.cuh"
 
 #include <cstdio>
@@ -37,6 +37,8 @@ int tc_persist_run(Engine *e, const tc::Data &td, double *part, int stride, int 
   pa.max_pumps = max_pumps;
   pa.listed_done = listed_done;
   pa.n_max = n_max;
+  static const int bar_mode = [] { const char *v = getenv("TNUTS_BAR_MODE"); return v ? atoi(v) : 0; }();
+  pa.bar_mode = bar_mode;
   pa.gbar = scratch;
   pa.n_done = count_done_dev;
   pa.h_done = h_done;

@@ -22,9 +22,9 @@
 // at pump % 16 == 8, exactly as the host loop does with its stream-ordered snapshots) -- so chains do
 // not depend on whether, or when, the persistent kernel takes over (tests/test_gpu_tc.py).
 //
-// Cross-SM visibility: everything one phase writes and another SM reads in a later phase goes through
-// L2 -- the translation unit is compiled with -Xptxas -dlcm=cg (global loads bypass L1), explicit
-// loads below use __ldcg, and every phase boundary is a grid barrier with release / acquire fences.
+// Cross-SM visibility: every phase boundary is a grid barrier whose fences release this CTA's writes
+// and invalidate its SM's L1 (the acquire side), so what another SM wrote in an earlier phase is read
+// from L2; the few loads that bypass L1 explicitly (__ldcg) are the ones polled inside a phase.
 #pragma once
 #include "lockstep_kernels.cuh"
 #include "logistic_tc.cuh"
@@ -42,6 +42,7 @@ struct PersistArgs {
   long long max_pumps;         // budget: the launch ends before this global pump index
   int listed_done;             // finished-chain count the current work list was built for
   int n_max;                   // C - listed_done: bound of the listed chains
+  int bar_mode;                // grid barrier variant (experiments)
   unsigned long long *gbar;    // grid barrier counter, zero at launch
   int *n_done;                 // finished chains (device)
   int *h_done;                 // mapped pinned mirror of n_done for the host's progress trace
@@ -56,18 +57,44 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
   return v;
 }
 
-// all CTAs of the (co-resident) grid; `target` is this thread's running arrival total
-__device__ __forceinline__ void grid_barrier(unsigned long long *bar, unsigned long long &target, unsigned nblk) {
+// all CTAs of the (co-resident) grid; `target` is this thread's running arrival total.
+// mode (experiments, TNUTS_BAR_MODE): 0 sc fences + acquire polls, 1 acq_rel fences + relaxed polls,
+// 2 release arrival + acquire polls, 3 sc fences + volatile polls (cooperative groups' recipe)
+__device__ __forceinline__ void grid_barrier(unsigned long long *bar, unsigned long long &target, unsigned nblk,
+                                             int mode) {
   target += nblk;
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1ull);
     const long long t0 = clock64();
-    while (ld_acquire_u64(bar) < target) {
-      if (clock64() - t0 > 8000000000LL) __trap();   // a protocol bug traps instead of hanging the GPU
+    if (mode == 1) {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(bar) : "memory");
+      unsigned long long v;
+      do {
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
+        if (clock64() - t0 > 8000000000LL) __trap();
+      } while (v < target);
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    } else if (mode == 2) {
+      asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(bar) : "memory");
+      while (ld_acquire_u64(bar) < target) {
+        if (clock64() - t0 > 8000000000LL) __trap();
+      }
+    } else if (mode == 3) {
+      __threadfence();
+      atomicAdd(bar, 1ull);
+      while (*(volatile unsigned long long *)bar < target) {
+        if (clock64() - t0 > 8000000000LL) __trap();
+      }
+      __threadfence();
+    } else {
+      __threadfence();
+      atomicAdd(bar, 1ull);
+      while (ld_acquire_u64(bar) < target) {
+        if (clock64() - t0 > 8000000000LL) __trap();   // a protocol bug traps instead of hanging the GPU
+      }
+      __threadfence();
     }
-    __threadfence();
   }
   __syncthreads();
 }
@@ -127,7 +154,7 @@ k_tc_persist(const __grid_constant__ CUtensorMap mapX, const float *__restrict__
   int listed_done = pa.listed_done, n_max = pa.n_max, done = pa.listed_done, snap = pa.listed_done;
   long long p = pa.pump0;
   int reason = 0;
-  // phase timing of CTA 0 (thread 0): where a pump's time goes, for the host's trace
+  // phase timing (first epilogue thread of every CTA): where a pump's time goes, for the host's trace
   long long tph[7] = {0, 0, 0, 0, 0, 0, 0};
   auto now = [] {
     unsigned long long t;
@@ -154,7 +181,7 @@ k_tc_persist(const __grid_constant__ CUtensorMap mapX, const float *__restrict__
       if (b == 0) persist_compact(ls.ts.phase, C, ls.list, ls.count, wsum);
       listed_done = done;
       n_max = C - done;
-      grid_barrier(pa.gbar, bar_target, nblk);
+      grid_barrier(pa.gbar, bar_target, nblk, pa.bar_mode);
       lap(6);
     }
     const int n = __ldcg(ls.count);                               // listed chains
@@ -186,16 +213,18 @@ k_tc_persist(const __grid_constant__ CUtensorMap mapX, const float *__restrict__
         pass += 1;
       }
     }
-    __syncthreads();
     lap(0);
-    grid_barrier(pa.gbar, bar_target, nblk);
+    grid_barrier(pa.gbar, bar_target, nblk, pa.bar_mode);
     lap(1);
 
     // ---- R: sum of the row-chunk partials in chunk order + prior -> zg, zlp (k_logistic_reduce_finish) ----
     if (grad_pass && etid >= 0) {
       const size_t cs = (size_t)(D + 1) * cap;
       const long long total = (long long)(D + 1) * n;
-      for (long long o = (long long)b * (32 * kEpiWarps) + etid; o < total; o += (long long)nblk * (32 * kEpiWarps)) {
+      // 32 consecutive outputs per warp, warps dealt round-robin over the CTAs: every SM pulls its
+      // share of the partials (a few CTAs alone are bound by their outstanding-load limit)
+      const long long wstep = (long long)nblk * kEpiWarps * 32;
+      for (long long o = ((long long)(etid >> 5) * nblk + b) * 32 + (etid & 31); o < total; o += wstep) {
         const int d = (int)(o / n), k = (int)(o - (long long)d * n);
         const int c = __ldcg(ls.list + k);
         const double *q = part + (size_t)d * cap + k;
@@ -229,9 +258,8 @@ k_tc_persist(const __grid_constant__ CUtensorMap mapX, const float *__restrict__
         }
       }
     }
-    __syncthreads();
     lap(2);
-    grid_barrier(pa.gbar, bar_target, nblk);
+    grid_barrier(pa.gbar, bar_target, nblk, pa.bar_mode);
     lap(3);
 
     // ---- P: per-chain state machine, 8 listed chains per CTA ----
@@ -242,9 +270,8 @@ k_tc_persist(const __grid_constant__ CUtensorMap mapX, const float *__restrict__
       const Tile t(etid, chain);
       ls_pump_body<Team>(t, st, ls, rp, m, out, pa.n_done, red, &s_maxlev);
     }
-    __syncthreads();
     lap(4);
-    grid_barrier(pa.gbar, bar_target, nblk);
+    grid_barrier(pa.gbar, bar_target, nblk, pa.bar_mode);
     lap(5);
     if (__ldcg(pa.n_done) >= C) {          // every chain has finished its transitions
       ++p;
@@ -252,12 +279,12 @@ k_tc_persist(const __grid_constant__ CUtensorMap mapX, const float *__restrict__
       break;
     }
   }
-  if (threadIdx.x == 0 && pa.cta_times) {
+  if (threadIdx.x == 64 && pa.cta_times) {   // the first epilogue thread: it has work in every phase
     pa.cta_times[3 * b + 0] = tph[0];
     pa.cta_times[3 * b + 1] = tph[2];
     pa.cta_times[3 * b + 2] = tph[4];
   }
-  if (b == 0 && threadIdx.x == 0) {
+  if (b == 0 && threadIdx.x == 64) {
     pa.out_state[0] = p - pa.pump0;
     pa.out_state[1] = (long long)pass;
     pa.out_state[2] = __ldcg(pa.n_done);
