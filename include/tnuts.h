@@ -169,6 +169,16 @@ int tnuts_run(tnuts_engine *e, int64_t n_transitions, int64_t first_keep, int64_
 int tnuts_run_streamed(tnuts_engine *e, int64_t n_transitions, int64_t first_keep, int64_t thin,
                        double *host_draws, int64_t chunk_draws, int64_t *n_kept);
 
+/* tnuts_run_streamed into a slab of a wider chain array: the host array is
+ * [n_kept][ncol][host_chain_stride] and host_draws points at this engine's first chain in it
+ * (host_chain_stride >= n_chains).  Several engines (one per GPU) fill ONE
+ * (iterations x names x chains) array, the layout `bundle_samples` produces for an ensemble
+ * (src/mcmc/abstractmcmc.jl:133-166, AbstractMCMC.mcmcsample with MCMCThreads), each with its
+ * own overlapped device->host copies and no host-side reshuffle. */
+int tnuts_run_streamed_strided(tnuts_engine *e, int64_t n_transitions, int64_t first_keep, int64_t thin,
+                               double *host_draws, int64_t host_chain_stride, int64_t chunk_draws,
+                               int64_t *n_kept);
+
 /* copy the draws kept by the last tnuts_run to the host.  Any pointer may be NULL.
  *   params [n_kept][P][n_chains]   constrained (user-space) parameters
  *   logp   [n_kept][3][n_chains]   logprior, loglikelihood, logjoint (no Jacobian)

@@ -210,8 +210,9 @@ def test_unit_metric_matches_oracle(built, name, strategy):
         st = out["stats"].transpose(2, 0, 1)
         np.testing.assert_array_equal(st[:, :8, 0], ref["stats"][:, :8, 0])          # n_steps
         np.testing.assert_allclose(out["theta"].transpose(2, 0, 1)[:, :8], ref["theta"][:, :8], atol=1e-7)
-        # the adapted step sizes agree after all windows (loose: the chains decorrelate by rounding)
-        np.testing.assert_allclose(np.median(eng.stepsize()), np.median(ref["eps"]), rtol=0.05)
+        # the adapted step sizes agree after all windows (loose: the chains decorrelate by rounding, and
+        # the median of 64 chains whose step sizes spread by ~20 % has a standard error of ~3 %)
+        np.testing.assert_allclose(np.median(eng.stepsize()), np.median(ref["eps"]), rtol=0.12)
         eng.close()
 
 

@@ -56,6 +56,8 @@ SYMBOLS = {
     "tnuts_run": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
     "tnuts_run_streamed": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64, _dp, C.c_int64,
                                      C.POINTER(C.c_int64)]),
+    "tnuts_run_streamed_strided": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64, _dp, C.c_int64, C.c_int64,
+                                             C.POINTER(C.c_int64)]),
     "tnuts_fetch": (C.c_int, [_H, _dp, _dp, _dp, _dp]),
     "tnuts_num_columns": (C.c_int, [_H]),
     "tnuts_fetch_draws": (C.c_int, [_H, _dp]),

@@ -492,7 +492,7 @@ int tnuts_init(tnuts_engine *h, const double *theta0) {
 // every finished segment's draws are copied device->host on a second stream while the next
 // segment computes (the draw index is the slowest dimension, so a segment is contiguous).
 static int run_segments(Engine *e, int64_t n_transitions, int64_t first_keep, int64_t thin,
-                        double *host_draws, int64_t chunk_draws, int64_t *n_kept) {
+                        double *host_draws, int64_t chunk_draws, int64_t *n_kept, int64_t host_stride = 0) {
   if (!e || !e->inited) return set_error(e, TNUTS_E_ARG, "tnuts_run: call tnuts_init first");
   if (n_transitions < 0 || thin < 1) return set_error(e, TNUTS_E_ARG, "tnuts_run: bad n_transitions/thin");
   TN_CUDA(e, cudaSetDevice(e->device));
@@ -502,6 +502,10 @@ static int run_segments(Engine *e, int64_t n_transitions, int64_t first_keep, in
   if (rc) return rc;
   if (host_draws && !e->copy_stream) TN_CUDA(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   const size_t C = (size_t)e->st.C, row = (size_t)e->out.ncol * C;
+  // host layout [keep][ncol][hstride]: hstride > C when this engine's chains are a slab of a wider
+  // chain array (several GPUs filling one (iterations x names x chains) array)
+  const size_t hstride = host_stride > 0 ? (size_t)host_stride : C;
+  if (host_draws && hstride < C) return set_error(e, TNUTS_E_ARG, "tnuts_run_streamed: host stride < n_chains");
   double *const base = e->out.draws, *const tbase = e->out.theta;
   // the lock-step strategy advances chains asynchronously (each at its own transition), so a
   // prefix of the draws is not complete before the end: one segment, one copy
@@ -539,9 +543,13 @@ static int run_segments(Engine *e, int64_t n_transitions, int64_t first_keep, in
       if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess ||
           cudaEventRecord(ev, e->stream) != cudaSuccess ||
           cudaStreamWaitEvent(e->copy_stream, ev, 0) != cudaSuccess ||
-          cudaMemcpyAsync(host_draws + (size_t)k_done * row, base + (size_t)k_done * row,
-                          8 * (size_t)(k_end - k_done) * row, cudaMemcpyDeviceToHost,
-                          e->copy_stream) != cudaSuccess) {
+          (hstride == C
+               ? cudaMemcpyAsync(host_draws + (size_t)k_done * row, base + (size_t)k_done * row,
+                                 8 * (size_t)(k_end - k_done) * row, cudaMemcpyDeviceToHost, e->copy_stream)
+               : cudaMemcpy2DAsync(host_draws + (size_t)k_done * e->out.ncol * hstride, 8 * hstride,
+                                   base + (size_t)k_done * row, 8 * C, 8 * C,
+                                   (size_t)(k_end - k_done) * e->out.ncol, cudaMemcpyDeviceToHost,
+                                   e->copy_stream)) != cudaSuccess) {
         rc = set_error(e, TNUTS_E_CUDA, "tnuts_run_streamed: D2H enqueue failed");
         break;
       }
@@ -579,6 +587,14 @@ int tnuts_run_streamed(tnuts_engine *h, int64_t n_transitions, int64_t first_kee
   Engine *e = (Engine *)h;
   if (!host_draws) return set_error(e, TNUTS_E_ARG, "tnuts_run_streamed: host_draws is NULL");
   return run_segments(e, n_transitions, first_keep, thin, host_draws, chunk_draws, n_kept);
+}
+
+int tnuts_run_streamed_strided(tnuts_engine *h, int64_t n_transitions, int64_t first_keep, int64_t thin,
+                               double *host_draws, int64_t host_chain_stride, int64_t chunk_draws,
+                               int64_t *n_kept) {
+  Engine *e = (Engine *)h;
+  if (!host_draws) return set_error(e, TNUTS_E_ARG, "tnuts_run_streamed_strided: host_draws is NULL");
+  return run_segments(e, n_transitions, first_keep, thin, host_draws, chunk_draws, n_kept, host_chain_stride);
 }
 
 int tnuts_num_columns(const tnuts_engine *h) {

@@ -25,6 +25,7 @@ __device__ __forceinline__ double ls_logaddexp(double a, double b) {
 // whole CTA; inside the persistent pump kernel (tc_persist.cuh) it is 8 warps of a larger CTA that
 // synchronise on a named barrier.  tid() is the thread's index inside its team.
 struct BlockTeam {
+  static constexpr bool kWarp = false;
   static constexpr bool kContiguous = true;   // the tile's 8 chains are consecutive (64 B per d)
   __device__ static __forceinline__ int tid() { return threadIdx.x; }
   __device__ static __forceinline__ void sync() { __syncthreads(); }
@@ -33,6 +34,7 @@ struct BlockTeam {
 };
 template <int BAR, int TID0>
 struct NamedTeam {
+  static constexpr bool kWarp = false;
   static constexpr bool kContiguous = false;  // chains picked from the work list
   __device__ static __forceinline__ int tid() { return (int)threadIdx.x - TID0; }
   __device__ static __forceinline__ void sync() {
@@ -64,6 +66,19 @@ struct NamedTeam {
   }
 };
 
+// One warp = ONE chain, lane = d-lane: the team of the persistent pump kernel's tail, where there are
+// more warps than unfinished chains.  No CTA barrier anywhere (a chain only walks the sections of the
+// state machine it needs, and never waits for seven neighbours), and the reductions over d are
+// shuffles -- in the same association order as the 8-chain tile's, so the results are bit-identical.
+struct WarpTeam {
+  static constexpr bool kWarp = true;
+  static constexpr bool kContiguous = false;
+  __device__ static __forceinline__ int tid() { return (int)(threadIdx.x & 31); }
+  __device__ static __forceinline__ void sync() { __syncwarp(); }
+  __device__ static __forceinline__ int sync_or(int p) { return __any_sync(0xffffffffu, p); }
+  __device__ static __forceinline__ int sync_and(int p) { return __all_sync(0xffffffffu, p); }
+};
+
 struct Tile {
   int c, cl, dl;
   __device__ Tile() {
@@ -77,11 +92,33 @@ struct Tile {
     dl = tid >> 3;
     c = chain;
   }
+  // lane `lane` of a WarpTeam
+  __device__ static Tile of_warp(int lane, int chain) {
+    Tile t(0, chain);
+    t.cl = 0;
+    t.dl = lane;
+    return t;
+  }
 };
 
 // sum over the 32 d-lanes of each chain for NR values at once; result valid in every thread
 template <int NR, class TM = BlockTeam>
 __device__ __forceinline__ void tile_reduce(double (&v)[NR], double *smem /* [NR][8][8] */) {
+  if constexpr (TM::kWarp) {
+    // the tile's order: d-lanes {4w .. 4w+3} pairwise ((a0 + a1) + (a2 + a3)), then the eight groups
+    // w = 0 .. 7 one after the other onto 0.0
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      double x = v[r];
+      x += __shfl_xor_sync(0xffffffffu, x, 1);
+      x += __shfl_xor_sync(0xffffffffu, x, 2);
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += __shfl_sync(0xffffffffu, x, 4 * w);
+      v[r] = s;
+    }
+    return;
+  }
   const int tid = TM::tid();
   const int lane = tid & 31, warp = tid >> 5, cl = tid & 7;
 #pragma unroll

@@ -13,7 +13,8 @@
 //              -- grid barrier --
 //              R  fixed-order sum of the row-chunk partials + prior, spread over all CTAs
 //              -- grid barrier --
-//              P  NUTS state machine (ls_pump_body) for 8 listed chains per CTA, 256 threads
+//              P  NUTS state machine (ls_pump_body), one warp per listed chain, the chains dealt
+//                 round-robin over the CTAs (WarpTeam: no CTA barrier, shuffle reductions)
 //              -- grid barrier --
 //
 // It is bit-identical to the host-pumped path by construction: the same row cut per number of chain
@@ -132,13 +133,12 @@ k_tc_persist(const __grid_constant__ CUtensorMap mapX, const float *__restrict__
              double *part /* [chunks][D+1][cap] */, int cap, ChainState st, LockstepState ls, RunParams rp,
              ModelDev m, DrawBuffers out, PersistCut cut, PersistArgs pa) {
   using Core = TcCore<KP>;
-  using Team = NamedTeam<13, 64>;   // warps 2..9: the 256 threads that run the state machine
+  using Team = WarpTeam;            // state machine: one epilogue warp per listed chain
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[Core::NBARS];
   __shared__ uint32_t tmem_slot;
   __shared__ double lp_part[kEpiWarps / 4][kChainsPerCta];
-  __shared__ double red[2 * 64];
-  __shared__ int s_maxlev;
+  __shared__ int s_maxlev[kEpiWarps];
   __shared__ int wsum[33];
 
   Core core;
@@ -262,13 +262,15 @@ k_tc_persist(const __grid_constant__ CUtensorMap mapX, const float *__restrict__
     grid_barrier(pa.gbar, bar_target, nblk, pa.bar_mode);
     lap(3);
 
-    // ---- P: per-chain state machine, 8 listed chains per CTA ----
+    // ---- P: per-chain state machine, one warp per listed chain, chains dealt over the CTAs ----
     if (b == 0 && threadIdx.x == 0 && (p & 63) == 0) *(volatile int *)pa.h_done = __ldcg(pa.n_done);
-    if (etid >= 0 && etid < kTileThreads && 8 * b < n) {
-      const int slot = 8 * b + (etid & (kTileC - 1));
-      const int chain = slot < n ? __ldcg(ls.list + slot) : C;
-      const Tile t(etid, chain);
-      ls_pump_body<Team>(t, st, ls, rp, m, out, pa.n_done, red, &s_maxlev);
+    if (etid >= 0) {
+      const int w = etid >> 5;
+      const int slot = w * (int)nblk + b;      // n <= kPersistMaxTiles * 128 <= kEpiWarps * grid
+      if (slot < n) {
+        const Tile t = Tile::of_warp(etid & 31, __ldcg(ls.list + slot));
+        ls_pump_body<Team>(t, st, ls, rp, m, out, pa.n_done, nullptr, &s_maxlev[w]);
+      }
     }
     lap(4);
     grid_barrier(pa.gbar, bar_target, nblk, pa.bar_mode);

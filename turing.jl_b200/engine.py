@@ -83,6 +83,19 @@ class Engine:
         assert out.shape[0] >= self.n_kept
         return self.n_kept
 
+    def run_streamed_slab(self, n_transitions, first_keep, thin, out, lo, chunk_draws=100):
+        """run + overlapped D2H into chains [lo, lo + C) of a wider chain array `out`
+        [n_kept, ncol, n_chains_total] (several engines, one per GPU, fill one array)"""
+        k = C.c_int64(0)
+        assert out.flags.c_contiguous and out.dtype == np.float64 and out.ndim == 3
+        assert out.shape[1] == self.ncol and 0 <= lo and lo + self.C <= out.shape[2]
+        base = C.cast(out.ctypes.data + 8 * lo, C.POINTER(C.c_double))
+        check(self.h, self.L.tnuts_run_streamed_strided(self.h, int(n_transitions), int(first_keep), int(thin),
+                                                        base, int(out.shape[2]), int(chunk_draws), C.byref(k)))
+        self.n_kept = k.value
+        assert out.shape[0] >= self.n_kept
+        return self.n_kept
+
     def set_option(self, name, value):
         check(self.h, self.L.tnuts_set_option(self.h, name.encode(), float(value)))
 

@@ -9,6 +9,7 @@ Mirrors, with the same names, argument meaning and error behaviour:
   loadstate / initial_state resume                             src/mcmc/hmc.jl:135-152
 The difference: all chains advance inside one engine call instead of one task per chain.
 """
+import ctypes as C
 import threading
 import time
 import warnings
@@ -146,11 +147,21 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
         value[0, P + 3:, :] = np.nan
     tm["alloc"] = time.perf_counter() - t_start - tm["create"]
 
+    uid = None
+    ok = [False] * ndev
+    gate = threading.Barrier(ndev)
+    if diagnostics and ndev > 1:
+        from .distributed import _new_unique_id
+        uid = _new_unique_id()
+
     def work(i):
         try:
             e = engines[i]
             lo, hi = bounds[i], bounds[i + 1]
             first = None
+            if uid is not None:
+                # one in-process NCCL communicator over the engines (joined before anything can fail)
+                e.comm_init(uid.ctypes.data_as(C.c_void_p), ndev, i)
             if initial_state is not None:
                 e.set_state(initial_state["blobs"][i])
                 # mcmcsample keeps the very first step from the restored state, then thins
@@ -181,16 +192,28 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
                     # straight into the chain array, D2H overlapped with the computation
                     e.run_streamed(n_tr, first_keep, thinning, value[row:], chunk_draws)
                 else:
-                    e.run(n_tr, first_keep, thinning)
-                    value[row:row + e.n_kept, :, lo:hi] = e.fetch_draws()
+                    # this GPU's chains are a slab [lo, hi) of the chain axis: strided D2H copies,
+                    # overlapped with the computation like the single-GPU path, no host reshuffle
+                    e.run_streamed_slab(n_tr, first_keep, thinning, value[row:], lo, chunk_draws)
             else:
                 e.n_kept = 0
-            diag = e.diagnostics() if (diagnostics and ndev == 1 and e.n_kept >= 4) else None
+            pooled = True
+            if uid is not None:
+                # pooled over every GPU's chains (a collective): only if every engine got this far
+                ok[i] = True
+                gate.wait()
+                pooled = all(ok)
+            diag = e.diagnostics() if (diagnostics and pooled and e.n_kept >= 4) else None
             ndiv = e.divergences if e.n_kept else 0
             results[i] = (diag, e.grad_evals, e.device_seconds, e.stepsize(),
                           e.get_state() if save_state else None, e.launches, ndiv)
         except Exception as ex:  # re-raised on the caller's thread
             errors[i] = ex
+            if uid is not None and not ok[i]:
+                try:
+                    gate.wait(timeout=600)
+                except threading.BrokenBarrierError:
+                    pass
 
     if ndev == 1:
         work(0)
