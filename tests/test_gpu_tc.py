@@ -20,7 +20,7 @@ import pytest
 
 import turing_jl_b200 as T
 
-from helpers import oracle_of
+from helpers import oracle_of, small_models
 
 pytestmark = pytest.mark.gpu
 
@@ -163,4 +163,40 @@ def test_persistent_tail_kernel_is_bit_identical_to_the_host_pumped_path(built, 
     assert ka[5] > 0 and kb[5] == 0          # the persistent kernel really ran / really did not
     assert ga == gb
     assert np.array_equal(da, db, equal_nan=True)
+    assert np.array_equal(sa, sb)
+
+
+@pytest.mark.parametrize("family,C,tc,persist", [
+    ("logistic", 1300, 1, 1),     # host-pumped views 1300 -> 640 .. -> persistent views 512 -> 256 -> 128
+    ("logistic", 1300, 1, 0),     # every view host-pumped
+    ("logistic", 600, 0, 0),      # fp64 DMMA likelihood
+    ("hier", 520, 0, 0),          # a chain-local family on the pump
+])
+def test_progressive_compaction_is_bit_identical(built, family, C, tc, persist):
+    """lockstep.cu: as chains finish, the unfinished ones are gathered into narrower state arrays (column
+    k of a view = chain gid[k]).  Per-chain arithmetic does not depend on the column, the gather points
+    follow the refresh schedule -> identical draws, state blob and gradient count with option compact=0"""
+    if family == "logistic":
+        model = T.models.synthetic_logistic(3000, 33, seed=4)
+    else:
+        model = small_models()["hier_small"]
+    spl = T.NUTS(20, 0.8)
+    res = []
+    for compact in (1, 0):
+        e = T.Engine(model, spl, C, 20, seed=9, strategy=2)
+        if tc:
+            e.set_option("logistic_tc", 1)
+        e.set_option("persist", persist)
+        e.set_option("compact", compact)
+        e.set_option("keep_theta", 1)
+        e.init()
+        e.run(32, 1, 1)
+        out = e.fetch(theta=True)
+        res.append((e.fetch_draws(), out["theta"], e.get_state(), e.grad_evals, e.launches))
+        e.close()
+    (da, ta, sa, ga, la), (db, tb, sb, gb, lb) = res
+    assert ga == gb
+    assert la != lb                       # the gathers really ran
+    assert np.array_equal(da, db, equal_nan=True)
+    assert np.array_equal(ta, tb, equal_nan=True)
     assert np.array_equal(sa, sb)

@@ -74,6 +74,12 @@ struct DrawBuffers {
   int ncol;        // P + 3 + TNUTS_NSTAT
   double *draws;   // [keep][ncol][C]
   double *theta;   // [keep][D][C] or nullptr
+  // Compacted state (lockstep.cu, "progressive compaction"): the kernel works on a narrower copy of
+  // the per-chain arrays that holds only the unfinished chains; column k of that copy is chain gid[k]
+  // of the engine (its Philox address and its column of the draw arrays, which stay Cout wide).
+  // gid == nullptr: the state arrays are the engine's own, column = chain.
+  const int *gid = nullptr;
+  int Cout = 0;
 };
 
 struct RunParams {

@@ -613,6 +613,7 @@ int tnuts_set_option(tnuts_engine *h, const char *name, double value) {
   else if (n == "logistic_tc") e->logistic_tc = value != 0.0;
   else if (n == "time_kernels") e->time_kernels = value != 0.0;
   else if (n == "persist") e->persist = value != 0.0;
+  else if (n == "compact") e->compact = value != 0.0;
   else return set_error(e, TNUTS_E_ARG, "tnuts_set_option: unknown option " + n);
   return TNUTS_OK;
 }

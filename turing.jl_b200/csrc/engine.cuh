@@ -68,6 +68,9 @@ struct Engine {
   long long kernel_tile_launches = 0;  // sum over launches of 128-chain tiles (tcgen05 path)
   // the tail of a lock-step run as one persistent cooperative kernel (tc_persist.cuh); option "persist"
   bool persist = true;
+  // lock-step runs gather the unfinished chains into narrower arrays as the others finish (lockstep.cu);
+  // option "compact"
+  bool compact = true;
   double persist_seconds = 0.0;     // CUDA-event time of the persistent launches of the last run
   long long persist_pumps = 0;      // pumps (leapfrogs of every unfinished chain) they executed
 

@@ -24,9 +24,9 @@ namespace tnuts {
 int comm_allreduce_sum(Engine *e, double *buf, size_t n);  // comm.cu (no-op when world == 1)
 namespace tc { struct Data; }
 // persist.cu: the tail of a run as one persistent cooperative kernel (tc_persist.cuh)
-int tc_persist_run(Engine *e, const tc::Data &td, double *part, int stride, int *count_done_dev, int *h_done,
-                   long long pump0, long long max_pumps, int listed_done, int n_max, long long *pumps,
-                   int *n_done);
+int tc_persist_run(Engine *e, const tc::Data &td, const PersistView &pv, double *part, int stride,
+                   int *count_done_dev, int *h_done, long long pump0, long long max_pumps, int listed_done, int n_max,
+                   long long *pumps, int *n_done, int *reason, int *sched_done);
 
 template <class T>
 static int ls_alloc(Engine *e, std::vector<void *> *pool, T **p, size_t n) {
@@ -327,7 +327,7 @@ int lockstep_create(Engine *e) {
   A(ls->list, C); A(ls->count, 2);
   A(ls->fs_eps, C); A(ls->fs_epsp, C); A(ls->fs_H, C); A(ls->fs_dir, C); A(ls->fs_phase, C);
   A(ls->fs_iter, C); A(ls->r0, DC);
-  TN_CUDA(e, cudaMallocHost((void **)&ls->h_count, 2 * sizeof(int)));
+  TN_CUDA(e, cudaMallocHost((void **)&ls->h_count, 4 * sizeof(int)));
   if ((rc = gradwork_alloc(e, &x->gw, (int)C, &x->allocs))) return rc;
   // hierarchical model: centred sufficient statistics per group, computed once on the host
   if (e->model.family == TNUTS_HIER_LINREG) {
@@ -684,19 +684,208 @@ static int lockstep_run_sg(Engine *e) {
   return TNUTS_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Progressive compaction.  Chains finish a run at very different pump counts (config 3: the median
+// chain needs 27 000 leapfrogs, the slowest 1 % need 90 000 - 200 000), so most pumps serve a small
+// and shrinking subset of the chains -- scattered over [rows][C] arrays in which every touched 8-byte
+// element then sits in a cache line of its own (4400 lines = 560 KB per chain: 128 unfinished chains
+// alone use up L2 next to the X planes, and the state machine runs at DRAM latency).  Whenever the
+// unfinished chains fit half of the current width, they are gathered into arrays of that width
+// ("view"), all kernels of the pump work on the view, and column k of the view is chain gid[k] of
+// the engine for the two things that name a chain globally: its Philox address and its column of the
+// draw arrays (DrawBuffers::gid).  Chains are scattered back before the next gather and at the end of
+// the run.  Per-chain arithmetic does not depend on the column a chain lives in, and the compaction
+// points are a function of the (deterministic) refresh schedule, so results are bit-identical with
+// and without it (option "compact", tests/test_gpu_sampling.py).
+// ------------------------------------------------------------------------------------------
+struct ColArray {
+  char *home, *view;
+  int rows, esz;
+};
+
+template <class F>
+static void for_each_chain_array(ChainState &st, LockstepState &ls, F &&f) {
+  const int D = st.D;
+#define COL(p, rows) f(reinterpret_cast<void **>(&(p)), (int)(rows), (int)sizeof(*(p)))
+  COL(st.theta, D); COL(st.grad, D); COL(st.lp, 1); COL(st.minv, D); COL(st.eps, 1);
+  COL(st.da_mu, 1); COL(st.da_xbar, 1); COL(st.da_hbar, 1); COL(st.da_eps, 1); COL(st.da_m, 1);
+  COL(st.wf_n, 1); COL(st.wf_mean, D); COL(st.wf_m2, D); COL(st.iter, 1); COL(st.n_grad, 1);
+  COL(st.init_tries, 1); COL(st.status, 1);
+  COL(ls.zt, D); COL(ls.zr, D); COL(ls.zg, D); COL(ls.edge[0], 3 * D); COL(ls.edge[1], 3 * D);
+  COL(ls.rho, D); COL(ls.rho_s, D); COL(ls.thC, D); COL(ls.gC, D); COL(ls.thS, D); COL(ls.gS, D);
+  COL(ls.ck_r, ls.levels * D); COL(ls.ck_rho, ls.levels * D);
+  TreeScalars &s = ls.ts;
+  COL(s.H0, 1); COL(s.sum_a, 1); COL(s.dHmax, 1); COL(s.lw, 1); COL(s.lw_s, 1); COL(s.lpC, 1); COL(s.HC, 1);
+  COL(s.lpS, 1); COL(s.HS, 1); COL(s.zlp, 1); COL(s.zH, 1); COL(s.elp, 2); COL(s.n_a, 1);
+  COL(s.depth, 1); COL(s.active, 1); COL(s.sub_active, 1); COL(s.term_s, 1); COL(s.numerr, 1); COL(s.v, 1);
+  COL(s.n, 1); COL(s.phase, 1); COL(s.iter0, 1); COL(s.iter_end, 1);
+#undef COL
+}
+
+// to_view: view[r][k] = home[r][gid[k]] for k < n; else the other way round
+__global__ void k_cols_move(const ColArray *tab, const int *__restrict__ gid, int n, int Chome, int Cview,
+                            int to_view) {
+  const ColArray a = tab[blockIdx.y];
+  const long long tot = (long long)a.rows * n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / n;
+    const int k = (int)(i - r * n);
+    const size_t oh = (size_t)r * Chome + gid[k], ov = (size_t)r * Cview + k;
+    if (a.esz == 8) {
+      double *h = reinterpret_cast<double *>(a.home), *v = reinterpret_cast<double *>(a.view);
+      if (to_view) v[ov] = h[oh];
+      else h[oh] = v[ov];
+    } else {
+      int *h = reinterpret_cast<int *>(a.home), *v = reinterpret_cast<int *>(a.view);
+      if (to_view) v[ov] = h[oh];
+      else h[oh] = v[ov];
+    }
+  }
+}
+
+// columns [n, Cview) of a view hold no chain: finished, not ok; the work list is the identity
+__global__ void k_view_finish(int *phase, int *status, int *list, int n, int Cview) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Cview) return;
+  if (k >= n) {
+    phase[k] = 2;
+    status[k] = 1;
+  }
+  list[k] = k < n ? k : 0;
+}
+
+struct Compactor {
+  Engine *e = nullptr;
+  ChainState st;          // current view (== the engine's arrays while cap == C)
+  LockstepState ls;
+  DrawBuffers out;
+  int cap = 0, n_cols = 0;     // width of the view, columns that hold a chain
+  bool compacted = false;
+  char *pool = nullptr;
+  size_t pool_bytes = 0;
+  ColArray *tab_dev = nullptr;
+  int *gid[2] = {nullptr, nullptr};
+  int cur = 0, n_tab = 0, max_rows = 1;
+
+  void begin(Engine *e_) {
+    e = e_;
+    st = e->st;
+    ls = *e->ls;
+    out = e->out;
+    cap = e->st.C;
+    n_cols = cap;
+  }
+  static int want_cap(int n) { return std::max(128, ((n + 127) / 128) * 128); }
+  // the largest number of unfinished chains at which a view of width cap_ is worth narrowing
+  static int narrow_below(int cap_) { return cap_ >= 256 ? 128 * (cap_ / 256) : 0; }
+
+  int scatter_back() {
+    if (!compacted) return TNUTS_OK;
+    const dim3 g((unsigned)std::min<long long>(4096, ((long long)max_rows * n_cols + 255) / 256), n_tab);
+    if (n_cols > 0) k_cols_move<<<g, 256, 0, e->stream>>>(tab_dev, gid[cur], n_cols, e->st.C, cap, 0);
+    e->launches += 1;
+    TN_CUDA(e, cudaGetLastError());
+    return TNUTS_OK;
+  }
+
+  // gather the unfinished chains (n_max is the schedule's bound on their number) into a view of
+  // width want_cap(n_max); on return the view's work list is the identity and ls->count[0] = n
+  int compact(int n_max) {
+    LockstepState *home = e->ls;
+    const int C = e->st.C, D = e->st.D;
+    const int ncap = want_cap(n_max);
+    int rc;
+    if ((rc = scatter_back())) return rc;
+    if (!pool) {
+      // sized once, for the first (widest) view
+      size_t bytes = 0;
+      n_tab = 0;
+      ChainState s0 = e->st;
+      LockstepState l0 = *home;
+      for_each_chain_array(s0, l0, [&](void **p, int rows, int esz) {
+        if (!*p) return;
+        bytes += (((size_t)rows * ncap * esz + 255) / 256) * 256;
+        max_rows = std::max(max_rows, rows);
+        ++n_tab;
+      });
+      pool_bytes = bytes + (((size_t)ncap * 4 + 255) / 256) * 256;   // + the view's work list
+      TN_CUDA(e, cudaMallocAsync((void **)&pool, pool_bytes, e->stream));
+      TN_CUDA(e, cudaMallocAsync((void **)&tab_dev, sizeof(ColArray) * n_tab, e->stream));
+      TN_CUDA(e, cudaMallocAsync((void **)&gid[0], sizeof(int) * C, e->stream));
+      TN_CUDA(e, cudaMallocAsync((void **)&gid[1], sizeof(int) * C, e->stream));
+    }
+    // the unfinished chains of the engine, in chain order -> the new gid
+    const int nxt = compacted ? 1 - cur : 0;
+    k_ls_running_flags<<<(C + 255) / 256, 256, 0, e->stream>>>(*home, C, home->ts.sub_active);
+    k_ls_compact<<<1, 1024, 0, e->stream>>>(home->ts.sub_active, C, gid[nxt], home->count);
+    e->launches += 2;
+    TN_CUDA(e, cudaMemcpyAsync(home->h_count + 2, home->count, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    TN_CUDA(e, cudaStreamSynchronize(e->stream));
+    const int n = home->h_count[2];
+    if (n > ncap) return set_error(e, TNUTS_E_CUDA, "compaction: more unfinished chains than the schedule's bound");
+    // lay the view out in the pool and build the move table
+    std::vector<ColArray> tab;
+    tab.reserve(n_tab);
+    st = e->st;
+    ls = *home;
+    size_t off = 0;
+    for_each_chain_array(st, ls, [&](void **p, int rows, int esz) {
+      if (!*p) return;
+      ColArray a{reinterpret_cast<char *>(*p), pool + off, rows, esz};
+      off += (((size_t)rows * ncap * esz + 255) / 256) * 256;
+      *p = a.view;
+      tab.push_back(a);
+    });
+    ls.list = reinterpret_cast<int *>(pool + off);
+    st.C = ncap;
+    ls.C = ncap;
+    (void)D;
+    TN_CUDA(e, cudaMemcpyAsync(tab_dev, tab.data(), sizeof(ColArray) * tab.size(), cudaMemcpyHostToDevice, e->stream));
+    TN_CUDA(e, cudaStreamSynchronize(e->stream));   // `tab` is a stack object
+    if (n > 0) {
+      const dim3 g((unsigned)std::min<long long>(4096, ((long long)max_rows * n + 255) / 256), n_tab);
+      k_cols_move<<<g, 256, 0, e->stream>>>(tab_dev, gid[nxt], n, C, ncap, 1);
+    }
+    k_view_finish<<<(ncap + 255) / 256, 256, 0, e->stream>>>(ls.ts.phase, st.status, ls.list, n, ncap);
+    e->launches += 2;
+    TN_CUDA(e, cudaGetLastError());
+    out = e->out;
+    out.gid = gid[nxt];
+    out.Cout = C;
+    cur = nxt;
+    cap = ncap;
+    n_cols = n;
+    compacted = true;
+    return TNUTS_OK;
+  }
+
+  // end of the run (also on the error paths): chains back home, pool released
+  int finish() {
+    int rc = scatter_back();
+    compacted = false;
+    if (pool) cudaFreeAsync(pool, e->stream);
+    if (tab_dev) cudaFreeAsync(tab_dev, e->stream);
+    for (int i = 0; i < 2; ++i)
+      if (gid[i]) cudaFreeAsync(gid[i], e->stream);
+    pool = nullptr;
+    tab_dev = nullptr;
+    gid[0] = gid[1] = nullptr;
+    return rc;
+  }
+};
+
 int lockstep_run(Engine *e) {
   if (e->cfg.algorithm == TNUTS_ALG_SGHMC || e->cfg.algorithm == TNUTS_ALG_SGLD) return lockstep_run_sg(e);
   LockstepState *ls = e->ls;
-  ChainState &st = e->st;
   const RunParams &rp = e->rp;
-  const int C = st.C;
-  const int T = tiles(C);
+  const int C = e->st.C;
   int rc;
   volatile int *h_done = ls->h_count;
   TN_CUDA(e, cudaStreamSynchronize(e->stream));  // no pump of an earlier run may still write the mirror
   *h_done = 0;
   TN_CUDA(e, cudaMemsetAsync(ls->count + 1, 0, sizeof(int), e->stream));
-  k_ls_begin_run<<<(C + 255) / 256, 256, 0, e->stream>>>(st, *ls, rp.n_transitions, ls->count + 1);
+  k_ls_begin_run<<<(C + 255) / 256, 256, 0, e->stream>>>(e->st, *ls, rp.n_transitions, ls->count + 1);
   e->launches += 1;
   cudaEvent_t ev[2];
   TN_CUDA(e, cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
@@ -724,9 +913,12 @@ int lockstep_run(Engine *e) {
   if (e->time_kernels) timer_of(e)->begin_run();
   static const bool trace = getenv("TNUTS_PUMP_TRACE") != nullptr;
   long long pumps_done = 0;
+  Compactor cp;   // the state the pump works on: the engine's arrays, later narrower copies of them
+  cp.begin(e);
   for (long long pump = 0; pump < max_pumps; ++pump) {
     pumps_done = pump;
-    if (trace && pump % 4096 == 0) fprintf(stderr, "[tnuts pump] %lld done=%d listed=%d\n", pump, (int)*h_done, n_max);
+    if (trace && pump % 4096 == 0)
+      fprintf(stderr, "[tnuts pump] %lld done=%d listed=%d width=%d\n", pump, (int)*h_done, n_max, cp.cap);
     if (!lockstep_ranks) {
       done = *h_done;
     } else if (pump % 16 == 0 && pump > 0) {
@@ -747,14 +939,20 @@ int lockstep_run(Engine *e) {
     }
     if (done >= C) break;
     if (done != listed_done && (pump % 8 == 0)) {  // refresh the gradient work list
-      k_ls_running_flags<<<(C + 255) / 256, 256, 0, e->stream>>>(*ls, C, ls->ts.sub_active);
-      k_ls_compact<<<1, 1024, 0, e->stream>>>(ls->ts.sub_active, C, ls->list, ls->count);
-      e->launches += 2;
       listed_done = done;
       n_max = C - done;
+      if (e->compact && n_max <= Compactor::narrow_below(cp.cap)) {
+        if ((rc = cp.compact(n_max))) break;       // leaves the identity list of the narrower view
+        if (trace) fprintf(stderr, "[tnuts pump] %lld: %d unfinished chains gathered into a view of width %d\n", pump, cp.n_cols, cp.cap);
+      } else {
+        k_ls_running_flags<<<(cp.cap + 255) / 256, 256, 0, e->stream>>>(cp.ls, cp.cap, cp.ls.ts.sub_active);
+        k_ls_compact<<<1, 1024, 0, e->stream>>>(cp.ls.ts.sub_active, cp.cap, cp.ls.list, ls->count);
+        e->launches += 2;
+      }
       if (persist_ok && n_max <= tc::kPersistMaxTiles * tc::kChainsPerCta) {
         // The listed chains fit one wave of (chain tile, row chunk) CTAs: the rest of the run is ONE
-        // persistent cooperative kernel (tc_persist.cuh), same arithmetic and same refresh schedule.
+        // persistent cooperative kernel (tc_persist.cuh), same arithmetic and same refresh schedule;
+        // it only comes back to have its chains gathered into a narrower view.
         tc::Data *td = tc_data_of(e);
         if (!td->ready) {
           const char *msg = tc::prepare(e->model.X, e->model.y, e->model.N, e->model.D, e->stream, td);
@@ -769,30 +967,47 @@ int lockstep_run(Engine *e) {
         if (e->time_kernels) {
           cudaEventCreate(&pe0);
           cudaEventCreate(&pe1);
-          cudaEventRecord(pe0, e->stream);
         }
-        long long ran = 0;
-        int nd = 0;
-        rc = tc_persist_run(e, *td, gw->part, gw->stride, ls->count + 1, ls->h_count, pump, max_pumps, listed_done,
-                            n_max, &ran, &nd);
+        long long p0 = pump;
+        for (;;) {
+          long long ran = 0;
+          int nd = 0, reason = 0, sched_done = 0;
+          const PersistView pv{&cp.st, &cp.ls, &cp.out, C, e->compact ? Compactor::narrow_below(cp.cap) : 0};
+          if (e->time_kernels) cudaEventRecord(pe0, e->stream);
+          rc = tc_persist_run(e, *td, pv, gw->part, gw->stride, ls->count + 1, ls->h_count, p0, max_pumps, listed_done,
+                              n_max, &ran, &nd, &reason, &sched_done);
+          if (e->time_kernels) {
+            float ms = 0.f;
+            if (!rc && cudaEventRecord(pe1, e->stream) == cudaSuccess && cudaEventSynchronize(pe1) == cudaSuccess &&
+                cudaEventElapsedTime(&ms, pe0, pe1) == cudaSuccess)
+              e->persist_seconds += ms * 1e-3;
+          }
+          e->persist_pumps += ran;
+          p0 += ran;
+          pumps_done = p0;
+          if (trace)
+            fprintf(stderr, "[tnuts pump] persistent kernel, width %d: %lld pumps up to pump %lld, done=%d\n", cp.cap, ran,
+                    p0, nd);
+          if (rc || reason != 3) break;
+          // at a list refresh with few enough chains left for a narrower view
+          listed_done = sched_done;
+          n_max = C - sched_done;
+          if ((rc = cp.compact(n_max))) break;
+        }
         if (e->time_kernels) {
-          float ms = 0.f;
-          if (!rc && cudaEventRecord(pe1, e->stream) == cudaSuccess && cudaEventSynchronize(pe1) == cudaSuccess &&
-              cudaEventElapsedTime(&ms, pe0, pe1) == cudaSuccess)
-            e->persist_seconds += ms * 1e-3;
           cudaEventDestroy(pe0);
           cudaEventDestroy(pe1);
         }
-        e->persist_pumps += ran;
-        pumps_done = pump + ran;
-        if (trace) fprintf(stderr, "[tnuts pump] persistent kernel from pump %lld: %lld pumps, done=%d\n", pump, ran, nd);
         break;   // the completion check below reports chains the pump budget left unfinished
       }
     }
     if (pump > 0) {  // on the first pump no leaf is pending yet
-      if ((rc = grad_launch(e, ls->zt, C, ls->ts.zlp, ls->zg, ls->list, ls->count, C, n_max, gw_of(e)))) break;
+      if ((rc = grad_launch(e, cp.ls.zt, cp.cap, cp.ls.ts.zlp, cp.ls.zg, cp.ls.list, ls->count, cp.cap, n_max,
+                            gw_of(e))))
+        break;
     }
-    k_ls_pump<<<T, kTileThreads, 0, e->stream>>>(st, *ls, rp, e->model, e->out, ls->count + 1, ls->h_count);
+    k_ls_pump<<<tiles(cp.cap), kTileThreads, 0, e->stream>>>(cp.st, cp.ls, rp, e->model, cp.out, ls->count + 1,
+                                                             ls->h_count);
     e->launches += 1;
     if (!lockstep_ranks && pump % 64 == 63) {
       const int slot = (int)((pump / 64) & 1);
@@ -804,6 +1019,10 @@ int lockstep_run(Engine *e) {
   cudaEventDestroy(ev[1]);
   cudaEventDestroy(ev_cnt);
   if (trace) fprintf(stderr, "[tnuts pump] finished after %lld pumps\n", pumps_done);
+  {
+    const int rc2 = cp.finish();   // chains back into the engine's arrays
+    if (!rc) rc = rc2;
+  }
   if (rc) return rc;
   TN_CUDA(e, cudaGetLastError());
   // The loop is bounded (max_pumps): make sure every chain really finished, otherwise the rows of

@@ -55,4 +55,14 @@ struct LockstepState {
   double *r0 = nullptr;  // [D][C] momentum of the search
 };
 
+// the state the persistent pump kernel works on (persist.cu): the engine's own arrays or a compacted
+// copy of them (lockstep.cu, progressive compaction)
+struct PersistView {
+  const ChainState *st;
+  const LockstepState *ls;
+  const DrawBuffers *out;
+  int c_total;             // chains of the engine (the finished-chain counter runs up to this)
+  int exit_below;          // return for a re-compaction once the unfinished chains drop to this many (0: never)
+};
+
 }  // namespace tnuts

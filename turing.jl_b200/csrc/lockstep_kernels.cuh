@@ -355,8 +355,19 @@ k_sg_step(ChainState st, RunParams rp, ModelDev m, DrawBuffers out, long long k_
 template <class TM>
 __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, LockstepState ls, RunParams rp,
                                              ModelDev m, DrawBuffers out, int *n_done, double *red,
-                                             int *s_maxlev_p) {
+                                             int *s_maxlev_p, long long *tprof = nullptr) {
   int &s_maxlev = *s_maxlev_p;
+  // profiling aid of the persistent kernel's trace (tprof != nullptr for one warp only): ns per section
+  long long tp_mark = 0;
+  auto tp_lap = [&](int i) {
+    if (tprof && TM::tid() == 0) {
+      unsigned long long tnow;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tnow)::"memory");
+      if (i >= 0) tprof[i] += (long long)tnow - tp_mark;
+      tp_mark = (long long)tnow;
+    }
+  };
+  tp_lap(-1);
   const int C = st.C, D = st.D;
   TreeScalars &s = ls.ts;
   const size_t DC = (size_t)D * C;
@@ -389,7 +400,10 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
       }
     }
   }
-  const uint32_t gchain = (uint32_t)(rp.chain_offset + t.c);
+  // engine-wide chain index: Philox address and column of the draw arrays (compacted state: gid)
+  const int gcol = (out.gid && t.c < C) ? out.gid[t.c] : t.c;
+  const int Cout = out.gid ? out.Cout : C;
+  const uint32_t gchain = (uint32_t)(rp.chain_offset + gcol);
   // chain scalars (registers, redundantly in the chain's 32 threads)
   double eps = 0, H0 = 0, lw = 0, lw_s = 0, sum_a = 0, dHmax = 0, lpC = 0, HC = 0, lpS = 0, HS = 0,
          zlp = 0, elp0 = 0, elp1 = 0;
@@ -405,6 +419,7 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
     elp0 = s.elp[t.c]; elp1 = s.elp[C + t.c]; n_a = s.n_a[t.c];
     v = s.v[t.c]; j = s.depth[t.c]; n = s.n[t.c]; numerr = s.numerr[t.c];
   }
+  tp_lap(0);   // chain scalars
   const bool leaf = phase == 1;
   bool start_transition = phase == 0;
   uint32_t it = (uint32_t)(iter + 1);
@@ -424,6 +439,7 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
     }
   }
   tile_reduce<2, TM>(a1, red);
+  tp_lap(1);   // [A] second half kick + kinetic energy
   const bool hmc = rp.algorithm != TNUTS_ALG_NUTS;
   bool accept = false, divergent = false, term_s = false, sub_done = false;
   bool trans_end = false;
@@ -482,6 +498,7 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
       term_s = true;
     }
   }
+  tp_lap(2);   // leaf weights
   // checkpoints / sub-tree U-turn partial dot products (leaf index n is per chain)
   const int idx_max = __popc((unsigned)n >> 1);
   const bool odd = (n & 1) != 0;
@@ -534,6 +551,7 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
     if (!sub_done) n += 1;
   }
 
+  tp_lap(3);   // checkpoints + sub-tree U-turns
   // ================= [B] end of a doubling =================
   if (TM::sync_or(leaf && sub_done)) {
     const bool me = leaf && sub_done;
@@ -598,6 +616,7 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
     }
   }
 
+  tp_lap(4);   // [B]
   // ================= [T] end of a transition =================
   if (TM::sync_or(trans_end)) {
     long long k_slot = -1;
@@ -653,19 +672,19 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
       double prior, lik;
       ls_user_logp<TM>(m, thC_, C, t, rec, rec ? lpC : 0.0, red, prior, lik);
       if (rec) {
-        double *row = out.draws + (size_t)k_slot * out.ncol * C + t.c;
+        double *row = out.draws + (size_t)k_slot * out.ncol * Cout + gcol;
     #pragma unroll 4
     for (int d = t.dl; d < D; d += kTileD) {
           const double th = thC_[(size_t)d * C + t.c];
-          row[(size_t)d * C] = ls_is_positive(m, d) ? exp(th) : th;
-          if (out.theta) out.theta[((size_t)k_slot * D + d) * C + t.c] = th;
+          row[(size_t)d * Cout] = ls_is_positive(m, d) ? exp(th) : th;
+          if (out.theta) out.theta[((size_t)k_slot * D + d) * Cout + gcol] = th;
         }
         if (t.dl == 0) {
-          row[(size_t)(D + 0) * C] = prior;
-          row[(size_t)(D + 1) * C] = lik;
-          row[(size_t)(D + 2) * C] = prior + lik;
+          row[(size_t)(D + 0) * Cout] = prior;
+          row[(size_t)(D + 1) * Cout] = lik;
+          row[(size_t)(D + 2) * Cout] = prior + lik;
 #pragma unroll
-          for (int q = 0; q < TNUTS_NSTAT; ++q) row[(size_t)(D + 3 + q) * C] = stats[q];
+          for (int q = 0; q < TNUTS_NSTAT; ++q) row[(size_t)(D + 3 + q) * Cout] = stats[q];
         }
       }
     }
@@ -784,6 +803,7 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
     }
   }
 
+  tp_lap(5);   // [T] + [S]
   // ================= [D] first half kick + drift of the next leaf =================
   if (phase == 1) {
     se = v ? eps : -eps;
@@ -806,6 +826,7 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
     }
     if (leaf) st.n_grad[t.c] += 1;
   }
+  tp_lap(6);   // [D] + scalars out
 }
 
 static __global__ void __launch_bounds__(kTileThreads)
