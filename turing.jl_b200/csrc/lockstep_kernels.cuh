@@ -21,6 +21,29 @@ __device__ __forceinline__ double ls_logaddexp(double a, double b) {
   return mx + log1p(exp(-fabs(a - b)));
 }
 
+// Memory-level parallelism of the state machine's passes over d.  Every pass reads a few [D][C]
+// arrays at this lane's dimensions d = dl, dl + 32, ... and writes some of them back.  Written as one
+// loop ("load, compute, store" per d) the compiler keeps a store between the loads of consecutive
+// iterations (same array, addresses it cannot tell apart) and sinks every load next to its use: a pass
+// became 8 - 12 dependent L2 round trips, and the whole pump was bound by that latency (k_ls_pump
+// 0.11 ms for 50 MB of traffic; 20 - 40 us per leapfrog of a single chain in the persistent kernel).
+// The passes therefore load a batch of kNB dimensions of all their arrays first (index clamped to
+// D - 1 for the lanes past the end, whose results are masked), gate the first use on the last loads
+// having arrived (ls_gate), and only then compute and store.  Same operations per element in the same
+// order: results are unchanged.
+constexpr int kNB = 4;
+// x, once `last` (the value of a batch's last load) has arrived; the bit pattern compared with is a
+// signalling NaN that no computation produces
+__device__ __forceinline__ double ls_gate(double x, double last) {
+  return __double_as_longlong(last) == 0x7ff4dead0000beefLL ? last : x;
+}
+#define LS_BATCH_OFFSETS(o, d0)                                                                    \
+  size_t o[kNB];                                                                                   \
+  _Pragma("unroll") for (int i_ = 0; i_ < kNB; ++i_) o[i_] = (size_t)min((d0) + i_ * kTileD, D - 1) * C + t.c
+#define LS_BATCH_LOAD(dst, src, o)                                                                 \
+  double dst[kNB];                                                                                 \
+  _Pragma("unroll") for (int i_ = 0; i_ < kNB; ++i_) dst[i_] = (src)[o[i_]]
+
 // A "team" is the 256 threads that own one tile of 8 chains.  In the stand-alone kernels it is the
 // whole CTA; inside the persistent pump kernel (tc_persist.cuh) it is 8 warps of a larger CTA that
 // synchronise on a named barrier.  tid() is the thread's index inside its team.
@@ -428,14 +451,21 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
   double se = v ? eps : -eps, half = 0.5 * se;
   double a1[2] = {0.0, 0.0};
   if (leaf) {
-#pragma unroll 4
-    for (int d = t.dl; d < D; d += kTileD) {
-      const size_t o = (size_t)d * C + t.c;
-      const double g = zg_[o];
-      const double r = zr_[o] + half * g;
-      zr_[o] = r;
-      a1[0] += minv_[o] * r * r;
-      a1[1] += isfinite(g) ? 0.0 : 1.0;
+    for (int d0 = t.dl; d0 < D; d0 += kNB * kTileD) {
+      LS_BATCH_OFFSETS(o, d0);
+      LS_BATCH_LOAD(g4, zg_, o);
+      LS_BATCH_LOAD(r4, zr_, o);
+      LS_BATCH_LOAD(m4, minv_, o);
+      g4[0] = ls_gate(ls_gate(ls_gate(g4[0], g4[kNB - 1]), r4[kNB - 1]), m4[kNB - 1]);
+#pragma unroll
+      for (int i = 0; i < kNB; ++i)
+        if (d0 + i * kTileD < D) {
+          const double g = g4[i];
+          const double r = r4[i] + half * g;
+          zr_[o[i]] = r;
+          a1[0] += m4[i] * r * r;
+          a1[1] += isfinite(g) ? 0.0 : 1.0;
+        }
     }
   }
   tile_reduce<2, TM>(a1, red);
@@ -460,11 +490,16 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
       dHmax = dH;
       numerr = ok ? 0 : 1;
       if (accept) {
-#pragma unroll 4
-        for (int d = t.dl; d < D; d += kTileD) {
-          const size_t o = (size_t)d * C + t.c;
-          thC_[o] = zt_[o];
-          gC_[o] = zg_[o];
+        for (int d0 = t.dl; d0 < D; d0 += kNB * kTileD) {
+          LS_BATCH_OFFSETS(o, d0);
+          LS_BATCH_LOAD(t4, zt_, o);
+          LS_BATCH_LOAD(g4, zg_, o);
+#pragma unroll
+          for (int i = 0; i < kNB; ++i)
+            if (d0 + i * kTileD < D) {
+              thC_[o[i]] = t4[i];
+              gC_[o[i]] = g4[i];
+            }
         }
         lpC = zlp;
         HC = zH;
@@ -514,29 +549,57 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
 #pragma unroll
   for (int q = 0; q < 2 * kMaxLevels; ++q) dots[q] = 0.0;
   if (leaf && !hmc) {
-#pragma unroll 4
-    for (int d = t.dl; d < D; d += kTileD) {
-      const size_t o = (size_t)d * C + t.c;
-      const double r = zr_[o];
-      const double rs = rhos_[o] + r;
-      rhos_[o] = rs;
+    const bool ck_store = !divergent && !odd, ck_dots = !divergent && odd;
+    for (int d0 = t.dl; d0 < D; d0 += kNB * kTileD) {
+      LS_BATCH_OFFSETS(o, d0);
+      LS_BATCH_LOAD(r4, zr_, o);
+      LS_BATCH_LOAD(rs4, rhos_, o);
+      double t4[kNB], g4[kNB], m4[kNB];
       if (accept) {
-        thS_[o] = zt_[o];
-        gS_[o] = zg_[o];
+#pragma unroll
+        for (int i = 0; i < kNB; ++i) {
+          t4[i] = zt_[o[i]];
+          g4[i] = zg_[o[i]];
+        }
       }
-      if (!divergent) {
-        if (!odd) {
-          ckr_[idx_max * DC + o] = r;
-          ckrho_[idx_max * DC + o] = rs;
-        } else {
-          const double mi = minv_[o];
-          for (int q = 0; q < nlev; ++q) {
-            const int i = idx_max - q;
-            const double cr = ckr_[i * DC + o];
-            const double sr = rs - ckrho_[i * DC + o] + cr;
-            dots[2 * q] += sr * (mi * cr);
-            dots[2 * q + 1] += sr * (mi * r);
+      if (ck_dots) {
+#pragma unroll
+        for (int i = 0; i < kNB; ++i) m4[i] = minv_[o[i]];
+      }
+      r4[0] = ls_gate(ls_gate(r4[0], r4[kNB - 1]), rs4[kNB - 1]);
+#pragma unroll
+      for (int i = 0; i < kNB; ++i) {
+        rs4[i] = rs4[i] + r4[i];
+        if (d0 + i * kTileD < D) {
+          rhos_[o[i]] = rs4[i];
+          if (accept) {
+            thS_[o[i]] = t4[i];
+            gS_[o[i]] = g4[i];
           }
+          if (ck_store) {
+            ckr_[idx_max * DC + o[i]] = r4[i];
+            ckrho_[idx_max * DC + o[i]] = rs4[i];
+          }
+        }
+      }
+      if (ck_dots) {
+        for (int q = 0; q < nlev; ++q) {
+          const size_t lv = (size_t)(idx_max - q) * DC;
+          double cr4[kNB], ch4[kNB];
+#pragma unroll
+          for (int i = 0; i < kNB; ++i) {
+            cr4[i] = ckr_[lv + o[i]];
+            ch4[i] = ckrho_[lv + o[i]];
+          }
+          cr4[0] = ls_gate(ls_gate(cr4[0], cr4[kNB - 1]), ch4[kNB - 1]);
+#pragma unroll
+          for (int i = 0; i < kNB; ++i)
+            if (d0 + i * kTileD < D) {
+              const double cr = cr4[i];
+              const double sr = rs4[i] - ch4[i] + cr;
+              dots[2 * q] += sr * (m4[i] * cr);
+              dots[2 * q + 1] += sr * (m4[i] * r4[i]);
+            }
         }
       }
     }
@@ -565,22 +628,42 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
     if (me) {
       double *e = ls.edge[v];
       const double *eo = ls.edge[1 - v];
-  #pragma unroll 4
-    for (int d = t.dl; d < D; d += kTileD) {
-        const size_t o = (size_t)d * C + t.c;
-        const double r = zr_[o];
-        e[o] = zt_[o];
-        e[DC + o] = r;
-        e[2 * DC + o] = zg_[o];
+      for (int d0 = t.dl; d0 < D; d0 += kNB * kTileD) {
+        LS_BATCH_OFFSETS(o, d0);
+        LS_BATCH_LOAD(r4, zr_, o);
+        LS_BATCH_LOAD(t4, zt_, o);
+        LS_BATCH_LOAD(g4, zg_, o);
+        LS_BATCH_LOAD(rh4, rho_, o);
+        LS_BATCH_LOAD(rs4, rhos_, o);
+        LS_BATCH_LOAD(m4, minv_, o);
+        double eo4[kNB], ts4[kNB], gs4[kNB];
+#pragma unroll
+        for (int i = 0; i < kNB; ++i) eo4[i] = eo[DC + o[i]];
         if (take) {
-          thC_[o] = thS_[o];
-          gC_[o] = gS_[o];
+#pragma unroll
+          for (int i = 0; i < kNB; ++i) {
+            ts4[i] = thS_[o[i]];
+            gs4[i] = gS_[o[i]];
+          }
         }
-        const double rho = rho_[o] + rhos_[o];
-        rho_[o] = rho;
-        const double mi = minv_[o];
-        d2[v] += rho * (mi * r);
-        d2[1 - v] += rho * (mi * eo[DC + o]);
+        r4[0] = ls_gate(ls_gate(ls_gate(r4[0], rh4[kNB - 1]), m4[kNB - 1]), eo4[kNB - 1]);
+#pragma unroll
+        for (int i = 0; i < kNB; ++i)
+          if (d0 + i * kTileD < D) {
+            const double r = r4[i];
+            e[o[i]] = t4[i];
+            e[DC + o[i]] = r;
+            e[2 * DC + o[i]] = g4[i];
+            if (take) {
+              thC_[o[i]] = ts4[i];
+              gC_[o[i]] = gs4[i];
+            }
+            const double rho = rh4[i] + rs4[i];
+            rho_[o[i]] = rho;
+            const double mi = m4[i];
+            d2[v] += rho * (mi * r);
+            d2[1 - v] += rho * (mi * eo4[i]);
+          }
       }
     }
     tile_reduce<2, TM>(d2, red);
@@ -599,13 +682,23 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
       if (cont) {  // next doubling
         v = (uniform1(rp.seed, gchain, it, SLOT_DIRECTION, (uint32_t)j) < 0.5) ? 0 : 1;
         const double *en = ls.edge[v];
-    #pragma unroll 4
-    for (int d = t.dl; d < D; d += kTileD) {
-          const size_t o = (size_t)d * C + t.c;
-          zt_[o] = en[o];
-          zr_[o] = en[DC + o];
-          zg_[o] = en[2 * DC + o];
-          rhos_[o] = 0.0;
+        for (int d0 = t.dl; d0 < D; d0 += kNB * kTileD) {
+          LS_BATCH_OFFSETS(o, d0);
+          double et4[kNB], er4[kNB], eg4[kNB];
+#pragma unroll
+          for (int i = 0; i < kNB; ++i) {
+            et4[i] = en[o[i]];
+            er4[i] = en[DC + o[i]];
+            eg4[i] = en[2 * DC + o[i]];
+          }
+#pragma unroll
+          for (int i = 0; i < kNB; ++i)
+            if (d0 + i * kTileD < D) {
+              zt_[o[i]] = et4[i];
+              zr_[o[i]] = er4[i];
+              zg_[o[i]] = eg4[i];
+              rhos_[o[i]] = 0.0;
+            }
         }
         zlp = v ? elp1 : elp0;
         lw_s = -CUDART_INF;
@@ -635,26 +728,39 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
         in_window = iter >= rp.window_start && iter <= rp.window_end;
       }
       const double nw = (double)(wf_n + 1);
-  #pragma unroll 4
-    for (int d = t.dl; d < D; d += kTileD) {
-        const size_t o = (size_t)d * C + t.c;
-        const double th = thC_[o];
-        theta_[o] = th;
-        grad_[o] = gC_[o];
+      for (int d0 = t.dl; d0 < D; d0 += kNB * kTileD) {
+        LS_BATCH_OFFSETS(o, d0);
+        LS_BATCH_LOAD(tc4, thC_, o);
+        LS_BATCH_LOAD(gc4, gC_, o);
+        double wm4[kNB], w24[kNB];
         if (in_window) {
-          double mean = st.wf_mean[o], m2 = st.wf_m2[o];
-          const double delta = th - mean;
-          mean += delta / nw;
-          m2 += delta * (th - mean);
-          if (wend) {
-            if (wf_n + 1 >= 10 && !rp.unit_metric)
-              minv_[o] = nw / ((nw + 5.0) * (nw - 1.0)) * m2 + 1e-3 * (5.0 / (nw + 5.0));
-            mean = 0.0;
-            m2 = 0.0;
+#pragma unroll
+          for (int i = 0; i < kNB; ++i) {
+            wm4[i] = st.wf_mean[o[i]];
+            w24[i] = st.wf_m2[o[i]];
           }
-          st.wf_mean[o] = mean;
-          st.wf_m2[o] = m2;
         }
+#pragma unroll
+        for (int i = 0; i < kNB; ++i)
+          if (d0 + i * kTileD < D) {
+            const double th = tc4[i];
+            theta_[o[i]] = th;
+            grad_[o[i]] = gc4[i];
+            if (in_window) {
+              double mean = wm4[i], m2 = w24[i];
+              const double delta = th - mean;
+              mean += delta / nw;
+              m2 += delta * (th - mean);
+              if (wend) {
+                if (wf_n + 1 >= 10 && !rp.unit_metric)
+                  minv_[o[i]] = nw / ((nw + 5.0) * (nw - 1.0)) * m2 + 1e-3 * (5.0 / (nw + 5.0));
+                mean = 0.0;
+                m2 = 0.0;
+              }
+              st.wf_mean[o[i]] = mean;
+              st.wf_m2[o[i]] = m2;
+            }
+          }
       }
       const double na = (double)n_a;
       stats[ST_NSTEPS] = na;
@@ -673,11 +779,18 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
       ls_user_logp<TM>(m, thC_, C, t, rec, rec ? lpC : 0.0, red, prior, lik);
       if (rec) {
         double *row = out.draws + (size_t)k_slot * out.ncol * Cout + gcol;
-    #pragma unroll 4
-    for (int d = t.dl; d < D; d += kTileD) {
-          const double th = thC_[(size_t)d * C + t.c];
-          row[(size_t)d * Cout] = ls_is_positive(m, d) ? exp(th) : th;
-          if (out.theta) out.theta[((size_t)k_slot * D + d) * Cout + gcol] = th;
+        for (int d0 = t.dl; d0 < D; d0 += kNB * kTileD) {
+          LS_BATCH_OFFSETS(o, d0);
+          LS_BATCH_LOAD(tc4, thC_, o);
+#pragma unroll
+          for (int i = 0; i < kNB; ++i) {
+            const int d = d0 + i * kTileD;
+            if (d < D) {
+              const double th = tc4[i];
+              row[(size_t)d * Cout] = ls_is_positive(m, d) ? exp(th) : th;
+              if (out.theta) out.theta[((size_t)k_slot * D + d) * Cout + gcol] = th;
+            }
+          }
         }
         if (t.dl == 0) {
           row[(size_t)(D + 0) * Cout] = prior;
@@ -748,29 +861,55 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
     if (start_transition) {
       lp0 = st.lp[t.c];
       if (trans_end) lp0 = lpC;  // just written by the dl == 0 thread of this chain
-  #pragma unroll 4
-    for (int d = t.dl; d < D; d += kTileD) {
-        const size_t o = (size_t)d * C + t.c;
-        double z0, z1;
-        normal2(rp.seed, gchain, it, SLOT_MOMENTUM, (uint32_t)(d >> 1), z0, z1);
-        const double mi = minv_[o];
-        const double r = ((d & 1) ? z1 : z0) / sqrt(mi);
-        const double th = theta_[o], g = grad_[o];
-        acc[0] += mi * r * r;
-        rho_[o] = r;
-        thC_[o] = th;
-        gC_[o] = g;
+    }
+    // One Philox / Box-Muller evaluation gives the normals of dimensions 2p and 2p + 1: the lane of
+    // the even dimension evaluates it and hands z1 to its neighbour (the d-lane next to it: 1 lane
+    // away in a one-warp team, 8 lanes away in a tile of 8 chains).  Every lane of the team runs the
+    // loop (the shuffles need whole warps); lanes whose chain does not start a transition only pass.
+    for (int b0 = 0; b0 < D; b0 += kNB * kTileD) {
+      const int d0 = b0 + t.dl;
+      LS_BATCH_OFFSETS(o, d0);
+      double m4[kNB], th4[kNB], g4[kNB], z4[kNB];
+      if (start_transition) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          double *e = ls.edge[q];
-          e[o] = th;
-          e[DC + o] = r;
-          e[2 * DC + o] = g;
+        for (int i = 0; i < kNB; ++i) {
+          m4[i] = minv_[o[i]];
+          th4[i] = theta_[o[i]];
+          g4[i] = grad_[o[i]];
         }
-        zt_[o] = th;
-        zr_[o] = r;
-        zg_[o] = g;
-        rhos_[o] = 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < kNB; ++i) {
+        const int d = d0 + i * kTileD;
+        double z0 = 0.0, z1 = 0.0;
+        if (start_transition && !(d & 1) && d < D)
+          normal2(rp.seed, gchain, it, SLOT_MOMENTUM, (uint32_t)(d >> 1), z0, z1);
+        const double zp = __shfl_xor_sync(0xffffffffu, z1, TM::kWarp ? 1 : kTileC);
+        z4[i] = (d & 1) ? zp : z0;
+      }
+      if (start_transition) {
+#pragma unroll
+        for (int i = 0; i < kNB; ++i)
+          if (d0 + i * kTileD < D) {
+            const double mi = m4[i];
+            const double r = z4[i] / sqrt(mi);
+            const double th = th4[i], g = g4[i];
+            acc[0] += mi * r * r;
+            rho_[o[i]] = r;
+            thC_[o[i]] = th;
+            gC_[o[i]] = g;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              double *e = ls.edge[q];
+              e[o[i]] = th;
+              e[DC + o[i]] = r;
+              e[2 * DC + o[i]] = g;
+            }
+            zt_[o[i]] = th;
+            zr_[o[i]] = r;
+            zg_[o[i]] = g;
+            rhos_[o[i]] = 0.0;
+          }
       }
     }
     tile_reduce<1, TM>(acc, red);
@@ -808,12 +947,20 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
   if (phase == 1) {
     se = v ? eps : -eps;
     half = 0.5 * se;
-#pragma unroll 4
-    for (int d = t.dl; d < D; d += kTileD) {
-      const size_t o = (size_t)d * C + t.c;
-      const double r = zr_[o] + half * zg_[o];
-      zr_[o] = r;
-      zt_[o] = zt_[o] + se * (minv_[o] * r);
+    for (int d0 = t.dl; d0 < D; d0 += kNB * kTileD) {
+      LS_BATCH_OFFSETS(o, d0);
+      LS_BATCH_LOAD(r4, zr_, o);
+      LS_BATCH_LOAD(g4, zg_, o);
+      LS_BATCH_LOAD(t4, zt_, o);
+      LS_BATCH_LOAD(m4, minv_, o);
+      r4[0] = ls_gate(ls_gate(ls_gate(r4[0], g4[kNB - 1]), t4[kNB - 1]), m4[kNB - 1]);
+#pragma unroll
+      for (int i = 0; i < kNB; ++i)
+        if (d0 + i * kTileD < D) {
+          const double r = r4[i] + half * g4[i];
+          zr_[o[i]] = r;
+          zt_[o[i]] = t4[i] + se * (m4[i] * r);
+        }
     }
   }
   if (in && t.dl == 0) {
@@ -829,7 +976,7 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
   tp_lap(6);   // [D] + scalars out
 }
 
-static __global__ void __launch_bounds__(kTileThreads)
+static __global__ void __launch_bounds__(kTileThreads, 2)
 k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers out, int *n_done,
           int *h_done /* mapped pinned host word */) {
   __shared__ double red[2 * 64];
