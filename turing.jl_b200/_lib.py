@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtnuts.so")
+# TNUTS_LIB: development knob, an alternative build of the same ABI (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("TNUTS_LIB") or os.path.join(_HERE, "libtnuts.so")
 
 NSTAT = 9
 STAT_NAMES = ("n_steps", "acceptance_rate", "log_density", "hamiltonian_energy",

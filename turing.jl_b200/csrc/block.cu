@@ -25,31 +25,13 @@ int block_run(Engine *e) {
     if (e->out.theta) TN_CUDA(e, cudaMalloc((void **)&tcm, 8 * (size_t)C * keep * D));
   }
   HierStatsDev hs{ls->hs_n, ls->hs_xbar, ls->hs_ybar, ls->hs_sxx, ls->hs_sxy, ls->hs_syy};
-  const int kd0 = (D + kBlockThreads - 1) / kBlockThreads;
-  const int kd = kd0 <= 1 ? 1 : kd0 <= 2 ? 2 : kd0 <= 4 ? 4 : 8;
-  const int Dp = kd * kBlockThreads;                    // scratch vectors: one slot per (thread, k)
-  const int Dps = ((D + 1 + 7) / 8) * 8;                // shared-memory vectors: D + a dummy slot for the padded lanes
-  // shared memory: theta + as many checkpoint levels as fit beside `occ` co-resident CTAs
-  static const int occ_env = [] { const char *v = getenv("TNUTS_BLOCK_OCC"); return v ? atoi(v) : 0; }();
-  const int occ = occ_env > 0 ? occ_env : (kd >= 8 ? 2 : 3);
-  int dev = 0, smem_sm = 0, smem_blk = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-  cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  const size_t red_bytes = sizeof(double) * (2 + 2 * kBlockCk) * kBlockWarps;
-  long long budget = (long long)smem_sm / occ - 1024;
-  if (budget > smem_blk) budget = smem_blk;
-  long long nls = ((budget - (long long)red_bytes) / 8 - Dps) / (2LL * Dps);
-  if (nls < 0) return set_error(e, TNUTS_E_UNSUPPORTED, "block_run: the model does not fit in shared memory");
-  const int nlev = nls > kBlockCk ? kBlockCk : (int)nls;
-  const size_t smem = sizeof(double) * (size_t)Dps * (1 + 2 * nlev) + red_bytes;
-  double *scratch = nullptr;
-  TN_CUDA(e, cudaMallocAsync((void **)&scratch, 8 * (size_t)C * block_scratch_vectors(nlev) * Dp, e->stream));
+  const size_t smem = sizeof(double) * ((size_t)D + (2 + 2 * kBlockCk) * kBlockWarps);
+  const int kd = (D + kBlockThreads - 1) / kBlockThreads;
 #define TN_BLK(M, KD)                                                                              \
   do {                                                                                             \
     auto kfn = k_block_run<M<KD>, KD>;                                                             \
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
-    kfn<<<C, kBlockThreads, smem, e->stream>>>(m, hs, e->st, rp, cm, keep, ncol, tcm, scratch, Dp, Dps, nlev); \
+    kfn<<<C, kBlockThreads, smem, e->stream>>>(m, hs, e->st, rp, cm, keep, ncol, tcm);             \
   } while (0)
 #define TN_BLK_KD(M)                  \
   do {                                \
@@ -62,7 +44,6 @@ int block_run(Engine *e) {
   else TN_BLK_KD(StdNormalBlock);
 #undef TN_BLK_KD
 #undef TN_BLK
-  cudaFreeAsync(scratch, e->stream);
   e->launches += 1;
   cudaError_t s = cudaGetLastError();
   if (s == cudaSuccess && keep > 0) {

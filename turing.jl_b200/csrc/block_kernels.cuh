@@ -233,73 +233,27 @@ __device__ __forceinline__ void draw_momentum_b(const RunParams &rp, uint32_t gc
 }
 
 // ------------------------------------------------------------------------------------------
-// run kernel: CTA c = chain c, all transitions of this call.
-//
-// Placement of the per-dimension vectors (a chain of D = 2005 carries ~43 of them, 16 KB each: far
-// more than a CTA's share of the register file, so the first version -- everything in registers,
-// 255 of them -- spilled 1.3 G local accesses per launch, ncu profiles/r01_ncu_k_block_run_hier.txt):
-//   registers      the five vectors every leapfrog touches: z.theta, z.r, z.grad, M^-1, rho of the
-//                  sub-tree being built                                     (5 * KD doubles / thread)
-//   shared memory  theta for the model's cross-dimension reads, and the first `ls` checkpoint levels
-//                  (r, rho) of the sub-tree U-turn checks (level = popcount of the leaf index: the low
-//                  levels are the ones trees of ordinary depth use)
-//   scratch (L2)   per chain, [vector][Dp] so that a CTA's accesses are coalesced: the deeper
-//                  checkpoint levels, both tree edges, rho of the whole tree, the sub-tree and tree
-//                  candidates -- vectors touched once per doubling or with probability 1/n per leaf
-// At KD = 8 that is ~110 registers: two chains per SM, each hiding the other's barrier latency.
+// run kernel: CTA c = chain c, all transitions of this call
 // ------------------------------------------------------------------------------------------
-enum BlockScratch { BS_THC = 0, BS_GC, BS_THS, BS_GS, BS_RHO, BS_E0, BS_E1 = BS_E0 + 3, BS_CK = BS_E1 + 3 };
-__host__ __device__ inline int block_scratch_vectors(int ls) { return BS_CK + 2 * (kBlockCk - ls); }
-// Checkpoint level i (the popcount of the leaf index) lives in shared memory when l0 <= i < l0 + ls.
-// Trees of depth 5-7 use levels 1-3 most (binomial in the leaf index), so a partial set starts at 1.
-__host__ __device__ inline int block_ck_first_smem_level(int ls) { return ls < kBlockCk ? 1 : 0; }
-
 template <class M, int KD>
-__global__ void __launch_bounds__(kBlockThreads, KD >= 8 ? 2 : 3)
+__global__ void __launch_bounds__(kBlockThreads)
 k_block_run(ModelDev m, HierStatsDev hs, ChainState st, RunParams rp, double *draws_cm /* [C][keep][ncol] */,
-            long long keep, int ncol, double *theta_cm /* [C][keep][D] or null */,
-            double *scratch /* [C][block_scratch_vectors(ls)][Dp] */, int Dp, int Dps, int ls) {
+            long long keep, int ncol, double *theta_cm /* [C][keep][D] or null */) {
   extern __shared__ double smem[];
-  double *sth = smem;                            // [Dps]
-  double *sck = smem + Dps;                      // [ls][2][Dps]
-  double *red = sck + (size_t)2 * ls * Dps;      // [(2 + 2*kBlockCk)][kBlockWarps]
+  double *sth = smem;             // [D]
+  double *red = smem + m.D;       // [(2 + 2*kBlockCk)][kBlockWarps]
   const int c = blockIdx.x, C = st.C, D = m.D, tid = threadIdx.x;
   if (st.status[c] != 0) return;
   const uint32_t gchain = (uint32_t)(rp.chain_offset + c);
-  double *sc = scratch + (size_t)c * block_scratch_vectors(ls) * Dp;
-  auto vec = [&](int i) { return sc + (size_t)i * Dp + tid; };          // + k * kBlockThreads
-  // checkpoint level i: base pointer of its r vector (rho follows one vector later) and the index
-  // limit -- shared-memory vectors are Dps < KD * 256 long, the padded lanes (d >= D, always zero)
-  // share the dummy slot Dps - 1
-  const int l0 = block_ck_first_smem_level(ls);
-  struct CkLevel {
-    double *r, *rho;
-    int lim;
-  };
-  auto ck = [&](int i) {
-    CkLevel L;
-    if (i >= l0 && i < l0 + ls) {
-      L.r = sck + (size_t)(2 * (i - l0)) * Dps;
-      L.rho = L.r + Dps;
-      L.lim = Dps - 1;
-    } else {
-      const int gi = i < l0 ? i : i - ls;
-      L.r = sc + (size_t)(BS_CK + 2 * gi) * Dp;
-      L.rho = L.r + Dp;
-      L.lim = 0x7fffffff;
-    }
-    return L;
-  };
-  // the hot vectors; between transitions z.theta / z.grad hold the chain's position
-  double zt[KD], zr[KD], zg[KD], minv[KD], rho_s[KD];
+  double th[KD], g[KD], minv[KD];
 #pragma unroll
   for (int k = 0; k < KD; ++k) {
     const int d = tid + k * kBlockThreads;
-    zt[k] = zg[k] = zr[k] = rho_s[k] = 0.0;
+    th[k] = g[k] = 0.0;
     minv[k] = 1.0;
     if (d < D) {
-      zt[k] = st.theta[(size_t)d * C + c];
-      zg[k] = st.grad[(size_t)d * C + c];
+      th[k] = st.theta[(size_t)d * C + c];
+      g[k] = st.grad[(size_t)d * C + c];
       minv[k] = st.minv[(size_t)d * C + c];
     }
   }
@@ -310,19 +264,15 @@ k_block_run(ModelDev m, HierStatsDev hs, ChainState st, RunParams rp, double *dr
 
   for (long long tt = 1; tt <= rp.n_transitions; ++tt) {
     const uint32_t it = (uint32_t)(iter + 1);
-    // ---- momentum refresh, H0; the position becomes the first tree candidate ----
-    draw_momentum_b<KD>(rp, gchain, it, SLOT_MOMENTUM, minv, D, zr);
+    // ---- momentum refresh, H0 ----
+    double r[KD];
+    draw_momentum_b<KD>(rp, gchain, it, SLOT_MOMENTUM, minv, D, r);
     double e0[2];
-    kin_parts<KD>(zr, zg, minv, D, e0[0], e0[1]);
+    kin_parts<KD>(r, g, minv, D, e0[0], e0[1]);
     block_reduce<2>(e0, red);
     const double K0 = 0.5 * e0[0];
     const double H0 = (isfinite(lp) && e0[1] == 0.0 && isfinite(K0)) ? (-lp + K0) : CUDART_INF;
     double stats[TNUTS_NSTAT];
-#pragma unroll
-    for (int k = 0; k < KD; ++k) {
-      vec(BS_THC)[k * kBlockThreads] = zt[k];
-      vec(BS_GC)[k * kBlockThreads] = zg[k];
-    }
     if (rp.algorithm != TNUTS_ALG_NUTS) {
       // ---- HMC / HMCDA: static trajectory + Metropolis accept (src/mcmc/hmc.jl:425-434) ----
       int L = rp.n_leapfrog;
@@ -330,21 +280,26 @@ k_block_run(ModelDev m, HierStatsDev hs, ChainState st, RunParams rp, double *dr
         L = (int)floor(rp.lambda / eps);
         if (L < 1) L = 1;
       }
-      double zlp = lp, zH = H0;
+      double zt[KD], zg[KD], zlp = lp, zH = H0;
+#pragma unroll
+      for (int k = 0; k < KD; ++k) {
+        zt[k] = th[k];
+        zg[k] = g[k];
+      }
       const double half = 0.5 * eps;
       int nsteps = 0;
       for (int l = 0; l < L; ++l) {
 #pragma unroll
         for (int k = 0; k < KD; ++k) {
-          zr[k] = zr[k] + half * zg[k];
-          zt[k] = zt[k] + eps * (minv[k] * zr[k]);
+          r[k] = r[k] + half * zg[k];
+          zt[k] = zt[k] + eps * (minv[k] * r[k]);
         }
         zlp = M::lpgrad(m, hs, sth, red, zt, zg);
         ++ngrad;
 #pragma unroll
-        for (int k = 0; k < KD; ++k) zr[k] = zr[k] + half * zg[k];
+        for (int k = 0; k < KD; ++k) r[k] = r[k] + half * zg[k];
         double ev[2];
-        kin_parts<KD>(zr, zg, minv, D, ev[0], ev[1]);
+        kin_parts<KD>(r, zg, minv, D, ev[0], ev[1]);
         block_reduce<2>(ev, red);
         const double K = 0.5 * ev[0];
         zH = (isfinite(zlp) && ev[1] == 0.0 && isfinite(K)) ? (-zlp + K) : CUDART_INF;
@@ -356,13 +311,12 @@ k_block_run(ModelDev m, HierStatsDev hs, ChainState st, RunParams rp, double *dr
       const double u = uniform1(rp.seed, gchain, it, SLOT_MH, 0u);
       const bool accept = u < alpha;
       if (accept) {
-        lp = zlp;
-      } else {
 #pragma unroll
         for (int k = 0; k < KD; ++k) {
-          zt[k] = vec(BS_THC)[k * kBlockThreads];
-          zg[k] = vec(BS_GC)[k * kBlockThreads];
+          th[k] = zt[k];
+          g[k] = zg[k];
         }
+        lp = zlp;
       }
       stats[ST_NSTEPS] = (double)nsteps;
       stats[ST_ACC] = alpha;
@@ -374,39 +328,38 @@ k_block_run(ModelDev m, HierStatsDev hs, ChainState st, RunParams rp, double *dr
       stats[ST_NUMERR] = isfinite(zH) ? 0.0 : 1.0;
       stats[ST_EPS] = eps;
     } else {
-      // ---- tree: both edges start at the current point, rho = r ----
+    // ---- tree ----
+      double edge[2][3 * KD], elp[2];
 #pragma unroll
       for (int k = 0; k < KD; ++k) {
-        const int o = k * kBlockThreads;
-        vec(BS_E0 + 0)[o] = zt[k];
-        vec(BS_E0 + 1)[o] = zr[k];
-        vec(BS_E0 + 2)[o] = zg[k];
-        vec(BS_E1 + 0)[o] = zt[k];
-        vec(BS_E1 + 1)[o] = zr[k];
-        vec(BS_E1 + 2)[o] = zg[k];
-        vec(BS_RHO)[o] = zr[k];
+        edge[0][k] = edge[1][k] = th[k];
+        edge[0][KD + k] = edge[1][KD + k] = r[k];
+        edge[0][2 * KD + k] = edge[1][2 * KD + k] = g[k];
       }
-      double elp[2] = {lp, lp};
+      elp[0] = elp[1] = lp;
+      double rho[KD], thC[KD], gC[KD];
+#pragma unroll
+      for (int k = 0; k < KD; ++k) {
+        rho[k] = r[k];
+        thC[k] = th[k];
+        gC[k] = g[k];
+      }
       double sum_a = 0.0, dHmax = 0.0, lw = 0.0, lpC = lp, HC = H0;
       long long n_a = 0;
-      int j = 0, vprev = -1;
+      double ck_r[kBlockCk][KD], ck_rho[kBlockCk][KD];
+      int j = 0;
       bool term = false, numerr = false;
       while (!term && j < rp.max_depth) {
         const int v = (uniform1(rp.seed, gchain, it, SLOT_DIRECTION, (uint32_t)j) < 0.5) ? 0 : 1;
         const double se = v ? eps : -eps, half = 0.5 * se;
-        double zlp = elp[v], zH = 0.0;
-        const int eb = v ? BS_E1 : BS_E0;
-        if (v != vprev && j > 0) {   // the registers still hold this edge otherwise
+        double zt[KD], zr[KD], zg[KD], zlp = elp[v], zH = 0.0;
 #pragma unroll
-          for (int k = 0; k < KD; ++k) {
-            const int o = k * kBlockThreads;
-            zt[k] = vec(eb + 0)[o];
-            zr[k] = vec(eb + 1)[o];
-            zg[k] = vec(eb + 2)[o];
-          }
+        for (int k = 0; k < KD; ++k) {
+          zt[k] = edge[v][k];
+          zr[k] = edge[v][KD + k];
+          zg[k] = edge[v][2 * KD + k];
         }
-        vprev = v;
-        double lpS = 0.0, HS = 0.0;
+        double rho_s[KD], thS[KD], gS[KD], lpS = 0.0, HS = 0.0;
 #pragma unroll
         for (int k = 0; k < KD; ++k) rho_s[k] = 0.0;
         double lw_s = -CUDART_INF;
@@ -435,13 +388,11 @@ k_block_run(ModelDev m, HierStatsDev hs, ChainState st, RunParams rp, double *dr
           for (int k = 0; k < KD; ++k) rho_s[k] += zr[k];
           for (int q = 0; q < nlev; ++q) {
             const int i = idx_max - q;
-            const CkLevel L = ck(i);
             double a = 0.0, b = 0.0;
 #pragma unroll
             for (int k = 0; k < KD; ++k) {
-              const int o = min(tid + k * kBlockThreads, L.lim);
-              const double cr = L.r[o];
-              const double sr = rho_s[k] - L.rho[o] + cr;
+              const double cr = ck_r[i][k];
+              const double sr = rho_s[k] - ck_rho[i][k] + cr;
               a += sr * (minv[k] * cr);
               b += sr * (minv[k] * zr[k]);
             }
@@ -461,11 +412,11 @@ k_block_run(ModelDev m, HierStatsDev hs, ChainState st, RunParams rp, double *dr
           const double lw_new = ls_logaddexp(lw_s, lw_leaf);
           const double p = (lw_leaf == -CUDART_INF) ? 0.0 : exp(lw_leaf - lw_new);
           const double u = uniform1(rp.seed, gchain, it, SLOT_LEAF, (1u << j) + (uint32_t)n);
-          if (u < p) {   // streaming multinomial: this leaf becomes the sub-tree's candidate
+          if (u < p) {
 #pragma unroll
             for (int k = 0; k < KD; ++k) {
-              vec(BS_THS)[k * kBlockThreads] = zt[k];
-              vec(BS_GS)[k * kBlockThreads] = zg[k];
+              thS[k] = zt[k];
+              gS[k] = zg[k];
             }
             lpS = zlp;
             HS = zH;
@@ -477,12 +428,10 @@ k_block_run(ModelDev m, HierStatsDev hs, ChainState st, RunParams rp, double *dr
             break;
           }
           if (!odd) {
-            const CkLevel L = ck(idx_max);
 #pragma unroll
             for (int k = 0; k < KD; ++k) {
-              const int o = min(tid + k * kBlockThreads, L.lim);
-              L.r[o] = zr[k];
-              L.rho[o] = rho_s[k];
+              ck_r[idx_max][k] = zr[k];
+              ck_rho[idx_max][k] = rho_s[k];
             }
           } else {
             for (int q = 0; q < nlev; ++q)
@@ -490,35 +439,33 @@ k_block_run(ModelDev m, HierStatsDev hs, ChainState st, RunParams rp, double *dr
             if (term_s) break;
           }
         }
-        // the extended edge, the tree's rho and the tree U-turn (the other edge's r comes from scratch)
+#pragma unroll
+        for (int k = 0; k < KD; ++k) {
+          edge[v][k] = zt[k];
+          edge[v][KD + k] = zr[k];
+          edge[v][2 * KD + k] = zg[k];
+        }
         elp[v] = zlp;
-        bool take = false;
         if (!term_s) {
           const double u = uniform1(rp.seed, gchain, it, SLOT_MH, (uint32_t)j);
           ++j;
           const double dl = lw_s - lw;
-          take = u < (dl < 0.0 ? exp(dl) : 1.0);
-          if (take) {
+          if (u < (dl < 0.0 ? exp(dl) : 1.0)) {
+#pragma unroll
+            for (int k = 0; k < KD; ++k) {
+              thC[k] = thS[k];
+              gC[k] = gS[k];
+            }
             lpC = lpS;
             HC = HS;
           }
         }
         double d2[2] = {0.0, 0.0};
-        const int ob = v ? BS_E0 : BS_E1;
 #pragma unroll
         for (int k = 0; k < KD; ++k) {
-          const int o = k * kBlockThreads;
-          vec(eb + 0)[o] = zt[k];
-          vec(eb + 1)[o] = zr[k];
-          vec(eb + 2)[o] = zg[k];
-          if (take) {
-            vec(BS_THC)[o] = vec(BS_THS)[o];
-            vec(BS_GC)[o] = vec(BS_GS)[o];
-          }
-          const double rho = vec(BS_RHO)[o] + rho_s[k];
-          vec(BS_RHO)[o] = rho;
-          d2[v] += rho * (minv[k] * zr[k]);
-          d2[1 - v] += rho * (minv[k] * vec(ob + 1)[o]);
+          rho[k] += rho_s[k];
+          d2[0] += rho[k] * (minv[k] * edge[0][KD + k]);
+          d2[1] += rho[k] * (minv[k] * edge[1][KD + k]);
         }
         block_reduce<2>(d2, red);
         lw = ls_logaddexp(lw, lw_s);
@@ -535,8 +482,8 @@ k_block_run(ModelDev m, HierStatsDev hs, ChainState st, RunParams rp, double *dr
       stats[ST_EPS] = eps;
 #pragma unroll
       for (int k = 0; k < KD; ++k) {
-        zt[k] = vec(BS_THC)[k * kBlockThreads];
-        zg[k] = vec(BS_GC)[k * kBlockThreads];
+        th[k] = thC[k];
+        g[k] = gC[k];
       }
       lp = lpC;
     }
@@ -571,9 +518,9 @@ k_block_run(ModelDev m, HierStatsDev hs, ChainState st, RunParams rp, double *dr
           if (d < D) {
             const size_t o = (size_t)d * C + c;
             double mean = st.wf_mean[o], m2 = st.wf_m2[o];
-            const double delta = zt[k] - mean;
+            const double delta = th[k] - mean;
             mean += delta / nw;
-            m2 += delta * (zt[k] - mean);
+            m2 += delta * (th[k] - mean);
             if (wend) {
               if (wf_n >= 10 && !rp.unit_metric) minv[k] = nw / ((nw + 5.0) * (nw - 1.0)) * m2 + 1e-3 * (5.0 / (nw + 5.0));
               mean = 0.0;
@@ -599,14 +546,14 @@ k_block_run(ModelDev m, HierStatsDev hs, ChainState st, RunParams rp, double *dr
     if (rp.first_keep >= 1 && tt >= rp.first_keep && (tt - rp.first_keep) % rp.thin == 0) {
       const long long ks = (tt - rp.first_keep) / rp.thin;
       double prior, lik;
-      M::user_logp(m, sth, red, zt, lp, prior, lik);
+      M::user_logp(m, sth, red, th, lp, prior, lik);
       double *row = draws_cm + ((size_t)c * keep + ks) * ncol;
 #pragma unroll
       for (int k = 0; k < KD; ++k) {
         const int d = tid + k * kBlockThreads;
         if (d < D) {
-          row[d] = ls_is_positive(m, d) ? exp(zt[k]) : zt[k];
-          if (theta_cm) theta_cm[((size_t)c * keep + ks) * D + d] = zt[k];
+          row[d] = ls_is_positive(m, d) ? exp(th[k]) : th[k];
+          if (theta_cm) theta_cm[((size_t)c * keep + ks) * D + d] = th[k];
         }
       }
       if (tid == 0) {
@@ -622,8 +569,8 @@ k_block_run(ModelDev m, HierStatsDev hs, ChainState st, RunParams rp, double *dr
   for (int k = 0; k < KD; ++k) {
     const int d = tid + k * kBlockThreads;
     if (d < D) {
-      st.theta[(size_t)d * C + c] = zt[k];
-      st.grad[(size_t)d * C + c] = zg[k];
+      st.theta[(size_t)d * C + c] = th[k];
+      st.grad[(size_t)d * C + c] = g[k];
       st.minv[(size_t)d * C + c] = minv[k];
     }
   }
