@@ -200,11 +200,29 @@ def _cpu_cache_path(name, model, cores, chains):
     return os.path.join(tempfile.gettempdir(), "tnuts_cpu_baseline_%s" % h.hexdigest()[:16])
 
 
-def cpu_full_job(name, model, spl, N, use_cache=True, quick=False):
-    """The whole schedule (warm-up + N draws from U(-2,2)) on `cores` chains, one chain per thread on
-    all host cores: MEASURED min bulk-ESS/s and grad-evals/s.  Eight schools: seconds.  configs[2]:
-    several minutes, so the result (and the adapted state the step loop resumes from) is cached in the
-    temp directory for the other arm / the other N of the same driver session on this box."""
+def _cpu_gradient_rate(om, D, cores, reps=6):
+    """gradient evaluations per second of `cores` threads, each streaming the data for its own chain
+    (what one-chain-per-thread sampling does all the time): the calibration of the CPU schedule"""
+    import concurrent.futures as cf
+    th = np.zeros((reps, D))
+    om.lpgrad(th[:1])
+    t = time.perf_counter()
+    with cf.ThreadPoolExecutor(cores) as ex:
+        list(ex.map(lambda _: om.lpgrad(th), range(cores)))
+    return cores * reps / (time.perf_counter() - t)
+
+
+def cpu_full_job(name, model, spl, N, use_cache=True, quick=False, budget_s=420.0):
+    """A whole sampling schedule (warm-up + draws from U(-2,2)) on `cores` chains, one chain per thread
+    on all host cores: MEASURED min bulk-ESS/s and grad-evals/s, nothing extrapolated.  Eight schools:
+    seconds.  configs[2] is bound by the host's memory bandwidth (every gradient of every chain streams
+    the 80 MB of X: 569 gradients/s on the 16 cores of this pool's GPU boxes), so the configured
+    500 + 1000 schedule takes 24 minutes there (measured once: DESIGN.md section 5).  The reference arm
+    has to end within minutes: the gradient rate is calibrated first and, if the configured schedule does
+    not fit `budget_s`, warm-up and draws are shortened by the same factor (never below 150 + 300: Stan's
+    window schedule needs 150 warm-up transitions) -- the line says which schedule ran.  The result (and
+    the adapted state the step loop resumes from) is cached in the temp directory for the other arm /
+    the other N of the same driver session on this box."""
     import oracle as O
     from oracle import diagnostics as dg
     cores = host_cores()
@@ -213,7 +231,7 @@ def cpu_full_job(name, model, spl, N, use_cache=True, quick=False):
     if quick:          # tests only: a short schedule
         N, nad = 40, 20
     chains = cores if heavy else 128 * cores
-    path = _cpu_cache_path(name + ("_quick" if quick else ""), model, cores, chains)
+    path = _cpu_cache_path(name + ("_quick" if quick else "") + "_b%d" % int(budget_s), model, cores, chains)
     if use_cache and os.path.exists(path + ".json") and os.path.exists(path + ".npz"):
         with open(path + ".json") as f:
             out = json.load(f)
@@ -222,6 +240,18 @@ def cpu_full_job(name, model, spl, N, use_cache=True, quick=False):
                         % (time.time() - out["measured_at"])
         return out, dict(theta=st["theta"], eps=st["eps"], minv=st["minv"])
     om = oracle_model(model)
+    schedule = "the configured schedule"
+    if heavy and not quick and budget_s > 0:
+        rate = _cpu_gradient_rate(om, model.D, cores)
+        # leapfrogs per transition of this workload (measured on both arms): 46 in warm-up, 24 after
+        est = chains * (46.0 * nad + 24.0 * N) / rate
+        if est > budget_s:
+            f = budget_s / est
+            nad_s, N_s = max(150, int(round(nad * f))), max(300, int(round(N * f)))
+            schedule = ("%d warm-up + %d draws instead of the configured %d + %d: calibrated at %.0f "
+                        "gradients/s on %d cores the configured schedule would take %.0f s, the budget is "
+                        "%.0f s" % (nad_s, N_s, nad, N, rate, cores, est, budget_s))
+            nad, N = nad_s, N_s
     cfg = O.make_config(delta=spl.delta, max_depth=spl.max_depth, delta_max=spl.Delta_max,
                         n_adapts=nad, seed=1234, sampler_mode=1)
     n_tr = nad + N - 1
@@ -231,8 +261,8 @@ def cpu_full_job(name, model, spl, N, use_cache=True, quick=False):
     s = dg.summarize(r["params"])
     out = {
         "value": r["n_grad"] / dt, "unit": "grad_evals/s", "cores": cores, "kind": "port",
-        "sample": "%d chains x (%d warm-up + %d draws) from U(-2,2), the whole schedule, one chain per "
-                  "thread, analytic gradient" % (chains, nad, N),
+        "sample": "%d chains x (%d warm-up + %d draws) from U(-2,2), one chain per thread, analytic "
+                  "gradient; %s" % (chains, nad, N, schedule),
         "seconds": dt, "ess_bulk_min": float(s["ess_bulk"].min()),
         "ess_bulk_min_per_sec": float(s["ess_bulk"].min() / dt),
         "rhat_max": float(s["rhat"].max()), "grad_evals": int(r["n_grad"]),
@@ -282,7 +312,8 @@ def run_reference(args):
     import turing_jl_b200 as T  # noqa: F401  host descriptors only (no GPU is touched on this arm)
     model, spl, N, C = build_workload(args.workload, args.chains)
     quick = args.ref_quick
-    full, st = cpu_full_job(args.workload, model, spl, N, use_cache=not args.no_cache, quick=quick)
+    full, st = cpu_full_job(args.workload, model, spl, N, use_cache=not args.no_cache, quick=quick,
+                            budget_s=args.ref_budget)
     heavy = args.workload == "logistic"
     vals = []
     if heavy:
@@ -296,7 +327,7 @@ def run_reference(args):
     else:
         # eight schools: a step is the whole job (seconds on the host cores)
         for i in range(args.warmup + args.steps):
-            f2, _ = cpu_full_job(args.workload, model, spl, N, use_cache=False, quick=quick)
+            f2, _ = cpu_full_job(args.workload, model, spl, N, use_cache=False, quick=quick, budget_s=0)
             if i >= args.warmup:
                 vals.append((f2["grad_evals"], f2["seconds"]))
         desc = full["sample"]
@@ -428,11 +459,13 @@ def bench_logistic(cx, args):
     cx.barrier()
     t0 = time.perf_counter()
     ch = T.sample(model, spl, T.MCMCThreads(), N, C, seed=seed, devices=[cx.local],
-                  chain_offset=cx.rank * C, verbose=False, engine_options=opts, save_state=True,
-                  keep_engine=True)
+                  chain_offset=cx.rank * C, verbose=False, engine_options=dict(opts, time_kernels=1),
+                  save_state=True, keep_engine=True)
     cx.barrier()
     full_wall = cx.allmax(time.perf_counter() - t0)
     eng = ch.info["engines"][0]
+    fk = eng.kernel_times()     # the gradient kernel's launches / the persistent tail inside the full job
+    full_dev_rank = ch.info["device_seconds"]
     full_dev = cx.allmax(ch.info["device_seconds"])
     full_grads = cx.allsum(ch.info["grad_evals"])
     full_launches = ch.info["gpu_launches"]
@@ -519,32 +552,45 @@ def bench_logistic(cx, args):
     if tc:
         executed = 18.0 * Nr * dpad * 128.0 * ktiles / ksec / 1e12 if ksec > 0 else None
         pk = cx.peaks["bf16_sustained"]
-        roof = {"bound": "tensor", "achieved": useful, "peak": pk, "unit": "TFLOP/s",
-                "frac": useful / pk if useful else None,
+        # the dominant kernel: k_logistic_tc (58 % of the full job's device time, every gradient of the
+        # full-width and mid-width pumps).  ALGORITHMIC flops per launch (4*N*D per gradient
+        # evaluation x the 4096 chains one full-width launch serves) / its launch time measured here
+        # with CUDA events on the engine's stream
+        fw_useful = 4.0 * Nr * Dm * C / (grad_ms_full_width * 1e-3) / 1e12
+        fw_exec = 18.0 * Nr * dpad * 128.0 * ((C + 127) // 128) / (grad_ms_full_width * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": fw_useful, "peak": pk, "unit": "TFLOP/s",
+                "frac": fw_useful / pk,
                 "traffic": ncu_traffic("k_logistic_tc"),
-                "kernel": "k_logistic_tc<128> (full-width pumps) + k_tc_persist<128> (<= 512 chains left)",
+                "kernel": "k_logistic_tc<128>, one full-width launch (%d chains x %d rows)" % (C, Nr),
                 "peak_source": cx.peaks["source"] + " bf16 sustained (the kernel is timed inside a long step)",
-                "algorithmic_flops_per_grad_eval": 4.0 * Nr * Dm,
-                "executed_bf16_tflops": executed, "executed_frac": executed / pk if executed else None,
-                "executed_frac_of_burst_peak": executed / cx.peaks["bf16_burst"] if executed else None,
-                "x_fp64_mma_peak": useful / FP64_MMA_PEAK_TFLOPS if useful else None,
-                "kernel_seconds_per_step": gsec / args.steps, "kernel_share_of_step": gsec / dev,
-                "k_logistic_tc": {"seconds_per_step": ksec / args.steps, "launches_per_step": klaunch / args.steps,
-                                  "share_of_step": ksec / dev},
-                "k_tc_persist": {"seconds_per_step": psec / args.steps, "pumps_per_step": ppumps / args.steps,
-                                 "share_of_step": psec / dev,
-                                 "us_per_pump": psec / ppumps * 1e6 if ppumps else None},
-                "full_width_launch_ms": grad_ms_full_width,
-                "note": "achieved = SURVEY 8(d) algorithmic work 4*N*D flops per gradient evaluation x "
-                        "the gradient evaluations of the timed steps / CUDA-event time of the "
-                        "kernels that evaluate them inside those steps: the k_logistic_tc launches of the "
-                        "host-pumped phase and the persistent tail kernel, which also runs the reduction and "
-                        "the NUTS state machine of its pumps (latency-bound: few chains, one leapfrog at a "
-                        "time).  k_logistic_tc evaluates the fp64 contraction as 9 bf16 plane "
-                        "products (6 for eta = X.B, 3 for X^T R) on padded tiles: executed_bf16_tflops "
-                        "counts those, incl. the idle lanes of partly filled 128-chain tiles; "
-                        "x_fp64_mma_peak compares the useful rate with the 37.19 TFLOP/s fp64 tensor "
-                        "peak measured on this chip"}
+                "algorithmic_flops_per_launch": 4.0 * Nr * Dm * C,
+                "launch_ms": grad_ms_full_width,
+                "executed_bf16_tflops": fw_exec, "executed_frac": fw_exec / pk,
+                "executed_frac_of_burst_peak": fw_exec / cx.peaks["bf16_burst"],
+                "x_fp64_mma_peak": fw_useful / FP64_MMA_PEAK_TFLOPS,
+                "share_of_full_job": fk[0] / full_dev_rank if full_dev_rank > 0 else None,
+                "share_of_step": ksec / dev,
+                "in_step": {"launches_per_step": klaunch / args.steps, "seconds_per_step": ksec / args.steps,
+                            "executed_bf16_tflops": executed,
+                            "executed_frac": executed / pk if executed else None},
+                "tail_kernel": {"kernel": "k_tc_persist<128> (gradient + reduction + NUTS state machine per "
+                                          "leapfrog of the <= 512 unfinished chains, one cooperative launch)",
+                                "bound": "latency (one leapfrog of a few chains at a time: 148 CTAs x 11-43 row "
+                                         "tiles, three grid barriers per leapfrog)",
+                                "seconds_per_step": psec / args.steps, "pumps_per_step": ppumps / args.steps,
+                                "us_per_pump": psec / ppumps * 1e6 if ppumps else None,
+                                "share_of_step": psec / dev,
+                                "share_of_full_job": fk[4] / full_dev_rank if full_dev_rank > 0 else None,
+                                "pumps_in_full_job": int(fk[5])},
+                "step_kernels": {"useful_tflops": useful, "frac": useful / pk if useful else None,
+                                 "seconds_per_step": gsec / args.steps, "share_of_step": gsec / dev,
+                                 "note": "all gradient evaluations of the timed steps x 4*N*D / the time of both "
+                                         "kernels (the tail kernel's time includes its reductions and state machine)"},
+                "note": "achieved counts the SURVEY 8(d) algorithmic work (4*N*D flops per gradient "
+                        "evaluation); the kernel evaluates the fp64 contraction as 9 bf16 plane products (6 for "
+                        "eta = X.B, 3 for X^T R) on tiles padded to 128 chains x 112 features: "
+                        "executed_bf16_tflops counts those; x_fp64_mma_peak compares the useful rate with the "
+                        "37.19 TFLOP/s fp64 tensor peak measured on this chip (tcgen05 has no f64 kind)"}
     else:
         roof = {"bound": "tensor", "achieved": useful, "peak": FP64_MMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": useful / FP64_MMA_PEAK_TFLOPS if useful else None, "traffic": ncu_traffic("k_logistic_mma"),
@@ -571,6 +617,8 @@ def bench_logistic(cx, args):
                      "ess_bulk_min_per_sec_e2e": ess_min / full_wall, "rhat_max": float(rhat.max()),
                      "d2h_bytes": int(full_d2h) * cx.world, "gpu_launches_per_gpu": int(full_launches),
                      "fp64_equivalent_tflops_sustained": 4.0 * Nr * Dm * full_grads / full_dev / 1e12 / cx.world,
+                     "k_logistic_tc_seconds": fk[0], "k_logistic_tc_launches": int(fk[1]),
+                     "k_tc_persist_seconds": fk[4], "k_tc_persist_pumps": int(fk[5]),
                      "api": "turing_jl_b200.sample(model, NUTS(0.8), MCMCThreads(), 1000, %d; save_state=true)" % C,
                      **stats},
         "e2e": {"value": e2e_value, "unit": "grad_evals/s",
@@ -661,7 +709,8 @@ def run_b200(args):
         if parity is not None:
             line["parity_checks"] = parity
         if not args.no_cpu_baseline and cx.world == 1:
-            full, st = cpu_full_job(args.workload, model, spl, N, use_cache=not args.no_cache)
+            full, st = cpu_full_job(args.workload, model, spl, N, use_cache=not args.no_cache,
+                                    budget_s=args.ref_budget)
             if args.workload == "logistic":
                 vals = [cpu_block(model, spl, full, st, args.ref_block) for _ in range(3)]
                 rate = sum(g for g, _ in vals[1:]) / sum(dt for _, dt in vals[1:])
@@ -685,7 +734,10 @@ def main():
     ap.add_argument("--workload", default="logistic", choices=["logistic", "eight_schools"])
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
     ap.add_argument("--block", type=int, default=20, help="logistic: post-warm-up transitions per step")
-    ap.add_argument("--ref-block", type=int, default=4, help="CPU legs: post-warm-up transitions per step")
+    ap.add_argument("--ref-block", type=int, default=2, help="CPU legs: post-warm-up transitions per step")
+    ap.add_argument("--ref-budget", type=float, default=420.0,
+                    help="CPU legs: seconds the measured sampling schedule may take (0: the configured schedule "
+                         "whatever it costs -- 24 minutes for configs[2] on 16 cores)")
     ap.add_argument("--ref-quick", action="store_true", help="tests: a short CPU schedule")
     ap.add_argument("--fp64", action="store_true", help="logistic: fp64 DMMA likelihood instead of tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")

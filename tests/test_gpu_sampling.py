@@ -274,3 +274,40 @@ def test_reference_posterior_pins_of_the_constrained_support_models(built):
     ch = T.sample(m2, T.NUTS(200, 0.8), T.MCMCThreads(), 500, 32, seed=5, verbose=False,
                   initial_params=[T.InitFromParams({"ps": [0.5, 0.5], "pd": [0.25] * 4})] * 32)
     assert abs(ch["ps[1]"].mean() - 5 / 16) < 0.01
+
+
+def test_abstractmcmc_step_interface_matches_sample(built):
+    """src/mcmc/hmc.jl:156-264: step(rng, model, spl; ...) gives the initial point and a state with
+    i = 0, step(rng, model, spl, state; ...) one transition; iterating it reproduces sample()'s chain"""
+    model = T.EightSchools()
+    spl = T.NUTS(20, 0.8)
+    ch = T.sample(model, spl, 30, seed=77, nadapts=20, discard_initial=0, verbose=False)
+    tr, st = T.step(None, model, spl, seed=77, nadapts=20)
+    assert st.i == 0 and set(tr.params) == set(model.param_names)
+    assert np.isnan(tr.stats["n_steps"]) and np.isfinite(tr.stats["logjoint"])
+    rows = [tr]
+    for _ in range(29):
+        tr, st = T.step(None, model, spl, st, nadapts=20)
+        rows.append(tr)
+    assert st.i == 29
+    for n in ("μ", "τ", "θ̃[3]"):
+        np.testing.assert_array_equal(np.array([r.params[n] for r in rows]), ch[n][:, 0])
+    np.testing.assert_array_equal(np.array([r.stats["n_steps"] for r in rows[1:]]), ch["n_steps"][1:, 0])
+    p, s, e = T.params_with_stats(model, spl, rows[-1], st, stats=True)
+    assert [k for k, _ in p] == list(model.param_names) and "acceptance_rate" in s and e == {}
+    st.engine.close()
+
+
+def test_callback_sees_every_kept_iteration(built):
+    """AbstractMCMC.mcmcsample's `callback(rng, model, sampler, transition, state, iteration)`; the chain is
+    the one sample() returns without a callback"""
+    model = T.gdemo_default()
+    spl = T.NUTS(30, 0.65)
+    seen = []
+    ch = T.sample(model, spl, T.MCMCThreads(), 40, 3, seed=5, verbose=False, chain_type=T.VNChain,
+                  callback=lambda rng, m, s, tr, st, i: seen.append((i, tr.params["m"].copy(), st.i)))
+    ref = T.sample(model, spl, T.MCMCThreads(), 40, 3, seed=5, verbose=False)
+    assert [i for i, _, _ in seen] == list(range(1, 41))
+    np.testing.assert_array_equal(np.stack([m for _, m, _ in seen]), ref["m"])
+    np.testing.assert_array_equal(ch["m"], ref["m"])
+    assert isinstance(ch, T.VNChain) and ch.parameters == ("s", "m")

@@ -185,3 +185,35 @@ def test_bench_cpu_block_steps_continue_the_full_job(tmp_path, monkeypatch):
     assert g > 3 * full["chains"] and dt > 0
     cb = b.cpu_baseline_object(full, g / dt, "blocks")
     assert cb["kind"] == "port" and cb["whole_job_grad_evals_per_sec"] == full["value"]
+
+
+def test_vnchain_groups_flat_columns_by_variable():
+    """chain_type = VNChain (the reference's default, src/mcmc/Inference.jl:65): whole variables by
+    name, elements by indexed name, sampler columns as extras, the saved state as last_sampler_state"""
+    import turing_jl_b200 as T
+    from turing_jl_b200.chains import INTERNALS
+    names = ("μ", "τ") + tuple("θ̃[%d]" % (j + 1) for j in range(3))
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal((5, len(names) + len(INTERNALS), 2))
+    ch = T.VNChain(v, names, INTERNALS, {"samplerstate": {"blobs": [b"x"], "seed": 1}})
+    assert ch.parameters == ("μ", "τ", "θ̃")
+    assert ch["θ̃"].shape == (5, 2, 3)
+    np.testing.assert_array_equal(ch["θ̃"][:, :, 1], v[:, 3, :])
+    np.testing.assert_array_equal(ch["θ̃[2]"], v[:, 3, :])
+    np.testing.assert_array_equal(ch["μ"], v[:, 0, :])
+    np.testing.assert_array_equal(ch["logjoint"], v[:, len(names) + 2, :])
+    assert "n_steps" in ch.extras and "is_accept" in ch and "θ̃" in ch
+    assert ch.last_sampler_state["seed"] == 1
+    assert ch.to_chains().shape == v.shape
+    assert ch.mean("θ̃").shape == (3,)
+
+
+def test_params_with_stats_overload():
+    """src/mcmc/Inference.jl:88-101: parameters from the transition as (string, value) pairs; stats only
+    on request; extras always empty"""
+    import turing_jl_b200 as T
+    tr = T.ParamsWithStats({"s": 2.0, "m": -1.0}, {"logjoint": -3.0, "n_steps": 7.0})
+    p, s, e = T.params_with_stats(None, None, tr, None)
+    assert p == [("s", 2.0), ("m", -1.0)] and s == {} and e == {}
+    p, s, e = T.params_with_stats(None, None, tr, None, params=False, stats=True, extras=True)
+    assert p is None and s["n_steps"] == 7.0 and e == {}

@@ -17,7 +17,7 @@ import warnings
 import numpy as np
 
 from . import _lib, pinned
-from .chains import INTERNALS, Chains
+from .chains import INTERNALS, Chains, ParamsWithStats
 from .engine import Engine
 from .samplers import (Hamiltonian, InitFromParams, InitFromUniform, MCMCThreads)
 
@@ -74,11 +74,13 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
            initial_state=None, nadapts=None, discard_adapt=True, discard_initial=-1, thinning=1,
            save_state=False, progress=False, verbose=True, check_model=True, devices=None,
            diagnostics=False, strategy=0, keep_engine=False, chain_offset=0, chunk_draws=None,
-           engine_options=None):
+           engine_options=None, callback=None):
     """sample(model, spl, N) | sample(model, spl, ensemble, N, n_chains).
 
     engine_options: {name: value} passed to tnuts_set_option before init, e.g.
-    {"logistic_tc": 1} (tcgen05 likelihood for logistic regression, include/tnuts.h)."""
+    {"logistic_tc": 1} (tcgen05 likelihood for logistic regression, include/tnuts.h).
+    callback: `callback(rng, model, sampler, transition, state, iteration)` after every kept iteration
+    (AbstractMCMC.mcmcsample's `callback` keyword); the engine then runs one kept draw per call."""
     if len(args) == 1:
         N, n_chains, single = int(args[0]), 1, True
         if initial_params is not None and not isinstance(initial_params, (list, tuple)):
@@ -187,7 +189,20 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
             if first is not None:
                 value[0, :P, lo:hi] = first[0].T
                 value[0, P:P + 3, lo:hi] = first[1].T
-            if n_tr > 0:
+            if n_tr > 0 and callback is not None:
+                # mcmcsample calls the callback after every kept iteration: one kept draw per engine call
+                if first is not None:
+                    callback(rng, model, spl, transition_of(model, value[0, :, lo:hi], single), HMCState(e, 0), 1)
+                it_done = 0
+                for k in range(N - row):
+                    n_k = first_keep if k == 0 else thinning
+                    e.run(n_k, n_k, 1)
+                    it_done += n_k
+                    value[row + k, :, lo:hi] = e.fetch_draws()[0]
+                    callback(rng, model, spl, transition_of(model, value[row + k, :, lo:hi], single),
+                             HMCState(e, it_done), row + k + 1)
+                e.n_kept = 0    # the engine's draw buffer holds the last draw only: no device diagnostics
+            elif n_tr > 0:
                 if ndev == 1:
                     # straight into the chain array, D2H overlapped with the computation
                     e.run_streamed(n_tr, first_keep, thinning, value[row:], chunk_draws)
@@ -259,6 +274,67 @@ def sample(model, spl, *args, rng=None, seed=None, chain_type=Chains, initial_pa
     tm["close"] = time.perf_counter() - t_c
     post_sample_hook(chain, spl, verbose=verbose)
     return chain
+
+
+class HMCState:
+    """`HMCState` (src/mcmc/hmc.jl:1-12: i, kernel, hamiltonian, z, adaptor).  Here the engine holds
+    all of it on the device (position, gradient, step size, metric, dual-averaging and Welford state);
+    `i` is the iteration counter, `blob()` the serialised state (`save_state` / `initial_state`)."""
+
+    def __init__(self, engine, i):
+        self.engine, self.i = engine, int(i)
+
+    def blob(self):
+        return self.engine.get_state()
+
+    def stepsize(self):
+        return self.engine.stepsize()
+
+
+def transition_of(model, cols, single):
+    """one kept draw ([ncol][chains] columns of the chain array) as a ParamsWithStats in user space"""
+    P = len(model.param_names)
+    pick = (lambda v: float(v[0])) if single else (lambda v: np.array(v))
+    params = {n: pick(cols[i]) for i, n in enumerate(model.param_names)}
+    stats = {n: pick(cols[P + i]) for i, n in enumerate(INTERNALS)}
+    return ParamsWithStats(params, stats)
+
+
+def step(rng, model, spl, state=None, *, initial_params=None, nadapts=0, n_chains=1, seed=None, device=0,
+         strategy=0, engine_options=None):
+    """`AbstractMCMC.step` for the Hamiltonian samplers on an engine of `n_chains` chains (default one).
+    step(rng, model, spl; initial_params, nadapts)  -- src/mcmc/hmc.jl:156-207: initial parameters (InitFromUniform
+        with <= 1000 tries, or the given ones), step-size search when `spl.eps == 0`, adaptor; the
+        transition is the initial point (logp columns, no sampler stats), the state has i = 0
+    step(rng, model, spl, state; nadapts)           -- src/mcmc/hmc.jl:209-264: one transition + adaptation
+        while i <= nadapts; the transition carries the AdvancedHMC statistics.
+    Returns (ParamsWithStats, HMCState)."""
+    single = n_chains == 1
+    P = len(model.param_names)
+    if state is None:
+        _check_model(model, spl)
+        na = int(nadapts) if spl.adaptive and spl.n_adapts != 0 else 0
+        e = Engine(model, spl, n_chains, na, _seed_from(rng, seed), device=device, strategy=strategy)
+        for k, v in (engine_options or {}).items():
+            e.set_option(k, v)
+        if initial_params is not None and not isinstance(initial_params, (list, tuple)):
+            initial_params = [initial_params] * n_chains
+        theta0 = _resolve_initial_params(model, initial_params, n_chains)
+        try:
+            e.init(theta0)
+        except _lib.TnutsError as ex:
+            e.close()
+            if ex.code == _lib.E_INIT:
+                raise RuntimeError(ex.message) from None
+            raise
+        p, lp = e.constrain(e.theta())
+        cols = np.full((P + len(INTERNALS), n_chains), np.nan)
+        cols[:P] = p.T
+        cols[P:P + 3] = lp.T
+        return transition_of(model, cols, single), HMCState(e, 0)
+    e = state.engine
+    e.run(1, 1, 1)
+    return transition_of(model, e.fetch_draws()[0], single), HMCState(e, state.i + 1)
 
 
 def post_sample_hook(chain, spl, verbose=True):

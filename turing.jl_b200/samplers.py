@@ -121,11 +121,16 @@ class MCMCThreads:
 
 
 class MCMCSerial(MCMCThreads):
-    pass
+    """`sample(model, spl, MCMCSerial(), N, n_chains)`: the reference runs the chains one after the
+    other on one task (AbstractMCMC.mcmcsample); the result is defined to be the same
+    chains as MCMCThreads gives (each chain has its own RNG stream), so the engine serves it with the
+    same batched launch -- same draws, only the schedule differs."""
 
 
 class MCMCDistributed(MCMCThreads):
-    pass
+    """`MCMCDistributed()`: one chain per worker process upstream.  Here the counterpart is the
+    one-process-per-GPU launch (`turing_jl_b200.distributed`, chains sharded over ranks with global
+    Philox chain ids); inside one process it is served like MCMCThreads."""
 
 
 class InitFromUniform:
