@@ -172,7 +172,7 @@ static int run_case(long long N, int D, int C, int ncheck, bool timing, bool use
              xm, N, D, C, ms, 4.0 * N * D * C / (ms * 1e-3) / 1e12);
     }
   }
-  tc::release(&data);
+  tc::release(&data, 0);
   cudaFree(dX);
   cudaFree(dy);
   cudaFree(dth);

@@ -31,7 +31,7 @@ int tc_persist_run(Engine *e, const tc::Data &td, const PersistView &pv, double 
 template <class T>
 static int ls_alloc(Engine *e, std::vector<void *> *pool, T **p, size_t n) {
   void *q = nullptr;
-  TN_CUDA(e, cudaMalloc(&q, (n ? n : 1) * sizeof(T)));
+  TN_CUDA(e, cudaMallocAsync(&q, (n ? n : 1) * sizeof(T), e->stream));   // stream-ordered pool, like engine.cu
   TN_CUDA(e, cudaMemsetAsync(q, 0, (n ? n : 1) * sizeof(T), e->stream));
   pool->push_back(q);
   *p = (T *)q;
@@ -280,10 +280,10 @@ static int gradwork_alloc(Engine *e, GradWork *gw, int cap, std::vector<void *> 
   gw->part_elems = (size_t)max_chunks * gw->stride * ((size_t)e->model.D + 1);
   const size_t D1 = (size_t)e->model.D + 1;
   void *p = nullptr;
-  TN_CUDA(e, cudaMalloc(&p, 8 * gw->part_elems));
+  TN_CUDA(e, cudaMallocAsync(&p, 8 * gw->part_elems, e->stream));
   pool->push_back(p);
   gw->part = (double *)p;
-  TN_CUDA(e, cudaMalloc(&p, 8 * D1 * cap));
+  TN_CUDA(e, cudaMallocAsync(&p, 8 * D1 * cap, e->stream));
   TN_CUDA(e, cudaMemsetAsync(p, 0, 8 * D1 * cap, e->stream));
   pool->push_back(p);
   gw->lik = (double *)p;
@@ -375,8 +375,8 @@ int lockstep_create(Engine *e) {
 void lockstep_destroy(Engine *e) {
   if (!e->ls) return;
   LockstepExt *x = ext_of(e);
-  for (void *p : x->allocs) cudaFree(p);
-  tc::release(&x->tcd);
+  for (void *p : x->allocs) cudaFreeAsync(p, e->stream);
+  tc::release(&x->tcd, e->stream);
   if (x->ls.h_count) cudaFreeHost(x->ls.h_count);
   delete x;
   e->ls = nullptr;

@@ -678,9 +678,12 @@ inline const char *prepare(const double *X_dev, const double *y_dev, long long n
   if (nrows > 0x7fffffffLL) return "logistic_tc: more than 2^31 rows per GPU";
   const int dp8 = (D + 7) & ~7;
   const long long npad = ((nrows + pl.t - 1) / pl.t) * pl.t + 64;
-  if (cudaMalloc((void **)&out->xb, sizeof(__nv_bfloat16) * 3 * (size_t)nrows * dp8) != cudaSuccess)
+  // stream-ordered pool (the engine keeps freed pool memory cached): a synchronous cudaFree of these
+  // at tnuts_destroy stalled every short job for tens of milliseconds
+  if (cudaMallocAsync((void **)&out->xb, sizeof(__nv_bfloat16) * 3 * (size_t)nrows * dp8, stream) != cudaSuccess)
     return "logistic_tc: cudaMalloc";
-  if (cudaMalloc((void **)&out->yf, sizeof(float) * (size_t)npad) != cudaSuccess) return "logistic_tc: cudaMalloc";
+  if (cudaMallocAsync((void **)&out->yf, sizeof(float) * (size_t)npad, stream) != cudaSuccess)
+    return "logistic_tc: cudaMalloc";
   const long long tot = nrows * dp8;
   k_tc_split_x<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(X_dev, nrows, D, dp8, out->xb);
   k_tc_convert_y<<<(unsigned)((npad + 255) / 256), 256, 0, stream>>>(y_dev, nrows, npad, out->yf);
@@ -703,9 +706,9 @@ inline const char *prepare(const double *X_dev, const double *y_dev, long long n
   return nullptr;
 }
 
-inline void release(Data *d) {
-  if (d->xb) cudaFree(d->xb);
-  if (d->yf) cudaFree(d->yf);
+inline void release(Data *d, cudaStream_t stream) {
+  if (d->xb) cudaFreeAsync(d->xb, stream);
+  if (d->yf) cudaFreeAsync(d->yf, stream);
   *d = Data();
 }
 
