@@ -43,8 +43,8 @@ const TNUTS_NSTAT = 9
 const STAT_NAMES = (:n_steps, :acceptance_rate, :log_density, :hamiltonian_energy,
     :hamiltonian_energy_error, :max_hamiltonian_energy_error, :tree_depth, :numerical_error,
     :step_size)
-const TNUTS_GDEMO, TNUTS_LINREG, TNUTS_EIGHT_SCHOOLS, TNUTS_LOGISTIC, TNUTS_HIER_LINREG, TNUTS_STD_NORMAL =
-    Int32.(0:5)
+const TNUTS_GDEMO, TNUTS_LINREG, TNUTS_EIGHT_SCHOOLS, TNUTS_LOGISTIC, TNUTS_HIER_LINREG, TNUTS_STD_NORMAL,
+      TNUTS_BETA_BERNOULLI, TNUTS_DIRICHLET_CATEGORICAL = Int32.(0:7)
 
 function check(h, rc)
     rc == 0 && return nothing
