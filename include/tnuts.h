@@ -195,14 +195,16 @@ int tnuts_fetch_draws(tnuts_engine *e, double *draws);
 /* engine options:
  *   "keep_theta"  (0/1, default 0) keeps linked-space draws for tnuts_fetch
  *   "sort_chains" (0/1, default 1) thread-per-chain strategy: re-sort chains by step size after warm-up
- *   "logistic_tc" (0/1, default 0) TNUTS_LOGISTIC with D <= 128: evaluate the likelihood and its
+ *   "logistic_tc" (0/1, default 0) TNUTS_LOGISTIC (D <= 256, the family's limit): evaluate the likelihood and its
  *                 gradient (the X*B contraction across chains, src/mcmc/hmc.jl:181) on the tcgen05
  *                 tensor cores with bf16x3 operand planes -- fp32-grade dot products, fp64
  *                 accumulation of the log-likelihood -- instead of the fp64 DMMA kernel.
  *                 Stated bounds (tests/test_gpu_tc.py): |d lp| <= 3e-7 |lp|,
- *                 |d grad| <= 1e-4 |grad|.  Set before tnuts_init.
+ *                 |d grad| <= 1e-4 |grad|.  Set before tnuts_init.  128 < D <= 256 runs a cluster of
+ *                 two CTAs per tile (one half of the features each, partial X*B exchanged through
+ *                 distributed shared memory).
  *   "time_kernels" (0/1, default 0) see tnuts_kernel_times
- *   "persist"     (0/1, default 1) "logistic_tc" on one GPU: once <= 512 chains are unfinished, the
+ *   "persist"     (0/1, default 1) "logistic_tc" on one GPU, D <= 128: once <= 512 chains are unfinished, the
  *                 rest of a tnuts_run is ONE persistent cooperative kernel (gradient, reduction and
  *                 NUTS state machine per leapfrog, grid barriers instead of launches); bit-identical
  *                 to the host-pumped path */

@@ -28,7 +28,10 @@ TC = {"logistic_tc": 1}
 
 
 @pytest.mark.parametrize("N,D,n", [(70, 100, 5), (5017, 100, 200), (3001, 128, 130), (2000, 64, 257),
-                                   (999, 20, 64), (300, 5, 33), (1, 3, 2), (64, 1, 1)])
+                                   (999, 20, 64), (300, 5, 33), (1, 3, 2), (64, 1, 1),
+                                   # 128 < D <= 256: the CTA-pair kernel (k_logistic_tc_wide), incl. a second
+                                   # half of one feature, ragged halves and several row chunks / chain tiles
+                                   (3001, 256, 130), (777, 129, 5), (20011, 200, 257), (64, 160, 1), (5000, 145, 300)])
 def test_tc_lpgrad_against_oracle(built, N, D, n):
     model = T.models.synthetic_logistic(N, D, seed=N + D)
     ldf = T.LogDensityFunction(model, options=TC)
@@ -63,11 +66,49 @@ def test_tc_energy_differences_are_tight(built):
     assert np.max(np.abs(d)) < 1e-3, np.max(np.abs(d))
 
 
-def test_tc_rejects_wide_models(built):
-    model = T.models.synthetic_logistic(257, 130, seed=5)
-    ldf = T.LogDensityFunction(model, options=TC)
-    with pytest.raises(T._lib.TnutsError):
-        ldf.logdensity(np.zeros((2, 130)))
+def test_tc_rejects_models_past_the_family_limit(built):
+    """D <= 256 is the logistic family's limit on every path (fp64 DMMA and tcgen05)"""
+    model = T.models.synthetic_logistic(300, 257, seed=5)
+    for opts in (TC, None):
+        with pytest.raises(T._lib.TnutsError):
+            T.LogDensityFunction(model, options=opts).logdensity(np.zeros((2, 257)))
+
+
+def test_tc_wide_matches_fp64_path_at_config5_width(built):
+    """D = 256 (BASELINE configs[4]'s feature count), 256 chains, enough rows for the full row cut:
+    the CTA-pair kernel against the fp64 DMMA kernel of the same engine, and bit-identical when
+    evaluated twice (the partial-eta exchange between the two CTAs is deterministic)"""
+    N, D, C = 150000, 256, 256
+    model = T.models.synthetic_logistic(N, D, seed=9)
+    rng = np.random.default_rng(1)
+    th = rng.standard_normal((C, D)) * 0.1
+    lp, g = T.LogDensityFunction(model, options=TC).logdensity_and_gradient(th)
+    lp2, g2 = T.LogDensityFunction(model, options=TC).logdensity_and_gradient(th)
+    np.testing.assert_array_equal(lp, lp2)
+    np.testing.assert_array_equal(g, g2)
+    rlp, rg = T.LogDensityFunction(model).logdensity_and_gradient(th)
+    np.testing.assert_allclose(lp, rlp, rtol=3e-7)
+    glik = rg + th / model.hyper[0] ** 2
+    err = np.linalg.norm(g - rg, axis=1)
+    assert np.all(err <= 1e-4 * np.linalg.norm(glik, axis=1)), (err / np.linalg.norm(glik, axis=1)).max()
+
+
+def test_tc_wide_sampling_follows_the_fp64_chains(built):
+    """the pump strategy on the CTA-pair kernel (work list, shrinking row cut): same seeds, nearly the same
+    arithmetic, so the first transitions build the same trees as the fp64 path"""
+    model = T.models.synthetic_logistic(900, 140, seed=12)
+    outs = []
+    for tc in (1, 0):
+        eng = T.Engine(model, T.NUTS(20, 0.8), 200, 20, seed=3)
+        eng.set_option("logistic_tc", tc)
+        eng.set_option("keep_theta", 1)
+        eng.init()
+        eng.run(30, 1, 1)
+        outs.append(eng.fetch(theta=True))
+        eng.close()
+    a, b = outs
+    assert np.mean(a["stats"][:3, 0] == b["stats"][:3, 0]) > 0.95
+    np.testing.assert_allclose(a["theta"][:2], b["theta"][:2], atol=1e-3)
 
 
 def test_tc_sampling_is_deterministic_and_matches_fp64_posterior(built):

@@ -57,7 +57,7 @@ struct Engine {
   bool ck_smem = true;     // thread-per-chain NUTS: lowest checkpoint levels in shared memory
   int occupancy = 2;  // CTAs of 128 threads per SM the thread-per-chain kernel is compiled for
   // logistic regression: likelihood gradient on the tcgen05 tensor cores (bf16x3 planes, fp32-grade
-  // dot products, logistic_tc.cuh) instead of the fp64 DMMA kernel; opt-in, D <= 128
+  // dot products, logistic_tc.cuh) instead of the fp64 DMMA kernel; opt-in
   bool logistic_tc = false;
   // measurement aid (option "time_kernels"): CUDA-event time of the dominant kernel's launches inside
   // tnuts_run (lock-step strategy: the family's batched gradient kernel), a systematic sample

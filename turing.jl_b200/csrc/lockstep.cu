@@ -205,7 +205,7 @@ static int grad_launch(Engine *e, const double *th, int C, double *lp, double *g
           e->launches += 2;
         }
         int rpc_;
-        tc::cut_for(m.N, (n_max + tc::kChainsPerCta - 1) / tc::kChainsPerCta, &chunks, &rpc_);
+        tc::cut_for(m.N, (n_max + tc::kChainsPerCta - 1) / tc::kChainsPerCta, &chunks, &rpc_, td->pl.wide ? 2 : 1);
         if ((size_t)chunks * stride * ((size_t)D + 1) > gw->part_elems)
           return set_error(e, TNUTS_E_UNSUPPORTED, "logistic_tc: partial buffer too small");
         KernelTimer *kt = e->time_kernels ? timer_of(e) : nullptr;
@@ -906,8 +906,9 @@ int lockstep_run(Engine *e) {
   int done = 0;
   // option "persist" (default on): tcgen05 logistic likelihood on one GPU (the per-leapfrog NCCL
   // all-reduce of row shards cannot run inside the persistent kernel)
+  // ... and D <= 128: the CTA-pair kernel of wider models (k_logistic_tc_wide) has no persistent form
   const bool persist_ok = e->persist && e->logistic_tc && e->model.family == TNUTS_LOGISTIC &&
-                          !(e->world > 1 && e->cfg.row_shards > 1);
+                          e->model.D <= 128 && !(e->world > 1 && e->cfg.row_shards > 1);
   e->persist_seconds = 0.0;
   e->persist_pumps = 0;
   if (e->time_kernels) timer_of(e)->begin_run();

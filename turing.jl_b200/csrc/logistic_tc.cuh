@@ -88,6 +88,35 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// ---- thread-block cluster (the CTA pair of the wide kernel, 128 < D <= 256) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// the shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// 16 bytes into the peer's shared memory; their arrival is counted as transaction bytes on the peer's
+// mbarrier `rbar` (both addresses are shared::cluster addresses of the same CTA).  The data is visible to
+// whoever observes the barrier's phase complete -- the mechanism TMA loads use, no fences on either side
+// (cluster-scope release / acquire qualifiers compile to MEMBAR.ALL.GPU and an L1 invalidation).
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint32_t rbar, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar) : "memory");
+}
+// arrival on a barrier of the peer CTA ("I have read my buffer"): orders this thread's earlier reads
+// before it, the form CUTLASS's ClusterBarrier uses for consumer releases across a cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t rbar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -229,9 +258,19 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *v) {
 // mbarrier phases are derived from RUNNING counters (tt0 = number of row tiles this CTA has processed
 // in earlier passes, pass = number of earlier passes), so passes can follow each other without
 // re-initialising anything.
-template <int KP>
+//
+// WIDE (128 < D <= 256): the feature axis is split over a CLUSTER of two CTAs.  TMEM cannot hold the
+// Theta planes (3 x 128 columns) and G (256 columns) of 256 features next to the eta buffers, so CTA h
+// of the pair owns the features [128 h, 128 h + 128): its Theta planes, its X boxes, its G columns --
+// the TMEM layout of the KP = 128 kernel on each SM.  GEMM1 then yields a PARTIAL eta (the sum over this
+// CTA's features); the epilogue threads write their partial to the peer's shared memory (DSMEM,
+// st.shared::cluster), signal the peer's mbarrier (release.cluster), wait for the peer's partial
+// (acquire.cluster) and add the two -- fp addition commutes, so both CTAs hold bit-identical eta and
+// compute identical residuals, which each feeds to GEMM2 for its own half of G.  Only CTA 0 reports lp.
+template <int KP, int STAGES = kStages, bool WIDE = false>
 struct TcCore {
   static_assert(KP == 64 || KP == 128, "feature padding is 64 or 128");
+  static_assert(!WIDE || KP == 128, "the CTA pair splits 256 features in two halves of 128");
   static constexpr int T = kT;
   static constexpr int NKB = KP / 64;                      // 128-byte boxes along the feature axis
   static constexpr uint32_t BOX_BYTES = T * 128;           // [T rows][64 bf16]
@@ -245,18 +284,27 @@ struct TcCore {
   static constexpr int NBUF = kG2Planes == 2 ? 3 : 2;
   static_assert(COL_BUF + NBUF * BUF_COLS <= kTmemCols, "TMEM budget");
   static constexpr int NEPI = 32 * kEpiWarps;
-  static constexpr int NBARS = 2 * kStages + 2 * 3 + 2;
+  static constexpr int NBARS = 2 * STAGES + 2 * 3 + 2 + (WIDE ? 4 : 0);
+  // WIDE: one exchange buffer per epilogue group, [2 row halves][8 float4][128 chains]
+  static constexpr uint32_t XBUF_BYTES = kChainsPerCta * T * 4;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + (WIDE ? 2 * XBUF_BYTES : 0) + 1024;
 
   uint32_t stage0, bar0, tmem;
+  uint32_t xbuf0, peer;   // WIDE: exchange buffers (after the stages), rank of the other CTA of the pair
+  int fbase;              // WIDE: first feature of this CTA's half (0 otherwise)
   int warp, lane, D, ks1, n2;
   int xmode;   // timing experiments (scripts/tc_logistic_check.cu) only; 0 in the product build
 
   __device__ __forceinline__ uint32_t bar_full(int s) const { return bar0 + 8u * s; }
-  __device__ __forceinline__ uint32_t bar_empty(int s) const { return bar0 + 8u * (kStages + s); }
-  __device__ __forceinline__ uint32_t bar_eta(int b) const { return bar0 + 8u * (2 * kStages + b); }
-  __device__ __forceinline__ uint32_t bar_r(int b) const { return bar0 + 8u * (2 * kStages + 3 + b); }
-  __device__ __forceinline__ uint32_t bar_theta() const { return bar0 + 8u * (2 * kStages + 6); }
-  __device__ __forceinline__ uint32_t bar_g() const { return bar0 + 8u * (2 * kStages + 7); }
+  __device__ __forceinline__ uint32_t bar_empty(int s) const { return bar0 + 8u * (STAGES + s); }
+  __device__ __forceinline__ uint32_t bar_eta(int b) const { return bar0 + 8u * (2 * STAGES + b); }
+  __device__ __forceinline__ uint32_t bar_r(int b) const { return bar0 + 8u * (2 * STAGES + 3 + b); }
+  __device__ __forceinline__ uint32_t bar_theta() const { return bar0 + 8u * (2 * STAGES + 6); }
+  __device__ __forceinline__ uint32_t bar_g() const { return bar0 + 8u * (2 * STAGES + 7); }
+  // WIDE: xfull[g] -- the peer's group g has written its partial eta into MY exchange buffer g;
+  //       xfree[g] -- the peer's group g has read ITS exchange buffer g (the one I write into)
+  __device__ __forceinline__ uint32_t bar_xfull(int g) const { return bar0 + 8u * (2 * STAGES + 8 + g); }
+  __device__ __forceinline__ uint32_t bar_xfree(int g) const { return bar0 + 8u * (2 * STAGES + 10 + g); }
 
   // barrier init + TMEM allocation; ends with a CTA-wide synchronisation
   __device__ __forceinline__ void setup(uint8_t *smem_raw, uint64_t *bars, uint32_t *tmem_slot,
@@ -266,15 +314,31 @@ struct TcCore {
     stage0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     bar0 = smem_u32(bars);
     D = D_;
-    ks1 = (D + 15) >> 4;          // GEMM1 k-steps (16 features each)
-    n2 = (D + 15) & ~15;          // GEMM2 N
+    fbase = 0;
+    peer = 0;
+    xbuf0 = stage0 + STAGES * STAGE_BYTES;
+    int dh = D;                   // features of this CTA
+    if constexpr (WIDE) {
+      const uint32_t rank = cluster_ctarank();
+      peer = rank ^ 1u;
+      fbase = (int)rank * KP;
+      dh = D - fbase < KP ? D - fbase : KP;
+    }
+    ks1 = (dh + 15) >> 4;         // GEMM1 k-steps (16 features each)
+    n2 = (dh + 15) & ~15;         // GEMM2 N
     xmode = 0;
     if (warp == 0 && elect_one()) tma_prefetch_desc(mapX);
     if (warp == 1) {
       if (elect_one()) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
           mbar_init(bar_full(s), 1);
           mbar_init(bar_empty(s), 1);
+        }
+        if constexpr (WIDE) {
+          for (int g = 0; g < 2; ++g) {
+            mbar_init(bar_xfull(g), 1);          // one arrive.expect_tx per use + 32 KB of st.async bytes
+            mbar_init(bar_xfree(g), NEPI / 2);   // every thread of the peer's group
+          }
         }
         for (int b = 0; b < NBUF; ++b) {
           mbar_init(bar_eta(b), 1);
@@ -289,6 +353,7 @@ struct TcCore {
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (WIDE) cluster_sync_all();   // the peer's barriers exist before anyone arrives on them
     tc_fence_after();
     tmem = *tmem_slot;
   }
@@ -296,6 +361,7 @@ struct TcCore {
   __device__ __forceinline__ void teardown() {
     tc_fence_before();
     __syncthreads();
+    if constexpr (WIDE) cluster_sync_all();   // no CTA leaves while its peer may still write to it
     if (warp == 1) {
       tc_fence_after();
       tmem_dealloc(tmem, kTmemCols);
@@ -306,19 +372,22 @@ struct TcCore {
   __device__ __forceinline__ void produce(const CUtensorMap *mapX, long long rbeg, int ntile, uint32_t tt0) {
     for (int t = 0; t < ntile; ++t) {
       const uint32_t tt = tt0 + (uint32_t)t;
-      const int s = (int)(tt % kStages);
-      const uint32_t ph = (tt / kStages) & 1u;
+      const int s = (int)(tt % STAGES);
+      const uint32_t ph = (tt / STAGES) & 1u;
       mbar_wait(bar_empty(s), ph ^ 1u);
       if (elect_one()) {
         const int npl = (xmode & 4) ? 1 : 3;   // experiment: one plane only (timing of the X stream)
-        mbar_expect_tx(bar_full(s), npl * PLANE_BYTES);
+        // WIDE: a 64-feature box that lies entirely past the features GEMM1 / GEMM2 read is not loaded
+        const int nkb = WIDE ? (n2 + 63) / 64 : NKB;
+        mbar_expect_tx(bar_full(s), npl * nkb * BOX_BYTES);
         const uint32_t dst = stage0 + (uint32_t)s * STAGE_BYTES;
         const int row0 = (int)(rbeg + (long long)t * T);
 #pragma unroll
         for (int pl = 0; pl < 3; ++pl)
 #pragma unroll
           for (int kb = 0; kb < NKB; ++kb)
-            if (pl < npl) tma_load_3d(dst + pl * PLANE_BYTES + kb * BOX_BYTES, mapX, bar_full(s), kb * 64, row0, pl);
+            if (pl < npl && kb < nkb)
+              tma_load_3d(dst + pl * PLANE_BYTES + kb * BOX_BYTES, mapX, bar_full(s), fbase + kb * 64, row0, pl);
       }
       __syncwarp();
     }
@@ -335,11 +404,13 @@ struct TcCore {
     const uint32_t idesc1 = instr_desc(T, 0);
     const int q0 = (xmode & 2) ? 5 : 0;
     const uint32_t tt = tt0 + (uint32_t)t;
-    const int s = (int)(tt % kStages);
-    mbar_wait(bar_full(s), (tt / kStages) & 1u);
+    const int s = (int)(tt % STAGES);
+    mbar_wait(bar_full(s), (tt / STAGES) & 1u);
     tc_fence_after();
     const uint32_t d_col = tmem + COL_BUF + (tt % NBUF) * BUF_COLS;
-    const uint32_t xs = (stage0 + (uint32_t)s * STAGE_BYTES) >> 4;
+    // 14-bit address field of the descriptor: in a cluster launch the shared-window address of every
+    // CTA but rank 0 carries the CTA's offset in its high bits, which would spill into the LBO field
+    const uint32_t xs = ((stage0 + (uint32_t)s * STAGE_BYTES) & 0x3FFFFu) >> 4;
     if (elect_one()) {
 #pragma unroll
       for (int q = 0; q < 6; ++q) {
@@ -364,11 +435,13 @@ struct TcCore {
     constexpr uint32_t LBO_MN = (BOX_BYTES >> 4) << 16;
     const uint32_t idesc2 = instr_desc(n2, 1);
     const uint32_t tt = tt0 + (uint32_t)t;
-    const int s = (int)(tt % kStages);
+    const int s = (int)(tt % STAGES);
     mbar_wait(bar_r((int)(tt % NBUF)), (tt / NBUF) & 1u);
     tc_fence_after();
     const uint32_t r_col = tmem + COL_BUF + (tt % NBUF) * BUF_COLS;
-    const uint32_t xs = (stage0 + (uint32_t)s * STAGE_BYTES) >> 4;
+    // 14-bit address field of the descriptor: in a cluster launch the shared-window address of every
+    // CTA but rank 0 carries the CTA's offset in its high bits, which would spill into the LBO field
+    const uint32_t xs = ((stage0 + (uint32_t)s * STAGE_BYTES) & 0x3FFFFu) >> 4;
     if (elect_one()) {
       // the gradient only steers the leapfrog map: with kG2Planes == 2 it keeps the products
       // down to 2^-16 (R_m*X_h, R_h*X_m, R_h*X_h), comparable to its fp32 accumulation error
@@ -423,7 +496,7 @@ struct TcCore {
         float a[2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          const int d = d0 + 2 * j + i;
+          const int d = fbase + d0 + 2 * j + i;
           const double *p = th + (size_t)d * C + c;
           a[i] = (live && d < D) ? (float)(CG_LOADS ? __ldcg(p) : *p) : 0.f;
         }
@@ -460,6 +533,33 @@ struct TcCore {
       tmem_ld16(buf + 32 * half, v);
       tmem_ld16(buf + 32 * half + 16, v + 16);
       tc_wait_ld();
+      if constexpr (WIDE) {
+        // eta = this CTA's partial + the peer's.  iu = how often this group has used its exchange
+        // buffer (running over passes); slot of this thread: [row half][8 x 16 B][chain]
+        const uint32_t iu = tt >> 1;
+        const uint32_t slot = xbuf0 + (uint32_t)grp * XBUF_BYTES + (uint32_t)(half * 8 * kChainsPerCta + kl()) * 16u;
+        const uint32_t rslot = mapa_shared(slot, peer);
+        const uint32_t rfull = mapa_shared(bar_xfull(grp), peer);
+        if (half == 0 && kl() == 0) mbar_expect_tx(bar_xfull(grp), XBUF_BYTES);   // this use's incoming bytes
+        mbar_wait(bar_xfree(grp), (iu & 1u) ^ 1u);   // the peer has read what I sent for use iu - 1
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          st_async_v4(rslot + (uint32_t)q * (kChainsPerCta * 16u), rfull, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        mbar_wait(bar_xfull(grp), iu & 1u);           // the peer's partial has landed in my buffer
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 o;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                       : "r"(slot + (uint32_t)q * (kChainsPerCta * 16u))
+                       : "memory");
+          v[4 * q] = __float_as_uint(__uint_as_float(v[4 * q]) + o.x);
+          v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + o.y);
+          v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + o.z);
+          v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + o.w);
+        }
+        mbar_arrive_remote(mapa_shared(bar_xfree(grp), peer));
+      }
       const bool dump = dbg && dbg_cta && t == 0;
       if (dump) {
 #pragma unroll
@@ -542,12 +642,12 @@ struct TcCore {
         if (live) {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (d0 + j < D) pc[(size_t)(d0 + j) * cap + k] = (double)__uint_as_float(g[j]);
+            if (fbase + d0 + j < D) pc[(size_t)(fbase + d0 + j) * cap + k] = (double)__uint_as_float(g[j]);
         }
       }
     }
     asm volatile("bar.sync %0, %1;" ::"r"(9 + wq()), "r"(32 * (kEpiWarps / 4)) : "memory");
-    if (cgi == 0 && live) {
+    if (cgi == 0 && live && fbase == 0) {
       double s = 0.0;
 #pragma unroll
       for (int q = 0; q < kEpiWarps / 4; ++q) s += lp_part[q][kl()];
@@ -556,20 +656,22 @@ struct TcCore {
   }
 };
 
-template <int KP>
-__global__ void __launch_bounds__(kThreads, 1)
-k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict__ yf, long long nrows, int D,
+constexpr int kWideStages = 3;   // X stages of the CTA-pair kernel (the exchange buffers take the fourth's room)
+
+// One gradient pass of this CTA's (chain tile, row chunk); Core::WIDE: of this CTA's feature half too
+// (blockIdx.x = 2 * chain tile + rank in the pair; both CTAs of a pair take every exit together).
+template <class Core, bool WIDE>
+__device__ __forceinline__ void logistic_tc_body(const CUtensorMap &mapX, const float *__restrict__ yf, long long nrows, int D,
               const double *__restrict__ th, int C, const int *__restrict__ list, const int *__restrict__ count,
               int n_all, int rows_per_chunk, double *__restrict__ part /* [chunks][D+1][cap] */, int cap,
               float *__restrict__ dbg, int xmode) {
-  using Core = TcCore<KP>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[Core::NBARS];
   __shared__ uint32_t tmem_slot;
   __shared__ double lp_part[kEpiWarps / 4][kChainsPerCta];
 
   const int n = count ? *count : n_all;
-  const int k0 = blockIdx.x * kChainsPerCta;
+  const int k0 = (WIDE ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) * kChainsPerCta;
   if (k0 >= n) return;
   const int chunk = blockIdx.y;
   const long long rbeg = (long long)chunk * rows_per_chunk;
@@ -599,18 +701,39 @@ k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict_
   core.teardown();
 }
 
+template <int KP>
+__global__ void __launch_bounds__(kThreads, 1)
+k_logistic_tc(const __grid_constant__ CUtensorMap mapX, const float *__restrict__ yf, long long nrows, int D,
+              const double *__restrict__ th, int C, const int *__restrict__ list, const int *__restrict__ count,
+              int n_all, int rows_per_chunk, double *__restrict__ part /* [chunks][D+1][cap] */, int cap,
+              float *__restrict__ dbg, int xmode) {
+  logistic_tc_body<TcCore<KP>, false>(mapX, yf, nrows, D, th, C, list, count, n_all, rows_per_chunk, part, cap, dbg, xmode);
+}
+
+// 128 < D <= 256: a cluster of two CTAs per (chain tile, row chunk), one feature half each
+static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+k_logistic_tc_wide(const __grid_constant__ CUtensorMap mapX, const float *__restrict__ yf, long long nrows, int D,
+                   const double *__restrict__ th, int C, const int *__restrict__ list, const int *__restrict__ count,
+                   int n_all, int rows_per_chunk, double *__restrict__ part /* [chunks][D+1][cap] */, int cap,
+                   float *__restrict__ dbg, int xmode) {
+  logistic_tc_body<TcCore<128, kWideStages, true>, true>(mapX, yf, nrows, D, th, C, list, count, n_all, rows_per_chunk,
+                                                        part, cap, dbg, xmode);
+}
+
 // ------------------------------------------------------------------------------------------
 // host side: plan, data preparation, launch
 // ------------------------------------------------------------------------------------------
 struct Plan {
-  int kp = 0, t = kT;       // feature padding, rows per tile
+  int kp = 0, t = kT;       // feature padding (per CTA), rows per tile
+  int wide = 0;             // 1: 128 < D <= 256, a CTA pair per (chain tile, row chunk)
   int chunks = 0, rpc = 0;  // FIXED row cut (a function of N only)
   size_t smem = 0;
 };
 
 inline bool plan(long long nrows, int D, Plan *p) {
-  if (D < 1 || D > 128 || nrows < 1) return false;
+  if (D < 1 || D > 256 || nrows < 1) return false;
   p->kp = D <= 64 ? 64 : 128;
+  p->wide = D > 128 ? 1 : 0;
   p->t = kT;
   const long long tiles = (nrows + p->t - 1) / p->t;
   // 37 chunks x 32 chain tiles (4096 chains) = 8 full waves of 148 CTAs
@@ -618,7 +741,7 @@ inline bool plan(long long nrows, int D, Plan *p) {
   const long long tpc = (tiles + want - 1) / want;
   p->rpc = (int)(tpc * p->t);
   p->chunks = (int)((nrows + p->rpc - 1) / p->rpc);
-  p->smem = (size_t)kStages * 3 * p->kp * p->t * 2 + 1024;
+  p->smem = p->wide ? (size_t)TcCore<128, kWideStages, true>::SMEM_BYTES : (size_t)kStages * 3 * p->kp * p->t * 2 + 1024;
   return true;
 }
 
@@ -632,9 +755,10 @@ inline bool plan(long long nrows, int D, Plan *p) {
 // sharding), not across different chain counts (the fp64 path keeps that stronger property).
 constexpr int kSMs = 148;
 constexpr int kCtaFixedTiles = 5;   // launch + TMEM alloc + Theta load + G store, in row-tile times
-inline void cut_for(long long nrows, int n_tiles, int *chunks, int *rpc) {
+inline void cut_for(long long nrows, int n_tiles, int *chunks, int *rpc, int ctas_per_tile = 1) {
   const long long tiles = (nrows + kT - 1) / kT;
   if (n_tiles < 1) n_tiles = 1;
+  n_tiles *= ctas_per_tile;   // the wide kernel runs a CTA pair per (chain tile, row chunk)
   long long best_c = 1, best_cost = -1;
   const long long cmax = tiles < kSMs ? tiles : kSMs;
   for (long long c = 1; c <= cmax; ++c) {
@@ -674,7 +798,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 inline const char *prepare(const double *X_dev, const double *y_dev, long long nrows, int D, cudaStream_t stream,
                            Data *out) {
   Plan pl;
-  if (!plan(nrows, D, &pl)) return "logistic_tc: needs 1 <= D <= 128";
+  if (!plan(nrows, D, &pl)) return "logistic_tc: needs 1 <= D <= 256";
   if (nrows > 0x7fffffffLL) return "logistic_tc: more than 2^31 rows per GPU";
   const int dp8 = (D + 7) & ~7;
   const long long npad = ((nrows + pl.t - 1) / pl.t) * pl.t + 64;
@@ -719,9 +843,9 @@ inline cudaError_t launch(const Data &d, long long nrows, int D, const double *t
   const Plan &p = d.pl;
   const int n_tiles = (n_max + kChainsPerCta - 1) / kChainsPerCta;
   int chunks, rpc;
-  cut_for(nrows, n_tiles, &chunks, &rpc);
+  cut_for(nrows, n_tiles, &chunks, &rpc, p.wide ? 2 : 1);
   if (chunks_out) *chunks_out = chunks;
-  const dim3 grid(n_tiles, chunks);
+  const dim3 grid(p.wide ? 2 * n_tiles : n_tiles, chunks);
 #define TN_TC_LAUNCH(KP_)                                                                                 \
   do {                                                                                                    \
     auto kfn = k_logistic_tc<KP_>;                                                                        \
@@ -736,7 +860,18 @@ inline cudaError_t launch(const Data &d, long long nrows, int D, const double *t
     kfn<<<grid, kThreads, p.smem, stream>>>(d.map, d.yf, nrows, D, th, C, list, count, n_all, rpc,        \
                                             part, cap, dbg, xmode);                                       \
   } while (0)
-  if (p.kp == 128) TN_TC_LAUNCH(128);
+  if (p.wide) {
+    auto kfn = k_logistic_tc_wide;
+    static int attr_dev_ = -1;
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (attr_dev_ != dev_) {
+      cudaError_t s_ = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+      if (s_ != cudaSuccess) return s_;
+      attr_dev_ = dev_;
+    }
+    kfn<<<grid, kThreads, p.smem, stream>>>(d.map, d.yf, nrows, D, th, C, list, count, n_all, rpc, part, cap, dbg, xmode);
+  } else if (p.kp == 128) TN_TC_LAUNCH(128);
   else TN_TC_LAUNCH(64);
 #undef TN_TC_LAUNCH
   return cudaGetLastError();

@@ -22,11 +22,12 @@ def _all_ok(dist, ok):
     return bool(flag.item() == 1)
 
 
-def rows_check(dist, rank, world, local, tc=False, big=False):
+def rows_check(dist, rank, world, local, tc=False, big=False, wide=False):
     """rows sharded over all ranks, per-leapfrog NCCL all-reduce: identical chains on every rank and
-    (fp64 path) equal to the single-GPU engine to rounding over the first transitions"""
+    (fp64 path) equal to the single-GPU engine to rounding over the first transitions.
+    wide: 128 < D <= 256, where the tcgen05 mode runs the CTA-pair kernel (config 5's regime)"""
     import torch
-    N, Dm, C = (2_000_000, 256, 256) if big else (4001, 24, 64)
+    N, Dm, C = (2_000_000, 256, 256) if big else ((6001, 160, 64) if wide else (4001, 24, 64))
     model = synthetic_logistic(N, Dm, seed=3)
     spl = NUTS(10, 0.8)
     n_tr = 14
@@ -145,6 +146,7 @@ def run_all(dist, rank, world, local):
         return out
     _, out["rows_sharded_fp64"] = rows_check(dist, rank, world, local, tc=False)
     _, out["rows_sharded_tcgen05"] = rows_check(dist, rank, world, local, tc=True)
+    _, out["rows_sharded_tcgen05_wide"] = rows_check(dist, rank, world, local, tc=True, wide=True)
     _, out["pooled_diagnostics"] = diag_check(dist, rank, world, local)
     if world >= 4 and world % 2 == 0:
         _, out["mesh_chains_x_rows"] = mesh_check(dist, rank, world, local, 2)
