@@ -285,8 +285,89 @@ def test_dense_metric_matches_oracle(built):
         assert np.max(ch.info["rhat"]) < 1.01
 
 
+def test_dense_metric_on_the_pump_strategy_matches_oracle(built):
+    """metricT = DenseEuclideanMetric on the pump strategy (dense_pump.cuh): the state machine runs the
+    unit-metric dynamics in whitened coordinates phi = U^-T theta, which is the dense-metric dynamics of
+    the oracle up to rounding.  (1) every family on strategy 2, incl. logistic regression with D > 32
+    (several dimensions per lane): the oracle's dense run over the first transitions, and the
+    diagonal-metric pump until the first window ends; (2) standard normal: through the covariance
+    refresh, its Cholesky factor and the re-expression of phi; (3) a metric is estimated, symmetric,
+    positive definite, and its diagonal is what tnuts_get_inv_metric reports; (4) resume is bit-exact;
+    (5) the reference's gdemo answers with NUTS-dense and HMCDA-dense on this strategy."""
+    models = dict(small_models())
+    models["logistic_d40"] = T.models.synthetic_logistic(400, 40, seed=21)
+    for name in ("gdemo", "eight_schools", "logistic_small", "logistic_d40", "hier_small"):
+        model = models[name]
+        spl = T.NUTS(120, 0.8, metricT="dense")
+        C, n_tr = 24, 110
+        eng = T.Engine(model, spl, C, 120, seed=41, strategy=2)
+        eng.set_option("keep_theta", 1)
+        eng.init()
+        eng.run(n_tr, 1, 1)
+        out = eng.fetch(theta=True)
+        ref = O.sample_chains(oracle_of(model), oracle_config(spl, 120, 41), C, n_tr)
+        np.testing.assert_array_equal(out["stats"].transpose(2, 0, 1)[:, :8, 0], ref["stats"][:, :8, 0], err_msg=name)
+        np.testing.assert_allclose(out["theta"].transpose(2, 0, 1)[:, :8], ref["theta"][:, :8], atol=1e-7, err_msg=name)
+        dm = eng.dense_inv_metric()
+        assert dm.shape == (C, model.D, model.D)
+        np.testing.assert_allclose(dm, dm.transpose(0, 2, 1), rtol=1e-9, atol=1e-12)
+        assert np.all(np.linalg.eigvalsh(dm) > 0)
+        assert np.any(np.abs(dm[:, 0, 1]) > 1e-9), name                    # the first window (iteration 100) has ended
+        np.testing.assert_allclose(np.diagonal(dm, axis1=1, axis2=2), eng.inv_metric(), rtol=0, atol=0)
+        # chains that still follow the oracle after the refresh estimated the same metric
+        th, rth = out["theta"].transpose(2, 0, 1), ref["theta"]
+        same = np.abs(th - rth).max(axis=(1, 2)) < 1e-5
+        if same.any():
+            np.testing.assert_allclose(eng.inv_metric()[same], ref["minv"][same], rtol=1e-6, err_msg=name)
+        eng.close()
+        diag = T.Engine(model, T.NUTS(120, 0.8), C, 120, seed=41, strategy=2)
+        diag.set_option("keep_theta", 1)
+        diag.init()
+        diag.run(99, 1, 1)                   # identity metric until the first window ends at iteration 100
+        dth = diag.fetch(theta=True)["theta"]
+        np.testing.assert_allclose(dth[:8], out["theta"][:8], atol=1e-9, err_msg=name)
+        diag.close()
+    # (2) linear dynamics: compare through the metric refresh (windows 7..36 of 40 warm-up iterations)
+    model = T.StdNormal(7)
+    spl = T.NUTS(40, 0.8, metricT="dense")
+    eng = T.Engine(model, spl, 32, 40, seed=7, strategy=2)
+    eng.set_option("keep_theta", 1)
+    eng.init()
+    eng.run(60, 1, 1)
+    out = eng.fetch(theta=True)
+    ref = O.sample_chains(oracle_of(model), oracle_config(spl, 40, 7), 32, 60)
+    th, rth = out["theta"].transpose(2, 0, 1), ref["theta"]
+    err = np.abs(th - rth).max(axis=(1, 2))
+    same = err < 1e-6
+    assert same.mean() >= 0.8, (same.mean(), np.sort(err)[-8:])
+    # (the whitened arithmetic rounds differently from the oracle's M^-1 r products: 1e-6, not 1e-8)
+    np.testing.assert_allclose(eng.stepsize()[same], ref["eps"][same], rtol=1e-6)
+    np.testing.assert_allclose(eng.inv_metric()[same], ref["minv"][same], rtol=1e-6)
+    # (4) resume: the blob carries phi, grad_phi, M^-1, its factor and the covariance accumulator
+    blob = None
+    a = T.Engine(model, spl, 32, 40, seed=7, strategy=2)
+    a.init()
+    a.run(25, 1, 1)                          # stops inside the second window
+    blob = a.get_state()
+    a.run(35, 1, 1)
+    tail = a.fetch()["params"]
+    a.close()
+    b = T.Engine(model, spl, 32, 40, seed=7, strategy=2)
+    b.set_state(blob)
+    b.run(35, 1, 1)
+    np.testing.assert_array_equal(b.fetch()["params"], tail)
+    b.close()
+    eng.close()
+    # (5) test/mcmc/hmc.jl:138-142 with the dense metric on the pump strategy
+    for spl in (T.NUTS(500, 0.8, metricT="dense"), T.HMCDA(500, 0.65, 0.3, metricT="dense")):
+        ch = T.sample(T.gdemo_default(), spl, T.MCMCThreads(), 1000, 256, seed=3, verbose=False,
+                      diagnostics=True, strategy=2)
+        assert abs(ch["s"].mean() - 49 / 24) < 0.1 and abs(ch["m"].mean() - 7 / 6) < 0.05
+        assert np.max(ch.info["rhat"]) < 1.01
+
+
 def test_dense_metric_unsupported_combinations(built):
-    with pytest.raises(T._lib.TnutsError):
-        T.Engine(small_models()["logistic_small"], T.NUTS(10, 0.8, metricT="dense"), 8, 10, seed=1)
-    with pytest.raises(T._lib.TnutsError):
-        T.Engine(T.EightSchools(), T.NUTS(10, 0.8, metricT="dense"), 8, 10, seed=1, strategy=2)
+    with pytest.raises(T._lib.TnutsError):      # the CTA-per-chain strategy has no dense form
+        T.Engine(small_models()["hier_small"], T.NUTS(10, 0.8, metricT="dense"), 8, 10, seed=1, strategy=3)
+    with pytest.raises(T._lib.TnutsError):      # D > 256 on the pump
+        T.Engine(small_models()["std_normal_d600"], T.NUTS(10, 0.8, metricT="dense"), 8, 10, seed=1)

@@ -401,14 +401,20 @@ static int set_model_impl(tnuts_engine *h, const tnuts_model *m, bool device_ptr
   if (sg && (e->cfg.strategy == STRAT_THREAD || e->cfg.strategy == STRAT_BLOCK))
     return set_error(e, TNUTS_E_UNSUPPORTED, "SGHMC / SGLD run on the batched (lock-step) strategy only");
   const bool dense = e->cfg.metric == TNUTS_METRIC_DENSE;
-  if (dense && (sg || !thread_ok || (e->cfg.strategy != STRAT_AUTO && e->cfg.strategy != STRAT_THREAD)))
+  // DenseEuclideanMetric: the thread-per-chain strategy (tiny D) or the pump strategy (whitened state
+  // machine, dense_pump.cuh: [D*D][C] arrays, D <= 256); the CTA-per-chain strategy keeps a chain's
+  // vectors in registers and has no dense form
+  if (dense && (sg || e->cfg.strategy == STRAT_BLOCK ||
+                (!(thread_ok && e->cfg.strategy != STRAT_LOCKSTEP) && m->D > 256)))
     return set_error(e, TNUTS_E_UNSUPPORTED,
-                     "DenseEuclideanMetric is implemented for NUTS / HMC / HMCDA on the thread-per-chain "
-                     "strategy (gdemo, README regression, eight schools, small standard normal)");
+                     "DenseEuclideanMetric is implemented for NUTS / HMC / HMCDA on the thread-per-chain strategy "
+                     "and, for D <= 256, on the pump strategy");
   if (sg) e->strategy = STRAT_LOCKSTEP;
   else if (e->cfg.strategy == STRAT_THREAD || (e->cfg.strategy == STRAT_AUTO && thread_ok)) e->strategy = STRAT_THREAD;
-  else if (e->cfg.strategy == STRAT_BLOCK || (e->cfg.strategy == STRAT_AUTO && block_ok)) e->strategy = STRAT_BLOCK;
+  else if (!dense && (e->cfg.strategy == STRAT_BLOCK || (e->cfg.strategy == STRAT_AUTO && block_ok))) e->strategy = STRAT_BLOCK;
   else e->strategy = STRAT_LOCKSTEP;
+  // dense metric on the pump: the state machine runs the unit-metric dynamics in whitened coordinates
+  if (dense && e->strategy == STRAT_LOCKSTEP) e->rp.unit_metric = 1;
 
   // chain state
   const size_t C = (size_t)e->cfg.n_chains, D = (size_t)m->D;
@@ -675,6 +681,16 @@ int tnuts_get_inv_metric(tnuts_engine *h, double *minv) {
   Engine *e = (Engine *)h;
   if (!e || !e->inited || !minv) return set_error(e, TNUTS_E_ARG, "tnuts_get_inv_metric: bad call");
   TN_CUDA(e, cudaSetDevice(e->device));
+  if (e->st.minv_dense && e->strategy == STRAT_LOCKSTEP) {
+    // whitened pump: st.minv is the identity of the phi space; report the diagonal of M^-1
+    const size_t C = (size_t)e->st.C, D = (size_t)e->D;
+    std::vector<double> tmp(D * C);
+    for (size_t d = 0; d < D; ++d)
+      TN_CUDA(e, cudaMemcpy(tmp.data() + d * C, e->st.minv_dense + (d * D + d) * C, 8 * C, cudaMemcpyDeviceToHost));
+    for (size_t c = 0; c < C; ++c)
+      for (size_t d = 0; d < D; ++d) minv[c * D + d] = tmp[d * C + c];
+    return TNUTS_OK;
+  }
   return fetch_dc(e, e->st.minv, minv);
 }
 

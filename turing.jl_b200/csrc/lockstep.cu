@@ -13,6 +13,7 @@
 #include "engine.cuh"
 #include "lockstep_kernels.cuh"
 #include "logistic_tc.cuh"
+#include "dense_pump.cuh"
 #include "lpgrad_kernels.cuh"
 
 #ifdef TNUTS_WITH_NCCL
@@ -327,6 +328,9 @@ int lockstep_create(Engine *e) {
   A(ls->list, C); A(ls->count, 2);
   A(ls->fs_eps, C); A(ls->fs_epsp, C); A(ls->fs_H, C); A(ls->fs_dir, C); A(ls->fs_phase, C);
   A(ls->fs_iter, C); A(ls->r0, DC);
+  if (e->st.minv_dense) {   // DenseEuclideanMetric: the whitened pump (dense_pump.cuh)
+    A(ls->wT, DC); A(ls->wG, DC); A(ls->dn_req, C); A(ls->dn_n, C);
+  }
   TN_CUDA(e, cudaMallocHost((void **)&ls->h_count, 4 * sizeof(int)));
   if ((rc = gradwork_alloc(e, &x->gw, (int)C, &x->allocs))) return rc;
   // hierarchical model: centred sufficient statistics per group, computed once on the host
@@ -646,6 +650,10 @@ int lockstep_init(Engine *e, const double *theta0_dev) {
   }
   k_ls_finish_init<<<(C + 255) / 256, 256, 0, e->stream>>>(st);
   e->launches += 1;
+  if (st.minv_dense) {   // DenseEuclideanMetric(D): identity, phi = theta
+    k_dense_init<<<148 * 8, 256, 0, e->stream>>>(st);
+    e->launches += 1;
+  }
   TN_CUDA(e, cudaGetLastError());
   return TNUTS_OK;
 }
@@ -907,7 +915,9 @@ int lockstep_run(Engine *e) {
   // option "persist" (default on): tcgen05 logistic likelihood on one GPU (the per-leapfrog NCCL
   // all-reduce of row shards cannot run inside the persistent kernel)
   // ... and D <= 128: the CTA-pair kernel of wider models (k_logistic_tc_wide) has no persistent form
-  const bool persist_ok = e->persist && e->logistic_tc && e->model.family == TNUTS_LOGISTIC &&
+  // (dense metric: the gathered views and the persistent kernel do not carry the [D*D][C] arrays)
+  const bool dense = e->st.minv_dense != nullptr;
+  const bool persist_ok = e->persist && e->logistic_tc && e->model.family == TNUTS_LOGISTIC && !dense &&
                           e->model.D <= 128 && !(e->world > 1 && e->cfg.row_shards > 1);
   e->persist_seconds = 0.0;
   e->persist_pumps = 0;
@@ -942,7 +952,7 @@ int lockstep_run(Engine *e) {
     if (done != listed_done && (pump % 8 == 0)) {  // refresh the gradient work list
       listed_done = done;
       n_max = C - done;
-      if (e->compact && n_max <= Compactor::narrow_below(cp.cap)) {
+      if (e->compact && !dense && n_max <= Compactor::narrow_below(cp.cap)) {
         if ((rc = cp.compact(n_max))) break;       // leaves the identity list of the narrower view
         if (trace) fprintf(stderr, "[tnuts pump] %lld: %d unfinished chains gathered into a view of width %d\n", pump, cp.n_cols, cp.cap);
       } else {
@@ -1002,6 +1012,20 @@ int lockstep_run(Engine *e) {
         break;   // the completion check below reports chains the pump budget left unfinished
       }
     }
+    if (dense) {
+      // whitened pump: the family's kernel sees theta = U'phi (wT, written by k_dense_post of the previous
+      // pump) and its gradient (wG) becomes grad_phi = U grad_theta (zg)
+      if (pump > 0) {
+        if ((rc = grad_launch(e, cp.ls.wT, cp.cap, cp.ls.ts.zlp, cp.ls.wG, cp.ls.list, ls->count, cp.cap, n_max,
+                              gw_of(e))))
+          break;
+        k_dense_grad<<<tiles(cp.cap), kTileThreads, 0, e->stream>>>(cp.st, cp.ls);
+      }
+      k_ls_pump_dense<<<tiles(cp.cap), kTileThreads, 0, e->stream>>>(cp.st, cp.ls, rp, e->model, cp.out, ls->count + 1,
+                                                                     ls->h_count);
+      k_dense_post<<<tiles(cp.cap), kTileThreads, 0, e->stream>>>(cp.st, cp.ls);
+      e->launches += 3;
+    } else {
     if (pump > 0) {  // on the first pump no leaf is pending yet
       if ((rc = grad_launch(e, cp.ls.zt, cp.cap, cp.ls.ts.zlp, cp.ls.zg, cp.ls.list, ls->count, cp.cap, n_max,
                             gw_of(e))))
@@ -1010,6 +1034,7 @@ int lockstep_run(Engine *e) {
     k_ls_pump<<<tiles(cp.cap), kTileThreads, 0, e->stream>>>(cp.st, cp.ls, rp, e->model, cp.out, ls->count + 1,
                                                              ls->h_count);
     e->launches += 1;
+    }
     if (!lockstep_ranks && pump % 64 == 63) {
       const int slot = (int)((pump / 64) & 1);
       if (pump >= 127) cudaEventSynchronize(ev[slot]);  // the event recorded 128 pumps ago

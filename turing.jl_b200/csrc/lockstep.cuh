@@ -53,6 +53,10 @@ struct LockstepState {
   double *fs_eps = nullptr, *fs_epsp = nullptr, *fs_H = nullptr;
   int *fs_dir = nullptr, *fs_phase = nullptr, *fs_iter = nullptr;
   double *r0 = nullptr;  // [D][C] momentum of the search
+  // DenseEuclideanMetric on this strategy (dense_pump.cuh; null otherwise)
+  double *wT = nullptr, *wG = nullptr;  // [D][C] theta-space position handed to / gradient returned by the family's kernel
+  int *dn_req = nullptr;                // [C] bit 0: Welford covariance push pending, bit 1: window end (new metric)
+  int *dn_n = nullptr;                  // [C] Welford count including the pending sample
 };
 
 // the state the persistent pump kernel works on (persist.cu): the engine's own arrays or a compacted

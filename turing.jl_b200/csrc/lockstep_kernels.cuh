@@ -375,7 +375,22 @@ k_sg_step(ChainState st, RunParams rp, ModelDev m, DrawBuffers out, long long k_
 // The per-chain state machine for one tile of 8 chains, executed by a team of 256 threads.
 // `t` carries the thread's chain id (t.c >= st.C: no chain in this lane) and d-lane;
 // `red` is [2 * 64] doubles and `s_maxlev_p` one int of shared memory private to the team.
-template <class TM>
+//
+// DENSE (DenseEuclideanMetric on this strategy, metricT of src/mcmc/hmc.jl:377-386): the "whitened
+// pump".  With M^-1 = U'U (U upper triangular, st.chol) the dense-metric dynamics in (theta, r) IS the
+// unit-metric dynamics in phi = U^-T theta, p = U r: the drift theta += eps M^-1 r becomes phi += eps p,
+// the kick uses grad_phi = U grad_theta, the kinetic energy r'M^-1 r / 2 is p'p / 2, the generalised
+// U-turn products rho . M^-1 r are rho_p . p, and the momentum draw r = U \ z is p = z -- the very
+// normals the unit-metric state machine draws.  So this state machine runs UNCHANGED on (phi, p) with
+// minv = 1; around it k_dense_post hands the family's gradient kernel theta = U'phi (ls.wT) and
+// k_dense_grad turns its gradient (ls.wG) into grad_phi = U grad_theta (ls.zg).  What changes here:
+// at the end of a transition the candidate is mapped back (theta = U' phi_C) for st.theta, the kept
+// draw and the Welford covariance; the chain's phi-space state for the next transition lives in
+// st.wf_m2 (phi; the diagonal Welford M2 is unused with a dense metric) and st.grad (grad_phi); the
+// Welford covariance push and, at a window end, the new metric (regularised covariance, Cholesky,
+// phi and grad_phi re-expressed in the new factor) are left to k_dense_post through ls.dn_req, and
+// a chain whose window just ended pauses (phase 3) until that kernel has renewed its metric.
+template <class TM, bool DENSE = false>
 __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, LockstepState ls, RunParams rp,
                                              ModelDev m, DrawBuffers out, int *n_done, double *red,
                                              int *s_maxlev_p, long long *tprof = nullptr) {
@@ -401,7 +416,8 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
   double *__restrict__ const thS_ = ls.thS, *__restrict__ const gS_ = ls.gS;
   double *__restrict__ const thC_ = ls.thC, *__restrict__ const gC_ = ls.gC;
   double *__restrict__ const ckr_ = ls.ck_r, *__restrict__ const ckrho_ = ls.ck_rho;
-  double *__restrict__ const minv_ = st.minv, *__restrict__ const theta_ = st.theta,
+  // start state of the next transition: (theta, grad); DENSE: (phi, grad_phi) in (st.wf_m2, st.grad)
+  double *__restrict__ const minv_ = st.minv, *__restrict__ const theta_ = DENSE ? st.wf_m2 : st.theta,
                               *__restrict__ const grad_ = st.grad;
   const bool in = t.c < C && st.status[t.c] == 0;
   int phase = in ? s.phase[t.c] : 2;
@@ -727,13 +743,17 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
         for (int q = 0; q < rp.n_splits; ++q) wend = wend || (rp.splits[q] == iter);
         in_window = iter >= rp.window_start && iter <= rp.window_end;
       }
+      if (DENSE && t.dl == 0) {   // Welford covariance / new metric: k_dense_post, right after this kernel
+        ls.dn_req[t.c] = (in_window ? 1 : 0) | (wend ? 2 : 0);
+        ls.dn_n[t.c] = (int)(wf_n + 1);
+      }
       const double nw = (double)(wf_n + 1);
       for (int d0 = t.dl; d0 < D; d0 += kNB * kTileD) {
         LS_BATCH_OFFSETS(o, d0);
         LS_BATCH_LOAD(tc4, thC_, o);
         LS_BATCH_LOAD(gc4, gC_, o);
         double wm4[kNB], w24[kNB];
-        if (in_window) {
+        if (!DENSE && in_window) {
 #pragma unroll
           for (int i = 0; i < kNB; ++i) {
             wm4[i] = st.wf_mean[o[i]];
@@ -746,7 +766,7 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
             const double th = tc4[i];
             theta_[o[i]] = th;
             grad_[o[i]] = gc4[i];
-            if (in_window) {
+            if (!DENSE && in_window) {
               double mean = wm4[i], m2 = w24[i];
               const double delta = th - mean;
               mean += delta / nw;
@@ -773,15 +793,35 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
       stats[ST_NUMERR] = (double)numerr;
       stats[ST_EPS] = eps;
     }
+    // the position in theta space: the candidate itself, DENSE: theta = U' phi_C into st.theta
+    const double *__restrict__ thU = thC_;
+    if constexpr (DENSE) {
+      TM::sync();   // phi_C may have been written by this chain's other lanes a moment ago ([B], HMC accept)
+      if (trans_end) {
+        const double *__restrict__ const U = st.chol;
+        for (int d = t.dl; d < D; d += kTileD) {
+          double acc0 = 0.0, acc1 = 0.0;   // theta_d = sum_{e <= d} U[e][d] phi_e
+          int e = 0;
+          for (; e + 1 <= d; e += 2) {
+            acc0 = fma(U[((size_t)e * D + d) * C + t.c], thC_[(size_t)e * C + t.c], acc0);
+            acc1 = fma(U[((size_t)(e + 1) * D + d) * C + t.c], thC_[(size_t)(e + 1) * C + t.c], acc1);
+          }
+          if (e <= d) acc0 = fma(U[((size_t)e * D + d) * C + t.c], thC_[(size_t)e * C + t.c], acc0);
+          st.theta[(size_t)d * C + t.c] = acc0 + acc1;
+        }
+      }
+      TM::sync();   // the record block below reads the whole theta column
+      thU = st.theta;
+    }
     if (TM::sync_or(trans_end && k_slot >= 0)) {
       const bool rec = trans_end && k_slot >= 0;
       double prior, lik;
-      ls_user_logp<TM>(m, thC_, C, t, rec, rec ? lpC : 0.0, red, prior, lik);
+      ls_user_logp<TM>(m, thU, C, t, rec, rec ? lpC : 0.0, red, prior, lik);
       if (rec) {
         double *row = out.draws + (size_t)k_slot * out.ncol * Cout + gcol;
         for (int d0 = t.dl; d0 < D; d0 += kNB * kTileD) {
           LS_BATCH_OFFSETS(o, d0);
-          LS_BATCH_LOAD(tc4, thC_, o);
+          LS_BATCH_LOAD(tc4, thU, o);
 #pragma unroll
           for (int i = 0; i < kNB; ++i) {
             const int d = d0 + i * kTileD;
@@ -847,6 +887,8 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
       if (iter >= s.iter_end[t.c]) {
         phase = 2;
         if (t.dl == 0) atomicAdd(n_done, 1);
+      } else if (DENSE && wend) {
+        phase = 3;   // wait for the new metric (k_dense_post sets phase 0)
       } else {
         start_transition = true;
         it = (uint32_t)(iter + 1);
@@ -984,6 +1026,15 @@ k_ls_pump(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers
   const Tile t;
   if (blockIdx.x == 0 && threadIdx.x == 0) *(volatile int *)h_done = *(volatile int *)n_done;
   ls_pump_body<BlockTeam>(t, st, ls, rp, m, out, n_done, red, &s_maxlev);
+}
+static __global__ void __launch_bounds__(kTileThreads, 2)
+k_ls_pump_dense(ChainState st, LockstepState ls, RunParams rp, ModelDev m, DrawBuffers out, int *n_done,
+                int *h_done /* mapped pinned host word */) {
+  __shared__ double red[2 * 64];
+  __shared__ int s_maxlev;
+  const Tile t;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *(volatile int *)h_done = *(volatile int *)n_done;
+  ls_pump_body<BlockTeam, true>(t, st, ls, rp, m, out, n_done, red, &s_maxlev);
 }
 
 // arm a run: every chain gets its transition window [iter0, iter_end) and phase 0
