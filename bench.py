@@ -634,6 +634,30 @@ def bench_logistic(cx, args):
     return line, model, spl, N
 
 
+def bench_wide_gradient(cx, rows=1_000_000, Dm=256, C=256, reps=6):
+    """BASELINE configs[4]'s per-GPU width (D = 256, 256 chains; 1e6 of a GPU's 6.25e6 rows): one
+    likelihood gradient of all chains on the tcgen05 CTA-pair kernel (k_logistic_tc_wide: a cluster of
+    two CTAs per tile, partial X.B exchanged through distributed shared memory) and on the fp64 DMMA
+    kernel, CUDA events on the engine's stream (tnuts_bench_gradient)."""
+    T = cx.T
+    model = T.models.synthetic_logistic(rows, Dm, seed=4)
+    out = {"workload": "logistic likelihood gradient, %d rows x D = %d, %d chains (BASELINE configs[4] per-GPU "
+                       "width, a slice of its rows)" % (rows, Dm, C), "gpu_launches": 0}
+    for name, tc in (("tcgen05_cta_pair", 1), ("fp64_dmma", 0)):
+        eng = T.Engine(model, T.NUTS(0.8, init_eps=0.01), C, 0, seed=1, device=cx.local)
+        eng.set_option("logistic_tc", tc)
+        eng.init()
+        l0 = eng.launches
+        dt = eng.bench_gradient(reps if tc else 2)
+        out["gpu_launches"] += int(eng.launches - l0)
+        out[name] = {"ms_per_gradient": dt * 1e3, "useful_tflops": 4.0 * rows * Dm * C / dt / 1e12}
+        eng.close()
+    pk = cx.peaks["bf16_sustained"]
+    out["tcgen05_cta_pair"]["frac_of_bf16_peak"] = out["tcgen05_cta_pair"]["useful_tflops"] / pk
+    out["speedup_over_fp64_dmma"] = out["fp64_dmma"]["ms_per_gradient"] / out["tcgen05_cta_pair"]["ms_per_gradient"]
+    return out
+
+
 def run_b200(args):
     import torch
     import turing_jl_b200 as T
@@ -687,6 +711,9 @@ def run_b200(args):
             sec = bench_eight_schools(cx, 3, 3)
             line["gpu_launches"] += sec["gpu_launches"]
             line["secondary"] = sec
+            if cx.rank == 0:
+                line["wide_kernel"] = bench_wide_gradient(cx)
+                line["gpu_launches"] += line["wide_kernel"].pop("gpu_launches")
     else:
         n_warm = max(args.warmup, 3)
         clocks = ClockSampler(cx.local)

@@ -92,8 +92,11 @@ extern "C" {
  * regulariser at the window ends. */
 #define TNUTS_METRIC_DIAG 0
 #define TNUTS_METRIC_UNIT 1
-#define TNUTS_METRIC_DENSE 2   /* thread-per-chain strategy (gdemo, README regression, eight schools,
-                                  small standard normal) with NUTS / HMC / HMCDA */
+#define TNUTS_METRIC_DENSE 2   /* NUTS / HMC / HMCDA; thread-per-chain strategy (gdemo, README regression,
+                                  eight schools, small standard normal) and, for D <= 256, the pump
+                                  strategy (every family; logistic regression incl. "logistic_tc"):
+                                  there the state machine runs the unit-metric dynamics in whitened
+                                  coordinates phi = U^-T theta, M^-1 = U'U */
 #define TNUTS_ALG_SGHMC 3
 #define TNUTS_ALG_SGLD 4
 

@@ -9,7 +9,8 @@ METRICS = {"diag": 0, "DiagEuclideanMetric": 0, "unit": 1, "UnitEuclideanMetric"
 
 def _metric_id(metricT):
     """metricT of the reference's constructors (AHMC.DiagEuclideanMetric / UnitEuclideanMetric /
-    DenseEuclideanMetric; the dense one runs on the thread-per-chain strategy only)"""
+    DenseEuclideanMetric; the dense one runs on the thread-per-chain strategy and, for D <= 256, on the
+    pump strategy)"""
     try:
         return METRICS[metricT]
     except KeyError:
