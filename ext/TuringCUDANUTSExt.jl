@@ -89,7 +89,7 @@ struct CUDANUTS{AD} <: AdaptiveHamiltonian
 end
 metric_id(::Type{<:AdvancedHMC.DiagEuclideanMetric}) = Int32(0)
 metric_id(::Type{<:AdvancedHMC.UnitEuclideanMetric}) = Int32(1)
-metric_id(::Type{<:AdvancedHMC.DenseEuclideanMetric}) = Int32(2)   # thread-per-chain families only
+metric_id(::Type{<:AdvancedHMC.DenseEuclideanMetric}) = Int32(2)   # thread-per-chain families; D <= 256 on the pump strategy
 CUDANUTS(s::NUTS; family, data, device=0, options=NamedTuple()) =
     CUDANUTS(s.n_adapts, s.δ, s.max_depth, s.Δ_max, s.ϵ, s.adtype, Int32(family), data, Int32(device),
              options, metric_id(Turing.Inference.getmetricT(s)))

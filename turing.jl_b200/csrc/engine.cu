@@ -824,6 +824,13 @@ struct BlobHeader {
 static constexpr uint32_t kBlobVersion = 2u;
 static constexpr uint32_t kBlobMagic = 0x544e5554u;  // "TUNT"
 
+// the metric word of the header: a dense-metric blob also names the strategy that wrote it (the pump
+// strategy keeps the whitened start state phi / grad_phi where the thread-per-chain strategy keeps
+// the unused diagonal Welford M2 / grad_theta)
+static int32_t blob_metric_word(const Engine *e) {
+  return e->cfg.metric | (e->st.minv_dense ? ((int32_t)e->strategy << 8) : 0);
+}
+
 static size_t blob_bytes(const Engine *e) {
   const size_t C = (size_t)e->st.C, D = (size_t)e->D;
   const size_t dense = e->st.minv_dense ? 8 * 3 * D * D * C : 0;
@@ -842,7 +849,7 @@ int tnuts_get_state(tnuts_engine *h, void *blob, size_t *nbytes) {
   TN_CUDA(e, cudaSetDevice(e->device));
   const size_t C = (size_t)e->st.C, D = (size_t)e->D;
   BlobHeader hd{kBlobMagic, kBlobVersion, (int32_t)C, (int32_t)D, e->model.family, e->cfg.algorithm,
-                e->cfg.n_adapts, e->cfg.seed, e->cfg.metric, e->cfg.chain_offset};
+                e->cfg.n_adapts, e->cfg.seed, blob_metric_word(e), e->cfg.chain_offset};
   char *p = (char *)blob;
   std::memcpy(p, &hd, sizeof(hd));
   p += sizeof(hd);
@@ -885,8 +892,9 @@ int tnuts_set_state(tnuts_engine *h, const void *blob, size_t nbytes) {
   // The arrays mean different things per sampler (SGHMC keeps its velocity where NUTS keeps the
   // Welford mean) and per metric, and the random streams are addressed by (seed, global chain id):
   // a blob from another sampler / metric / seed / shard would continue a different chain silently.
-  if (hd.algorithm != e->cfg.algorithm || hd.metric != e->cfg.metric)
-    return set_error(e, TNUTS_E_ARG, "tnuts_set_state: blob comes from another sampler or metric");
+  if (hd.algorithm != e->cfg.algorithm || hd.metric != blob_metric_word(e))
+    return set_error(e, TNUTS_E_ARG, "tnuts_set_state: blob comes from another sampler or metric (or, dense "
+                                     "metric, from another execution strategy)");
   if (hd.seed != e->cfg.seed || hd.chain_offset != e->cfg.chain_offset)
     return set_error(e, TNUTS_E_ARG, "tnuts_set_state: blob comes from another seed or chain shard "
                                      "(create the engine with the blob's seed and chain_offset)");

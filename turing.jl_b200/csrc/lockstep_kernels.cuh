@@ -794,7 +794,7 @@ __device__ __forceinline__ void ls_pump_body(const Tile &t, ChainState st, Locks
       stats[ST_EPS] = eps;
     }
     // the position in theta space: the candidate itself, DENSE: theta = U' phi_C into st.theta
-    const double *__restrict__ thU = thC_;
+    const double *thU = thC_;
     if constexpr (DENSE) {
       TM::sync();   // phi_C may have been written by this chain's other lanes a moment ago ([B], HMC accept)
       if (trans_end) {
