@@ -14,6 +14,19 @@ from helpers import oracle_config, oracle_of
 pytestmark = pytest.mark.gpu
 
 
+def test_demo_models_posterior_means(built):
+    """DynamicPPL.TestUtils.DEMO_MODELS as test/mcmc/external_sampler.jl:198-230 samples them (NUTS,
+    n_adapts = 1000, discard_initial = 1000, 2000 draws, rtol 0.2): the vector-valued demo models are two
+    independent one-observation gdemo blocks, E[s] = [19/8, 8/3], E[m] = [3/4, 1]; on the
+    thread-per-chain and the pump strategy"""
+    for strategy in (1, 2):
+        for x, es, em in ((1.5, 19 / 8, 3 / 4), (2.0, 8 / 3, 1.0)):
+            ch = T.sample(T.GDemo([x], []), T.NUTS(1000, 0.8), T.MCMCThreads(), 2000, 128, seed=4,
+                          diagnostics=True, verbose=False, strategy=strategy)
+            np.testing.assert_allclose([ch.mean("s"), ch.mean("m")], [es, em], rtol=0.05)
+            assert ch.rhat().max() < 1.01
+
+
 def test_gdemo_posterior_known_answer(built):
     """E[s] = 49/24, E[m] = 7/6 (test/mcmc/hmc.jl:138-142, atol 0.2); we also require 4 MCSE"""
     ch = T.sample(T.gdemo_default(), T.NUTS(1000, 0.8), T.MCMCThreads(), 2000, 256, seed=1,

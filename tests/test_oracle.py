@@ -134,6 +134,24 @@ def test_posterior_known_answers_gdemo(built):
         assert abs(s["mean"][0] - 49 / 24) < 0.2 and abs(s["mean"][1] - 7 / 6) < 0.2
 
 
+def test_posterior_known_answers_demo_models(built):
+    """The analytic posterior means the reference's `DEMO_MODELS` sweep is held to
+    (test/mcmc/external_sampler.jl:198-230: NUTS with n_adapts = 1000, discard_initial = 1000, 2000
+    draws, rtol 0.2 against DynamicPPL.TestUtils.posterior_mean).  Every demo model is the gdemo prior
+    s ~ InverseGamma(2, 3), m ~ Normal(0, sqrt(s)); the vector-valued ones observe 1.5 through
+    (s[1], m[1]) and 2.0 through (s[2], m[2]), i.e. two independent one-observation blocks with
+    E[s] = (3 + x^2 / 4) / 1.5 = [19/8, 8/3] and E[m] = x / 2 = [3/4, 1]; the scalar ones are gdemo
+    itself (49/24, 7/6, above)."""
+    for x, es, em in ((1.5, 19 / 8, 3 / 4), (2.0, 8 / 3, 1.0)):
+        m = O.OracleModel(O.GDEMO, D=2, N=1, y=[x], hyper=(2.0, 3.0))
+        cfg = O.make_config(delta=0.8, n_adapts=1000, seed=5, sampler_mode=1)
+        r = O.sample_chains(m, cfg, 32, 3000, first_keep=1001)
+        s = dg.summarize(r["params"])
+        np.testing.assert_allclose(s["mean"], [es, em], rtol=0.2)          # the reference's tolerance
+        assert np.abs((s["mean"] - np.array([es, em])) / s["mcse"]).max() < 4.0
+        assert s["rhat"].max() < 1.01
+
+
 def test_sampler_modes_same_tree(built):
     """AdvancedHMC merge sampling (mode 0) and the streaming form (mode 1) build the SAME tree:
     n_steps, depth, acceptance statistic and divergence flag of the first transition agree."""
