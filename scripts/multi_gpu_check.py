@@ -1,6 +1,6 @@
 """torchrun script: the multi-GPU modes against a single-GPU engine (turing.jl_b200/multi_gpu_checks.py).
   python -m torch.distributed.run --nnodes=1 --nproc-per-node=N --master-addr 127.0.0.1 \
-      --master-port 29611 scripts/multi_gpu_check.py --rows [--tc] [--big] | --diag | --mesh | --all"""
+      --master-port 29611 scripts/multi_gpu_check.py --rows [--tc] [--wide] [--big] | --diag | --mesh | --all"""
 import json
 import os
 import sys
@@ -29,7 +29,8 @@ def main():
         ok, det = M.mesh_check(dist, rank, world, local, 2)
         res, tag = {"mesh_chains_x_rows": det}, "MESH-OK"
     else:
-        ok, det = M.rows_check(dist, rank, world, local, tc="--tc" in sys.argv, big="--big" in sys.argv)
+        ok, det = M.rows_check(dist, rank, world, local, tc="--tc" in sys.argv, big="--big" in sys.argv,
+                               wide="--wide" in sys.argv)
         res, tag = {"rows_sharded": det}, "ROWS-OK"
     if rank == 0:
         print(json.dumps(res))

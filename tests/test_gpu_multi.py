@@ -52,6 +52,20 @@ def test_row_sharded_logistic_two_gpus(built):
     assert "ROWS-OK" in out.stdout
 
 
+def test_row_sharded_logistic_tc_wide_two_gpus(built):
+    """rows sharded, D = 160: the CTA-pair tcgen05 kernel under the per-leapfrog all-reduce"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+         "--master-addr", "127.0.0.1", "--master-port", "29615",
+         os.path.join(ROOT, "scripts", "multi_gpu_check.py"), "--rows", "--tc", "--wide"],
+        capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "ROWS-OK" in out.stdout
+
+
 def test_row_sharded_logistic_tc_two_gpus(built):
     """the tcgen05 likelihood on row shards: identical chains on every rank, close to single GPU"""
     import torch
