@@ -237,7 +237,11 @@ def test_progressive_compaction_is_bit_identical(built, family, C, tc, persist):
         e.close()
     (da, ta, sa, ga, la), (db, tb, sb, gb, lb) = res
     assert ga == gb
-    assert la != lb                       # the gathers really ran
+    if tc:
+        # the tcgen05 mode reads its finished-chain counter at fixed pump indices, so the gathers run at
+        # fixed pumps; the other modes poll a mapped counter and gather when the host happens to see it
+        # (a host far ahead of the GPU may issue the whole short run before any chain finishes)
+        assert la != lb                   # the gathers really ran
     assert np.array_equal(da, db, equal_nan=True)
     assert np.array_equal(ta, tb, equal_nan=True)
     assert np.array_equal(sa, sb)

@@ -108,6 +108,10 @@ __device__ __forceinline__ void st_async_v4(uint32_t raddr, uint32_t rbar, uint3
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                ::"r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar) : "memory");
 }
+__device__ __forceinline__ void st_async_b64(uint32_t raddr, uint32_t rbar, unsigned long long v) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+               ::"r"(raddr), "l"(v), "r"(rbar) : "memory");
+}
 // arrival on a barrier of the peer CTA ("I have read my buffer"): orders this thread's earlier reads
 // before it, the form CUTLASS's ClusterBarrier uses for consumer releases across a cluster
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t rbar) {
@@ -284,9 +288,11 @@ struct TcCore {
   static constexpr int NBUF = kG2Planes == 2 ? 3 : 2;
   static_assert(COL_BUF + NBUF * BUF_COLS <= kTmemCols, "TMEM budget");
   static constexpr int NEPI = 32 * kEpiWarps;
-  static constexpr int NBARS = 2 * STAGES + 2 * 3 + 2 + (WIDE ? 4 : 0);
-  // WIDE: one exchange buffer per epilogue group, [2 row halves][8 float4][128 chains]
-  static constexpr uint32_t XBUF_BYTES = kChainsPerCta * T * 4;
+  static constexpr int NBARS = 2 * STAGES + 2 * 3 + 2 + (WIDE ? 5 : 0);
+  // WIDE: one exchange buffer per epilogue group: 16 KB of incoming partial eta (fp32, the 32 rows of
+  // the tile this CTA finalises x 128 chains) and 16 KB of incoming R planes (the peer's 32 rows)
+  static constexpr uint32_t XHALF_BYTES = kChainsPerCta * (T / 2) * 4;
+  static constexpr uint32_t XBUF_BYTES = 2 * XHALF_BYTES;
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + (WIDE ? 2 * XBUF_BYTES : 0) + 1024;
 
   uint32_t stage0, bar0, tmem;
@@ -301,10 +307,12 @@ struct TcCore {
   __device__ __forceinline__ uint32_t bar_r(int b) const { return bar0 + 8u * (2 * STAGES + 3 + b); }
   __device__ __forceinline__ uint32_t bar_theta() const { return bar0 + 8u * (2 * STAGES + 6); }
   __device__ __forceinline__ uint32_t bar_g() const { return bar0 + 8u * (2 * STAGES + 7); }
-  // WIDE: xfull[g] -- the peer's group g has written its partial eta into MY exchange buffer g;
-  //       xfree[g] -- the peer's group g has read ITS exchange buffer g (the one I write into)
+  // WIDE: xfull[g] -- the peer's group g has written its partial eta (for the rows I finalise) into MY
+  //       exchange buffer g; rfull[g] -- ... its R planes (of the rows IT finalised); lpfull -- CTA 1's
+  //       log-likelihood share has arrived at CTA 0.  One arrive.expect_tx per use + st.async bytes.
   __device__ __forceinline__ uint32_t bar_xfull(int g) const { return bar0 + 8u * (2 * STAGES + 8 + g); }
-  __device__ __forceinline__ uint32_t bar_xfree(int g) const { return bar0 + 8u * (2 * STAGES + 10 + g); }
+  __device__ __forceinline__ uint32_t bar_rfull(int g) const { return bar0 + 8u * (2 * STAGES + 10 + g); }
+  __device__ __forceinline__ uint32_t bar_lpfull() const { return bar0 + 8u * (2 * STAGES + 12); }
 
   // barrier init + TMEM allocation; ends with a CTA-wide synchronisation
   __device__ __forceinline__ void setup(uint8_t *smem_raw, uint64_t *bars, uint32_t *tmem_slot,
@@ -336,9 +344,10 @@ struct TcCore {
         }
         if constexpr (WIDE) {
           for (int g = 0; g < 2; ++g) {
-            mbar_init(bar_xfull(g), 1);          // one arrive.expect_tx per use + 32 KB of st.async bytes
-            mbar_init(bar_xfree(g), NEPI / 2);   // every thread of the peer's group
+            mbar_init(bar_xfull(g), 1);
+            mbar_init(bar_rfull(g), 1);
           }
+          mbar_init(bar_lpfull(), 1);
         }
         for (int b = 0; b < NBUF; ++b) {
           mbar_init(bar_eta(b), 1);
@@ -533,33 +542,6 @@ struct TcCore {
       tmem_ld16(buf + 32 * half, v);
       tmem_ld16(buf + 32 * half + 16, v + 16);
       tc_wait_ld();
-      if constexpr (WIDE) {
-        // eta = this CTA's partial + the peer's.  iu = how often this group has used its exchange
-        // buffer (running over passes); slot of this thread: [row half][8 x 16 B][chain]
-        const uint32_t iu = tt >> 1;
-        const uint32_t slot = xbuf0 + (uint32_t)grp * XBUF_BYTES + (uint32_t)(half * 8 * kChainsPerCta + kl()) * 16u;
-        const uint32_t rslot = mapa_shared(slot, peer);
-        const uint32_t rfull = mapa_shared(bar_xfull(grp), peer);
-        if (half == 0 && kl() == 0) mbar_expect_tx(bar_xfull(grp), XBUF_BYTES);   // this use's incoming bytes
-        mbar_wait(bar_xfree(grp), (iu & 1u) ^ 1u);   // the peer has read what I sent for use iu - 1
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          st_async_v4(rslot + (uint32_t)q * (kChainsPerCta * 16u), rfull, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        mbar_wait(bar_xfull(grp), iu & 1u);           // the peer's partial has landed in my buffer
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 o;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
-                       : "r"(slot + (uint32_t)q * (kChainsPerCta * 16u))
-                       : "memory");
-          v[4 * q] = __float_as_uint(__uint_as_float(v[4 * q]) + o.x);
-          v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + o.y);
-          v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + o.z);
-          v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + o.w);
-        }
-        mbar_arrive_remote(mapa_shared(bar_xfree(grp), peer));
-      }
       const bool dump = dbg && dbg_cta && t == 0;
       if (dump) {
 #pragma unroll
@@ -624,10 +606,126 @@ struct TcCore {
     return lp;
   }
 
+  // WIDE: the epilogue of the CTA pair.  Each 64-row tile is finalised half by half: CTA r owns the
+  // rows [32 r, 32 r + 32) of every tile.  Per tile a thread (chain, group, half)
+  //   1. forwards its partial eta of 16 of the PEER's rows (st.async into the peer's buffer),
+  //   2. adds the peer's partial to its own for 16 of ITS rows, evaluates residuals and log-likelihood
+  //      terms for those (half the arithmetic of the one-CTA kernel per SM),
+  //   3. writes the R planes of its rows to its TMEM and forwards them to the peer,
+  //   4. copies the peer's R planes (the other 32 rows) from the buffer into its TMEM.
+  // Both CTAs then hold the same R[128 x 64] and feed GEMM2 for their half of the features.  The two
+  // hops synchronise the CTAs tile by tile, so the buffers need no "free" handshake: the peer sends the
+  // next partial only after it has received my R planes, which I send after reading its last partial,
+  // and it sends the next R planes only after my next partial, which I send after reading its last R.
+  __device__ __forceinline__ double epi_tiles_wide(const float *__restrict__ yf, long long nrows, long long rbeg,
+                                                   int ntile, uint32_t tt0) const {
+    const int grp = cg() & 1, half = cg() >> 1;
+    const int rank = fbase / KP;
+    const int base_m = 32 * rank + 16 * half;          // my 16 rows of the tile
+    const int base_t = 32 * (1 - rank) + 16 * half;    // the peer thread's 16 rows
+    double lp = 0.0;
+    constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+    // this thread's 64 B in each half of the group's exchange buffer: [row quarter][4 x 16 B][chain]
+    const uint32_t slot_x = xbuf0 + (uint32_t)grp * XBUF_BYTES + (uint32_t)(half * 4 * kChainsPerCta + kl()) * 16u;
+    const uint32_t slot_r = slot_x + XHALF_BYTES;
+    const uint32_t rslot_x = mapa_shared(slot_x, peer), rslot_r = mapa_shared(slot_r, peer);
+    const uint32_t rxfull = mapa_shared(bar_xfull(grp), peer), rrfull = mapa_shared(bar_rfull(grp), peer);
+    constexpr uint32_t QS = kChainsPerCta * 16u;       // stride between a thread's 16-byte pieces
+    for (int t = 0; t < ntile; ++t) {
+      const uint32_t tt = tt0 + (uint32_t)t;
+      if ((int)(tt & 1u) != grp) continue;
+      const uint32_t iu = tt >> 1;                     // uses of this group's buffer so far
+      const long long row0 = rbeg + (long long)t * T + base_m;
+      const float4 *yp = reinterpret_cast<const float4 *>(yf + row0);
+      const int bi = (int)(tt % NBUF);
+      const uint32_t buf = lane_addr() + COL_BUF + (uint32_t)bi * BUF_COLS;
+      if (half == 0 && kl() == 0) {                    // this use's incoming bytes
+        mbar_expect_tx(bar_xfull(grp), XHALF_BYTES);
+        mbar_expect_tx(bar_rfull(grp), XHALF_BYTES);
+      }
+      mbar_wait(bar_eta(bi), (tt / NBUF) & 1u);
+      tc_fence_after();
+      uint32_t v[16];
+      tmem_ld16(buf + base_t, v);                      // 1. the peer's rows: forward my partial
+      tc_wait_ld();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) st_async_v4(rslot_x + q * QS, rxfull, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      tmem_ld16(buf + base_m, v);                      // 2. my rows
+      tc_wait_ld();
+      mbar_wait(bar_xfull(grp), iu & 1u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 o;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                     : "r"(slot_x + q * QS)
+                     : "memory");
+        v[4 * q] = __float_as_uint(__uint_as_float(v[4 * q]) + o.x);
+        v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + o.y);
+        v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + o.z);
+        v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + o.w);
+      }
+      const int nvalid = (nrows - row0 >= 16) ? 16 : (int)(nrows - row0);  // <= 0: rows past the data
+      uint32_t pr[16];                                 // R planes of my 16 rows: h in pr[0..7], m in pr[8..15]
+      float tile_sum = 0.f;
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 y4 = __ldg(yp + j4);
+        const float ys[4] = {y4.x, y4.y, y4.z, y4.w};
+        float rr[4], tsum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int jj = 4 * j4 + i;
+          const float eta = __uint_as_float(v[jj]);
+          const float e = ex2_approx(-fabsf(eta) * kLog2e);      // the arithmetic of epi_tiles, term by term
+          const float x1 = 1.f + e;
+          float sg = fmaf(-8.f / 17.f, x1, 24.f / 17.f);
+          sg = sg * fmaf(-x1, sg, 2.f);
+          sg = sg * fmaf(-x1, sg, 2.f);
+          sg = sg * fmaf(-x1, sg, 2.f);
+          const float sig = eta >= 0.f ? sg : e * sg;
+          rr[i] = ys[i] - sig;
+          const float l1 = fmaxf(eta, 0.f) + kLn2 * lg2_approx(x1);
+          const float term = ys[i] * eta - l1;
+          tsum += (jj < nvalid) ? term : 0.f;
+        }
+        tile_sum += tsum;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int o = 2 * j4 + h2;
+          pr[o] = pack_bf16(rr[2 * h2], rr[2 * h2 + 1]);
+          pr[8 + o] = pack_bf16(rr[2 * h2] - bf16_lo(pr[o]), rr[2 * h2 + 1] - bf16_hi(pr[o]));
+        }
+      }
+      lp += (double)tile_sum;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)                      // 3. forward the R planes of my rows
+        st_async_v4(rslot_r + q * QS, rrfull, pr[4 * q], pr[4 * q + 1], pr[4 * q + 2], pr[4 * q + 3]);
+      // both warps of this (lane quarter, group) must have read eta before either overwrites it
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + wq() + 4 * grp), "r"(64) : "memory");
+      tmem_st8(buf + 0 * (T / 2) + base_m / 2, pr);
+      tmem_st8(buf + 1 * (T / 2) + base_m / 2, pr + 8);
+      mbar_wait(bar_rfull(grp), iu & 1u);              // 4. the peer's R planes
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(pr[4 * q]), "=r"(pr[4 * q + 1]), "=r"(pr[4 * q + 2]), "=r"(pr[4 * q + 3])
+                     : "r"(slot_r + q * QS)
+                     : "memory");
+      tmem_st8(buf + 0 * (T / 2) + base_t / 2, pr);
+      tmem_st8(buf + 1 * (T / 2) + base_t / 2, pr + 8);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_r(bi));
+    }
+    return lp;
+  }
+
   // G -> partial sums (fp64), chain slot fastest; this warp: features [32 cg, 32 cg + 32);
   // pc = part + chunk * (D + 1) * cap, k = chain slot in the work list
   __device__ __forceinline__ void epi_store(double *pc, int cap, int k, bool live, double lp,
-                                            double (*lp_part)[kChainsPerCta], uint32_t pass) const {
+                                            double (*lp_part)[kChainsPerCta], uint32_t pass,
+                                            double *lp_peer = nullptr) const {
     const int cgi = cg();
     lp_part[cgi][kl()] = lp;
     mbar_wait(bar_g(), pass & 1u);
@@ -647,7 +745,25 @@ struct TcCore {
       }
     }
     asm volatile("bar.sync %0, %1;" ::"r"(9 + wq()), "r"(32 * (kEpiWarps / 4)) : "memory");
-    if (cgi == 0 && live && fbase == 0) {
+    if constexpr (WIDE) {
+      // each CTA holds the log-likelihood of the rows it finalised: CTA 1 hands its share to CTA 0
+      // (lp_part[0] of the peer is free after the barrier above)
+      if (cgi == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < kEpiWarps / 4; ++q) s += lp_part[q][kl()];
+        if (fbase != 0) {
+          st_async_b64(mapa_shared(smem_u32(&lp_peer[kl()]), peer), mapa_shared(bar_lpfull(), peer),
+                       (unsigned long long)__double_as_longlong(s));
+        } else {
+          if (kl() == 0) mbar_expect_tx(bar_lpfull(), kChainsPerCta * 8u);
+          mbar_wait(bar_lpfull(), pass & 1u);
+          double o;
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(o) : "r"(smem_u32(&lp_peer[kl()])) : "memory");
+          if (live) pc[(size_t)D * cap + k] = s + o;
+        }
+      }
+    } else if (cgi == 0 && live) {
       double s = 0.0;
 #pragma unroll
       for (int q = 0; q < kEpiWarps / 4; ++q) s += lp_part[q][kl()];
@@ -669,6 +785,7 @@ __device__ __forceinline__ void logistic_tc_body(const CUtensorMap &mapX, const 
   __shared__ __align__(8) uint64_t bars[Core::NBARS];
   __shared__ uint32_t tmem_slot;
   __shared__ double lp_part[kEpiWarps / 4][kChainsPerCta];
+  __shared__ double lp_peer[WIDE ? kChainsPerCta : 1];   // WIDE, CTA 0: the peer's share of the log-likelihood
 
   const int n = count ? *count : n_all;
   const int k0 = (WIDE ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) * kChainsPerCta;
@@ -695,8 +812,10 @@ __device__ __forceinline__ void logistic_tc_body(const CUtensorMap &mapX, const 
     const bool live = k < n;
     const int c = live ? (list ? list[k] : k) : 0;
     core.template epi_theta<false>(th, C, c, live);
-    const double lp = core.epi_tiles(yf, nrows, rbeg, ntile, 0u, dbg, blockIdx.x == 0 && blockIdx.y == 0);
-    core.epi_store(part + (size_t)chunk * (D + 1) * cap, cap, k, live, lp, lp_part, 0u);
+    double lp;
+    if constexpr (WIDE) lp = core.epi_tiles_wide(yf, nrows, rbeg, ntile, 0u);
+    else lp = core.epi_tiles(yf, nrows, rbeg, ntile, 0u, dbg, blockIdx.x == 0 && blockIdx.y == 0);
+    core.epi_store(part + (size_t)chunk * (D + 1) * cap, cap, k, live, lp, lp_part, 0u, lp_peer);
   }
   core.teardown();
 }
