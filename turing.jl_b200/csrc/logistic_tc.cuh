@@ -696,11 +696,10 @@ struct TcCore {
           pr[o] = pack_bf16(rr[2 * h2], rr[2 * h2 + 1]);
           pr[8 + o] = pack_bf16(rr[2 * h2] - bf16_lo(pr[o]), rr[2 * h2 + 1] - bf16_hi(pr[o]));
         }
+        // 3. forward the R planes of these four rows (h, h, m, m) while the next four are evaluated
+        st_async_v4(rslot_r + j4 * QS, rrfull, pr[2 * j4], pr[2 * j4 + 1], pr[8 + 2 * j4], pr[8 + 2 * j4 + 1]);
       }
       lp += (double)tile_sum;
-#pragma unroll
-      for (int q = 0; q < 4; ++q)                      // 3. forward the R planes of my rows
-        st_async_v4(rslot_r + q * QS, rrfull, pr[4 * q], pr[4 * q + 1], pr[4 * q + 2], pr[4 * q + 3]);
       // both warps of this (lane quarter, group) must have read eta before either overwrites it
       asm volatile("bar.sync %0, %1;" ::"r"(1 + wq() + 4 * grp), "r"(64) : "memory");
       tmem_st8(buf + 0 * (T / 2) + base_m / 2, pr);
@@ -709,7 +708,7 @@ struct TcCore {
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(pr[4 * q]), "=r"(pr[4 * q + 1]), "=r"(pr[4 * q + 2]), "=r"(pr[4 * q + 3])
+                     : "=r"(pr[2 * q]), "=r"(pr[2 * q + 1]), "=r"(pr[8 + 2 * q]), "=r"(pr[8 + 2 * q + 1])
                      : "r"(slot_r + q * QS)
                      : "memory");
       tmem_st8(buf + 0 * (T / 2) + base_t / 2, pr);
