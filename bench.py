@@ -200,16 +200,28 @@ def _cpu_cache_path(name, model, cores, chains):
     return os.path.join(tempfile.gettempdir(), "tnuts_cpu_baseline_%s" % h.hexdigest()[:16])
 
 
-def _cpu_gradient_rate(om, D, cores, reps=6):
-    """gradient evaluations per second of `cores` threads, each streaming the data for its own chain
-    (what one-chain-per-thread sampling does all the time): the calibration of the CPU schedule"""
-    import concurrent.futures as cf
-    th = np.zeros((reps, D))
-    om.lpgrad(th[:1])
+def _cpu_gradient_rate(om, model, cores, n_transitions=12):
+    """gradient evaluations per second of the CPU job itself: `cores` chains, one per thread, take a
+    few NUTS transitions from a posterior-width cloud around the mode with the step size and metric an
+    adapted chain has (depth-3 trees) -- the sampler's own code path, threads and memory traffic.
+    (A first version timed bare gradient calls at theta = 0 from a Python thread pool: on the 16-core GPU
+    boxes that read 1454 gradients/s where the sampling job then ran at 605, and the schedule overshot
+    its time budget three times over.)"""
+    import oracle as O
+    X, y, D = model.X, model.y, model.D
+    b = np.zeros(D)
+    for _ in range(6):                                   # Newton steps to the posterior mode
+        p = 1.0 / (1.0 + np.exp(-(X @ b)))
+        H = (X * (p * (1.0 - p))[:, None]).T @ X + np.eye(D)
+        b = b + np.linalg.solve(H, X.T @ (y - p) - b)
+    var = np.diag(np.linalg.inv(H))
+    th = b + np.sqrt(var) * np.random.default_rng(7).standard_normal((cores, D))
+    cfg = O.make_config(delta=0.8, n_adapts=0, seed=77, sampler_mode=1)
+    eps, minv = np.full(cores, 0.38), np.tile(var, (cores, 1))
+    O.resume_chains(om, cfg, th, eps, minv, 1000, 1, n_threads=cores)          # warm the threads up
     t = time.perf_counter()
-    with cf.ThreadPoolExecutor(cores) as ex:
-        list(ex.map(lambda _: om.lpgrad(th), range(cores)))
-    return cores * reps / (time.perf_counter() - t)
+    r = O.resume_chains(om, cfg, th, eps, minv, 1000, n_transitions, n_threads=cores)
+    return r["n_grad"] / (time.perf_counter() - t)
 
 
 def cpu_full_job(name, model, spl, N, use_cache=True, quick=False, budget_s=420.0):
@@ -242,11 +254,15 @@ def cpu_full_job(name, model, spl, N, use_cache=True, quick=False, budget_s=420.
     om = oracle_model(model)
     schedule = "the configured schedule"
     if heavy and not quick and budget_s > 0:
-        rate = _cpu_gradient_rate(om, model.D, cores)
-        # leapfrogs per transition of this workload (measured on both arms): 46 in warm-up, 24 after
-        est = chains * (46.0 * nad + 24.0 * N) / rate
+        rate = _cpu_gradient_rate(om, model, cores)
+        # gradient evaluations per chain of this workload, from the two schedules measured on this pool's
+        # boxes (500 + 1000: 50 717, 150 + 300: 18 124): the deep trees of the first warm-up transitions
+        # cost ~4 200, every transition after that ~31
+        grads = lambda a, n: 4200.0 + 31.0 * (a + n)
+        est = chains * grads(nad, N) / rate
         if est > budget_s:
-            f = budget_s / est
+            # shorten warm-up and draws by the same factor so that the model fits the budget
+            f = max(0.0, (budget_s * rate / chains - 4200.0) / (31.0 * (nad + N)))
             nad_s, N_s = max(150, int(round(nad * f))), max(300, int(round(N * f)))
             schedule = ("%d warm-up + %d draws instead of the configured %d + %d: calibrated at %.0f "
                         "gradients/s on %d cores the configured schedule would take %.0f s, the budget is "
