@@ -259,10 +259,13 @@ def cpu_full_job(name, model, spl, N, use_cache=True, quick=False, budget_s=420.
         # boxes (500 + 1000: 50 717, 150 + 300: 18 124): the deep trees of the first warm-up transitions
         # cost ~4 200, every transition after that ~31
         grads = lambda a, n: 4200.0 + 31.0 * (a + n)
-        est = chains * grads(nad, N) / rate
+        # one chain per thread with as many chains as threads: the job lasts as long as its slowest chain
+        # (measured: 8 chains kept 3.5 of 8 cores busy on average; wall time = 1.66 x total work / rate)
+        straggler = 1.7
+        est = straggler * chains * grads(nad, N) / rate
         if est > budget_s:
             # shorten warm-up and draws by the same factor so that the model fits the budget
-            f = max(0.0, (budget_s * rate / chains - 4200.0) / (31.0 * (nad + N)))
+            f = max(0.0, (budget_s * rate / (straggler * chains) - 4200.0) / (31.0 * (nad + N)))
             nad_s, N_s = max(150, int(round(nad * f))), max(300, int(round(N * f)))
             schedule = ("%d warm-up + %d draws instead of the configured %d + %d: calibrated at %.0f "
                         "gradients/s on %d cores the configured schedule would take %.0f s, the budget is "
