@@ -673,6 +673,8 @@ def bench_wide_gradient(cx, rows=1_000_000, Dm=256, C=256, reps=6):
         eng.close()
     pk = cx.peaks["bf16_sustained"]
     out["tcgen05_cta_pair"]["frac_of_bf16_peak"] = out["tcgen05_cta_pair"]["useful_tflops"] / pk
+    out["tcgen05_cta_pair"]["traffic"] = ncu_traffic("k_logistic_tc_wide")
+    out["tcgen05_cta_pair"]["algorithmic_bytes"] = 3 * rows * Dm * 2
     out["speedup_over_fp64_dmma"] = out["fp64_dmma"]["ms_per_gradient"] / out["tcgen05_cta_pair"]["ms_per_gradient"]
     return out
 
