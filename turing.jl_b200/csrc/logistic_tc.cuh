@@ -267,10 +267,11 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *v) {
 // Theta planes (3 x 128 columns) and G (256 columns) of 256 features next to the eta buffers, so CTA h
 // of the pair owns the features [128 h, 128 h + 128): its Theta planes, its X boxes, its G columns --
 // the TMEM layout of the KP = 128 kernel on each SM.  GEMM1 then yields a PARTIAL eta (the sum over this
-// CTA's features); the epilogue threads write their partial to the peer's shared memory (DSMEM,
-// st.shared::cluster), signal the peer's mbarrier (release.cluster), wait for the peer's partial
-// (acquire.cluster) and add the two -- fp addition commutes, so both CTAs hold bit-identical eta and
-// compute identical residuals, which each feeds to GEMM2 for its own half of G.  Only CTA 0 reports lp.
+// CTA's features).  The pair finalises every row tile half by half (epi_tiles_wide): a CTA sends its
+// partial eta of the peer's 32 rows into the peer's shared memory (DSMEM, st.async whose bytes the
+// peer's mbarrier counts -- the mechanism TMA loads use, no fences), adds the peer's partial for its
+// own 32 rows, evaluates their residuals, and sends those R planes to the peer; both CTAs then hold
+// the same R[128 x 64] and feed GEMM2 for their own half of G.  CTA 1 hands its share of lp to CTA 0.
 template <int KP, int STAGES = kStages, bool WIDE = false>
 struct TcCore {
   static_assert(KP == 64 || KP == 128, "feature padding is 64 or 128");
