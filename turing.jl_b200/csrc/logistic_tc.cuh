@@ -112,11 +112,6 @@ __device__ __forceinline__ void st_async_b64(uint32_t raddr, uint32_t rbar, unsi
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
                ::"r"(raddr), "l"(v), "r"(rbar) : "memory");
 }
-// arrival on a barrier of the peer CTA ("I have read my buffer"): orders this thread's earlier reads
-// before it, the form CUTLASS's ClusterBarrier uses for consumer releases across a cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t rbar) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
-}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
